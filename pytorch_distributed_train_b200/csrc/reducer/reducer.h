@@ -1,0 +1,136 @@
+// Gradient reducer: the native half of our DistributedDataParallel.
+//
+// What it has to do is fixed by how the reference uses DDP (ref: ddp_example.py:64,91 →
+// c10d reducer.hpp:45-584): fire as each parameter's gradient is accumulated, pack gradients
+// into flat buckets, launch one collective per bucket as soon as the bucket is complete (in
+// bucket order, overlapped with the rest of backward), and finish at the end of backward.
+// How it does it is ours:
+//   * gradients live *in* the bucket (param.grad is a view) so "flatten" is free; on the
+//     SymmComm backend the bucket is peer-mapped NVLink memory that remote GPUs read directly;
+//   * the 1/world_size scale is folded into the collective (`postscale`) instead of a
+//     per-parameter multiply kernel (the reference path spends 10 tiny kernels on it);
+//   * bucket layout is rebuilt once from the observed grad-ready order, planner in C++.
+#pragma once
+#include <ATen/ATen.h>
+#include <pybind11/pybind11.h>
+#include <torch/csrc/autograd/function.h>
+
+#include <chrono>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <unordered_map>
+#include <vector>
+
+#include "../comm/comm.h"
+#include "bucket_plan.h"
+
+namespace pdt {
+
+namespace py = pybind11;
+
+struct GradBucket {
+  int64_t index;
+  bool is_last;
+  at::Tensor buffer;                    // flat, undivided local gradients
+  std::vector<at::Tensor> gradients;    // views into buffer, one per parameter
+  std::vector<at::Tensor> parameters;
+  std::vector<int64_t> offsets, lengths;
+};
+
+struct ReducerStats {
+  int64_t num_iterations = 0;
+  int64_t num_buckets_reduced = 0;       // lifetime
+  int64_t num_rebuilds = 0;
+  std::vector<int64_t> bucket_sizes_bytes;
+  std::vector<int64_t> grad_ready_order;  // previous iteration
+  std::vector<std::vector<int64_t>> bucket_indices;
+  // host-side wall times of the last sampled iteration, microseconds
+  double forward_us = 0, backward_compute_us = 0, backward_comm_us = 0, backward_total_us = 0;
+  double backward_comm_exposed_us = 0;    // time finalize spent waiting on collectives
+  bool has_rebuilt = false;
+  bool gradient_as_bucket_view = true;
+  bool find_unused_parameters = false;
+  int64_t total_param_bytes = 0;
+  int64_t copies_into_bucket = 0;         // grads that were not already bucket views (lifetime)
+};
+
+class Reducer {
+ public:
+  Reducer(std::vector<at::Tensor> params, std::vector<std::vector<int64_t>> bucket_indices,
+          std::shared_ptr<Comm> comm, int64_t bucket_bytes_cap, int64_t first_bucket_bytes_cap,
+          bool find_unused_parameters, bool gradient_as_bucket_view, bool static_graph);
+  ~Reducer();
+
+  void prepare_for_forward();
+  // Arms the hooks for the coming backward. `outputs` is only inspected when
+  // find_unused_parameters is on.
+  void prepare_for_backward(const std::vector<at::Tensor>& outputs);
+  // no_sync(): when false the hooks are inert and gradients just accumulate locally.
+  void set_require_sync(bool v) { require_sync_ = v; }
+  // Rebuild-once protocol: rank 0 proposes, everybody applies (layout agreed via the store).
+  bool should_rebuild() const;
+  std::vector<std::vector<int64_t>> propose_rebuild() const;
+  void apply_rebuild(const std::vector<std::vector<int64_t>>& bucket_indices);
+  // Python comm hook: hook(bucket: GradBucket) -> Tensor | object-with-wait()->Tensor
+  void register_comm_hook(py::object hook);
+  ReducerStats stats() const;
+  std::vector<at::Tensor> bucket_buffers() const;
+  // True when every parameter's .grad currently aliases its bucket slot.
+  bool grads_are_views() const;
+  // Re-point every param.grad at its bucket view (zeroing the bucket): used by the graph
+  // engine so backward writes land directly in comm-visible memory.
+  void install_grad_views(bool zero);
+  void set_postscale(double s) { postscale_ = s; }
+
+ private:
+  struct Bucket {
+    at::Tensor flat;
+    std::vector<int64_t> params;          // global param indices
+    std::vector<at::Tensor> views;        // same order as params
+    std::vector<int64_t> offsets, lengths;
+    size_t pending = 0;
+    bool launched = false;
+    std::shared_ptr<CommWork> work;
+    py::object py_future;                  // when a comm hook is installed
+    at::Tensor hook_result;
+  };
+  struct Loc { size_t bucket, slot; };
+
+  void build_buckets(const std::vector<std::vector<int64_t>>& bucket_indices);
+  void autograd_hook(size_t index);
+  void mark_variable_ready(size_t index);
+  void launch_ready_buckets();
+  void launch_bucket(size_t b);
+  void finalize_backward();
+  void search_unused(const std::vector<at::Tensor>& outputs);
+
+  std::vector<at::Tensor> params_;
+  std::shared_ptr<Comm> comm_;
+  int64_t bucket_bytes_cap_, first_bucket_bytes_cap_;
+  bool find_unused_, grad_as_view_, static_graph_;
+  bool require_sync_ = true;
+  bool expect_hooks_ = false;
+  bool callback_queued_ = false;
+  bool has_rebuilt_ = false;
+  double postscale_;
+
+  std::vector<Bucket> buckets_;
+  std::vector<Loc> locs_;
+  size_t next_bucket_ = 0;
+  std::vector<char> ready_;               // per param, this iteration
+  std::vector<char> locally_unused_;      // per param, this iteration
+  std::vector<int64_t> ready_order_, prev_ready_order_;
+  std::vector<std::pair<std::shared_ptr<torch::autograd::Node>, uintptr_t>> hooks_;
+  std::unordered_map<torch::autograd::Node*, size_t> acc_to_index_;
+  py::object comm_hook_;
+  bool has_comm_hook_ = false;
+  mutable std::mutex mu_;
+
+  using HClock = std::chrono::steady_clock;
+  HClock::time_point t_forward_start_, t_backward_start_, t_first_launch_, t_last_launch_;
+  bool saw_first_hook_ = false;
+  ReducerStats stats_;
+};
+
+}  // namespace pdt

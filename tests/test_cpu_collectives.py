@@ -1,0 +1,159 @@
+"""CPU backend collectives over our TCP mesh, world sizes 2-4 (BASELINE.json config 1 plumbing)."""
+import pytest
+import torch
+
+import pytorch_distributed_train_b200 as pdt
+from mp_helpers import run_ranks
+
+dist = pdt.distributed
+
+
+def _collectives(rank, world):
+    out = {}
+    # allreduce small / large(ring) / odd sizes / dtypes
+    for n in (1, 7, 1000, 100003):
+        t = torch.arange(n, dtype=torch.float32) * (rank + 1)
+        dist.all_reduce(t)
+        exp = torch.arange(n, dtype=torch.float32) * sum(r + 1 for r in range(world))
+        assert torch.equal(t, exp), f"allreduce n={n}"
+    t = torch.full((5,), float(rank))
+    dist.all_reduce(t, dist.ReduceOp.MAX)
+    assert torch.equal(t, torch.full((5,), float(world - 1)))
+    t = torch.full((5,), float(rank + 1))
+    dist.all_reduce(t, dist.ReduceOp.AVG)
+    assert torch.allclose(t, torch.full((5,), sum(range(1, world + 1)) / world))
+    for dt in (torch.int64, torch.int32, torch.float64, torch.bfloat16, torch.float16, torch.uint8):
+        t = torch.ones(33, dtype=dt) * (rank + 1)
+        dist.all_reduce(t)
+        assert torch.equal(t, torch.ones(33, dtype=dt) * sum(range(1, world + 1))), str(dt)
+    # bitwise identical results on all ranks for a big random vector (ring path)
+    g = torch.Generator().manual_seed(rank)
+    big = torch.randn(300000, generator=g)
+    dist.all_reduce(big)
+    out["big_sum_bits"] = big.view(torch.int32).sum().item()
+    # broadcast from every root
+    for root in range(world):
+        t = torch.arange(10.0) + 100 * root if rank == root else torch.zeros(10)
+        dist.broadcast(t, root)
+        assert torch.equal(t, torch.arange(10.0) + 100 * root)
+    # allgather
+    o = torch.empty(world * 3)
+    dist.all_gather_into_tensor(o, torch.full((3,), float(rank)))
+    assert torch.equal(o, torch.arange(world, dtype=torch.float32).repeat_interleave(3))
+    lst = [torch.empty(2) for _ in range(world)]
+    dist.all_gather(lst, torch.full((2,), float(rank)))
+    assert all(torch.equal(lst[r], torch.full((2,), float(r))) for r in range(world))
+    # reduce / reduce_scatter / gather / scatter / alltoall / send-recv
+    t = torch.ones(4) * (rank + 1)
+    dist.reduce(t, 0)
+    if rank == 0:
+        assert torch.equal(t, torch.ones(4) * sum(range(1, world + 1)))
+    rs = torch.empty(2)
+    dist.reduce_scatter_tensor(rs, torch.arange(2.0 * world) + rank)
+    assert torch.equal(rs, (torch.arange(2.0 * world) * world + sum(range(world)))[2 * rank:2 * rank + 2])
+    gl = [torch.empty(1) for _ in range(world)] if rank == 1 else None
+    dist.gather(torch.tensor([float(rank)]), gl, dst=1)
+    if rank == 1:
+        assert [int(x.item()) for x in gl] == list(range(world))
+    sc = torch.empty(2)
+    dist.scatter(sc, [torch.full((2,), float(r)) for r in range(world)] if rank == 0 else None, src=0)
+    assert torch.equal(sc, torch.full((2,), float(rank)))
+    a2a = torch.empty(world)
+    dist.all_to_all_single(a2a, torch.arange(world, dtype=torch.float32) + 10 * rank)
+    assert torch.equal(a2a, torch.tensor([10.0 * r + rank for r in range(world)]))
+    if rank == 0:
+        dist.send(torch.tensor([42.0]), 1)
+    elif rank == 1:
+        r = torch.empty(1)
+        dist.recv(r, 0)
+        assert r.item() == 42.0
+    dist.barrier()
+    w = dist.all_reduce(torch.ones(3), async_op=True)
+    assert w.wait() is True
+    objs = dist.all_gather_object({"r": rank})
+    assert [o["r"] for o in objs] == list(range(world))
+    assert dist.broadcast_object("hello" if rank == 0 else None, 0) == "hello"
+    out["rank"], out["world"], out["backend"] = dist.get_rank(), dist.get_world_size(), dist.get_backend()
+    out["records"] = len(dist.get_default_group().comm.flight_records())
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_collectives(world):
+    res = run_ranks(_collectives, world)
+    assert [r["rank"] for r in res] == list(range(world))
+    assert all(r["world"] == world and r["backend"] == "gloo" for r in res)
+    assert len({r["big_sum_bits"] for r in res}) == 1, "allreduce must be bitwise identical across ranks"
+    assert all(r["records"] > 0 for r in res)
+
+
+def _subgroups(rank, world):
+    g = dist.new_group([0, 2])
+    t = torch.ones(2) * (rank + 1)
+    if g is not None:
+        dist.all_reduce(t, group=g)
+        assert torch.equal(t, torch.ones(2) * 4) and g.size() == 2
+    else:
+        assert rank == 1
+    dist.monitored_barrier()
+    return True
+
+
+def test_new_group():
+    assert all(run_ranks(_subgroups, 3))
+
+
+def _double_init(rank, world):
+    try:
+        pdt.init_process_group("gloo", init_method="tcp://127.0.0.1:1", world_size=1, rank=0)
+    except RuntimeError as e:
+        return "twice" in str(e)
+    return False
+
+
+def test_double_init_is_an_error():
+    assert all(run_ranks(_double_init, 2))
+
+
+def _dead_peer(rank, world):
+    import os
+    import time
+
+    if rank == 1:
+        os._exit(7)  # dies before joining the collective
+    t = torch.ones(4)
+    t0 = time.time()
+    try:
+        dist.all_reduce(t)
+    except Exception as e:  # PeerClosedError / TimeoutError
+        return ("err", type(e).__name__, time.time() - t0)
+    return ("no-error",)
+
+
+def test_dead_rank_fails_fast_instead_of_hanging():
+    from pytorch_distributed_train_b200 import launcher
+
+    with pytest.raises((launcher.ProcessExitedException, launcher.ProcessRaisedException)):
+        run_ranks(_dead_peer, 2, grace_period=2.0)
+
+
+def test_single_process_env_rendezvous(monkeypatch):
+    from mp_helpers import free_port
+
+    monkeypatch.setenv("MASTER_ADDR", "127.0.0.1")
+    monkeypatch.setenv("MASTER_PORT", str(free_port()))
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    pdt.init_process_group("gloo")
+    try:
+        t = torch.ones(3)
+        dist.all_reduce(t)
+        assert torch.equal(t, torch.ones(3)) and dist.get_world_size() == 1
+    finally:
+        pdt.destroy_process_group()
+    assert not dist.is_initialized()
+
+
+def test_file_rendezvous(tmp_path):
+    pdt.init_process_group("gloo", init_method=f"file://{tmp_path}/rdzv", world_size=1, rank=0)
+    pdt.destroy_process_group()

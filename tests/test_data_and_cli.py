@@ -1,0 +1,88 @@
+"""MNIST idx parser, DataLoader paths, CLI flag parity and an end-to-end 2-process CPU run
+(ref: ddp_example.py:66-78,101-111; README.md:97-103)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import pytorch_distributed_train_b200 as pdt
+from pytorch_distributed_train_b200 import cli
+from pytorch_distributed_train_b200.data import (MNIST, DataLoader, DistributedSampler, SyntheticMNIST, TensorDataset,
+                                                 read_idx, synthesize_mnist_files, write_idx)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_idx_roundtrip_and_mnist(tmp_path):
+    t = (torch.arange(2 * 28 * 28) % 251).to(torch.uint8).view(2, 28, 28)
+    write_idx(str(tmp_path / "x-idx3-ubyte"), t)
+    assert torch.equal(read_idx(str(tmp_path / "x-idx3-ubyte")), t)
+    with pytest.raises(RuntimeError, match="never touches the network"):
+        MNIST(str(tmp_path / "none"), download=True)
+    synthesize_mnist_files(str(tmp_path), n=300)
+    ds = MNIST(str(tmp_path), train=True, download=True)
+    assert len(ds) == 300
+    img, y = ds[5]
+    assert img.shape == (1, 28, 28) and img.dtype == torch.float32 and 0 <= img.min() and img.max() <= 1 and isinstance(y, int)
+    xb, yb = ds.gather([5, 7])
+    assert torch.equal(xb[0], img) and yb.dtype == torch.int64 and xb.shape == (2, 1, 28, 28)
+
+
+def test_torchvision_reads_our_synthetic_files(tmp_path):
+    tv = pytest.importorskip("torchvision")
+    synthesize_mnist_files(str(tmp_path), n=64)
+    synthesize_mnist_files(str(tmp_path), n=16, train=False)  # torchvision checks all four files
+    ours = MNIST(str(tmp_path))
+    theirs = tv.datasets.MNIST(str(tmp_path), train=True, transform=tv.transforms.ToTensor(), download=False)
+    assert len(theirs) == 64
+    a, la = ours[3]
+    b, lb = theirs[3]
+    assert torch.allclose(a, b) and la == lb
+
+
+def test_dataloader_gather_equals_per_sample_collate():
+    ds = SyntheticMNIST(250, seed=1)
+
+    class Slow:  # same data without the batched fast path
+        def __len__(self):
+            return len(ds)
+
+        def __getitem__(self, i):
+            return ds[i]
+
+    s = DistributedSampler(ds, 2, 1, shuffle=True, seed=5)
+    fast = list(DataLoader(ds, batch_size=100, sampler=s))
+    slow = list(DataLoader(Slow(), batch_size=100, sampler=s))
+    assert len(fast) == len(slow) == 2  # 125 samples → 100 + 25
+    for (xa, ya), (xb, yb) in zip(fast, slow):
+        assert torch.equal(xa, xb) and torch.equal(ya, yb)
+    assert fast[-1][0].shape[0] == 25
+    pre = list(DataLoader(ds, batch_size=100, sampler=s, prefetch=2))
+    assert all(torch.equal(a[0], b[0]) for a, b in zip(pre, fast))
+    assert len(list(DataLoader(ds, batch_size=100, drop_last=True))) == 2
+    td = TensorDataset(torch.arange(10.0), torch.arange(10))
+    assert torch.equal(next(iter(DataLoader(td, batch_size=4)))[1], torch.arange(4))
+
+
+def test_cli_flags_match_reference():
+    p = cli.build_parser()
+    a = p.parse_args([])
+    # ref: ddp_example.py:103-106
+    assert (a.gpus, a.epochs, a.backend, a.syncbn) == (1, 2, "nccl", False)
+    b = p.parse_args(["-g", "4", "--epochs", "3", "--backend", "gloo", "--syncbn"])
+    assert (b.gpus, b.epochs, b.backend, b.syncbn) == (4, 3, "gloo", True)
+    assert a.batch_size == 100 and a.lr == 1e-4  # ref: ddp_example.py:59,62
+
+
+def test_train_script_two_cpu_ranks():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "train_mnist.py"), "-g", "2", "--backend", "gloo",
+                          "--epochs", "1", "--steps", "20", "--samples", "4000", "--syncbn"],
+                         capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    so = out.stdout
+    assert "Rank id:  0" in so and "Rank id:  1" in so          # ref: ddp_example.py:49
+    assert "Use SyncBN in training" in so                      # ref: ddp_example.py:56
+    assert "Epoch [1/1], Step [10/20], Loss:" in so and "Epoch [1/1], Step [20/20], Loss:" in so  # ref: :94
+    assert "Training complete in: " in so                      # ref: ddp_example.py:97
