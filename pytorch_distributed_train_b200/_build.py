@@ -28,6 +28,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 BUILD = PKG.parent / "build" / "pdt_obj"
 OUT = PKG / "_C.so"
+STAMP = PKG / "_C.stamp"
 
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
@@ -87,7 +88,7 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
     cxx_flags = ["-O2", "-g0", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wno-unused-function",
                  "-D_GLIBCXX_USE_CXX11_ABI=1", "-DTORCH_EXTENSION_NAME=_C", "-DTORCH_API_INCLUDE_EXTENSION_H",
                  "-DPDT_WITH_CUDA=1"]
-    nvcc_flags = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
+    nvcc_flags = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC",
                   "-Xcompiler", "-fvisibility=hidden", "--threads", "2", "-DPDT_WITH_CUDA=1"] + ARCH_FLAGS
     if ptxas_info:
         nvcc_flags += ["-Xptxas", "-v"]
@@ -100,11 +101,20 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
     for src in cu:
         jobs.append((src, [NVCC, "-c", str(src)] + nvcc_flags + common_inc))
 
-    objs, todo = [], []
+    objs, todo, keys = [], [], []
     for src, cmd in jobs:
         key = hashlib.sha256((src.read_text() + "\0" + " ".join(cmd) + "\0" + hdr).encode()).hexdigest()[:20]
+        keys.append(key)
         obj = BUILD / f"{src.relative_to(CSRC).as_posix().replace('/', '__')}.{key}.o"
         objs.append(obj)
+    # The stamp travels with the .so (gpurun snapshot), so a box that has the library but not the
+    # object cache does not rebuild.
+    stamp = hashlib.sha256("".join(keys).encode()).hexdigest()
+    if not force and OUT.exists() and STAMP.exists() and STAMP.read_text().strip() == stamp:
+        if verbose:
+            print(f"[pdt build] {OUT} up to date")
+        return OUT
+    for (src, cmd), obj in zip(jobs, objs):
         if force or not obj.exists():
             todo.append((src, cmd + ["-o", str(obj)], obj))
 
@@ -136,6 +146,7 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
                  f"-L{CUDA_HOME}/lib64", "-lcudart_static", "-lrt", "-ldl", "-lpthread"] + rpaths)
         _run(link, "link _C.so")
         os.replace(str(OUT) + ".tmp", OUT)
+    STAMP.write_text(stamp)
     if verbose:
         print(f"[pdt build] {OUT} ready ({len(todo)}/{len(jobs)} TUs rebuilt, {time.time() - t0:.1f}s)")
     return OUT

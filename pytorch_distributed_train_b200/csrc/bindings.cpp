@@ -179,6 +179,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("apply_rebuild", &Reducer::apply_rebuild)
       .def("register_comm_hook", &Reducer::register_comm_hook)
       .def("bucket_buffers", &Reducer::bucket_buffers)
+      .def("grad_views", &Reducer::grad_views)
       .def("grads_are_views", &Reducer::grads_are_views)
       .def("install_grad_views", &Reducer::install_grad_views, py::arg("zero") = true)
       .def("set_postscale", &Reducer::set_postscale)

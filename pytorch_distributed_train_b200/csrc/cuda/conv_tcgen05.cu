@@ -1,0 +1,600 @@
+// tcgen05 / TMEM / TMA kernels for sm_100a (hand-written PTX; no CUTLASS).
+//
+//  * gemm_tf32_umma_kernel — D[M,N] = A[M,K]·B[N,K]^T: both operands arrive by TMA
+//    (cp.async.bulk.tensor, SWIZZLE_128B), one elected thread issues tcgen05.mma.kind::tf32,
+//    the fp32 accumulator lives in TMEM and is read back with tcgen05.ld.  It is the self-test
+//    for every descriptor/barrier convention used below (tests/test_gpu_ops.py).
+//  * conv5x5_umma_kernel — the ConvNet's conv2 (88% of the model's FLOPs; ref:
+//    ddp_example.py:30) and its data gradient as an implicit GEMM: M = output pixels (128 per
+//    tile), N = output channels, K = 25 taps × input channels.  The im2col A-tile is never
+//    materialised in global memory: four producer warps gather it straight from the NHWC
+//    activation with 16-byte cp.async (zero-fill for the padding halo) into the 128B-swizzled
+//    K-major layout the UMMA descriptor expects; the repacked weights (B) are TMA-loaded once
+//    per CTA and stay resident in smem; the epilogue adds the bias, folds the per-channel
+//    Σy/Σy² that BatchNorm needs (saving a full re-read of y) and writes the tile with a TMA
+//    store.  TF32 inputs / fp32 accumulate is the same numerics contract the reference gets from
+//    cuDNN (torch allows TF32 in convolutions by default).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "conv_tcgen05.h"
+#include "cuda_utils.h"
+
+namespace pdt {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// TMA
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// Ampere-style async copy with zero fill (src_bytes = 0 → 16 zero bytes)
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// TMEM
+template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+//   start address >> 4 | LBO (ignored for swizzled K-major, set to 1) << 16 | SBO = 1024 B (8 rows × 128 B) >> 4 << 32
+//   | version 1 << 46 | layout SWIZZLE_128B (2) << 61.       [cf. cute/arch/mma_sm100_desc.hpp]
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=TF32 (2 at bits 7-9 / 10-12), both K-major,
+// N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 32;            // fp32 elements per 128-byte swizzle row
+constexpr int kStageBytes = kTileM * 128;
+
+// =====================================================================================================
+// TF32 GEMM self-test:  one CTA per 128-row tile of D; 4-stage TMA ring; 128 threads
+// =====================================================================================================
+template <int NT>  // N tile = whole N, multiple of 16, <= 256; TMEM columns = next pow2 >= 32
+struct GemmCfg {
+  static constexpr int kStages = 4;
+  static constexpr int kTmemCols = NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256;
+  static constexpr int kBBytes = NT * 128;
+  static constexpr size_t kSmem = 1024 + kStages * (kStageBytes + kBBytes) + 256;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(128, 1) gemm_tf32_umma_kernel(const __grid_constant__ CUtensorMap tm_a,
+                                                                const __grid_constant__ CUtensorMap tm_b, float* __restrict__ d, int M,
+                                                                int N, int K) {
+  using Cfg = GemmCfg<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + Cfg::kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb + Cfg::kStages * Cfg::kBBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* accum_full = bars + 2 * Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * kTileM;
+  const int nk = (K + kChunkK - 1) / kChunkK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % Cfg::kStages;
+        mbar_wait(&empty[s], ((kc / Cfg::kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], kStageBytes + Cfg::kBBytes);
+        tma_load_2d(sa + s * kStageBytes, &tm_a, &full[s], kc * kChunkK, m0);
+        tma_load_2d(sb + s * Cfg::kBBytes, &tm_b, &full[s], kc * kChunkK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_tf32(kTileM, NT);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % Cfg::kStages;
+      mbar_wait(&full[s], (kc / Cfg::kStages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a0 = smem_u32(sa + s * kStageBytes), b0 = smem_u32(sb + s * Cfg::kBBytes);
+#pragma unroll
+        for (int k = 0; k < kChunkK / 8; ++k)
+          umma_tf32(tmem_base, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kc | k) != 0);
+        umma_commit(&empty[s]);
+        if (kc == nk - 1) umma_commit(accum_full);
+      }
+      __syncwarp();
+    }
+  }
+  // epilogue: all four warps, warp w owns TMEM lanes 32w..32w+31 = D rows m0+32w+lane
+  mbar_wait(accum_full, 0);
+  __syncwarp();  // tcgen05.ld is .sync.aligned: the elected producer/MMA lane must have rejoined
+  tc_fence_after();
+  const int row = m0 + warp * 32 + (threadIdx.x & 31);
+#pragma unroll 1
+  for (int c0 = 0; c0 < NT; c0 += 16) {
+    float v[16];
+    tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    if (row < M) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        if (c0 + j < N) *reinterpret_cast<float4*>(d + static_cast<size_t>(row) * N + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// =====================================================================================================
+// Weight repack for the implicit GEMM:  Bm[NOUT][NCHUNK*32], K index = tap*CK + c  (zero padded)
+//   FWD : Bm[co][tap*16+ci] = w[co][ci][tap]
+//   DGRAD: Bm[ci][tap*32+co] = w[co][ci][24-tap]
+// =====================================================================================================
+template <bool FWD>
+__global__ void repack_weights_kernel(const float* __restrict__ w, float* __restrict__ bm, int Cout, int Cin) {
+  const int CK = FWD ? Cin : Cout, NOUT = FWD ? Cout : Cin;
+  const int tpc = kChunkK / CK, nchunk = (25 + tpc - 1) / tpc, kpad = nchunk * kChunkK;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NOUT * kpad) return;
+  const int n = i / kpad, k = i % kpad, tap = k / CK, c = k % CK;
+  float v = 0.f;
+  if (tap < 25) v = FWD ? w[(n * Cin + c) * 25 + tap] : w[(c * Cin + n) * 25 + (24 - tap)];
+  bm[i] = v;
+}
+
+// =====================================================================================================
+// Implicit-GEMM 5x5 convolution on tcgen05
+// =====================================================================================================
+template <int CK, int NOUT>
+struct ConvCfg {
+  static constexpr int kTapsPerChunk = kChunkK / CK;                           // 2 (fwd) / 1 (dgrad)
+  static constexpr int kChunks = (25 + kTapsPerChunk - 1) / kTapsPerChunk;     // 13 / 25
+  static constexpr int kStages = 4;
+  static constexpr int kLag = kStages - 1;
+  static constexpr int kBChunkBytes = NOUT * 128;
+  static constexpr int kTmemCols = 32;
+  static constexpr int kThreads = 192;                                         // 4 producer/epilogue warps + MMA warp + TMA warp
+  static constexpr size_t kSmem = 1024 + kStages * kStageBytes + kChunks * kBChunkBytes + kTileM * 128 + 1024;
+};
+
+template <int CK, int NOUT, bool FWD>
+__global__ void __launch_bounds__(192, 1) conv5x5_umma_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap tm_b,
+                                                              const __grid_constant__ CUtensorMap tm_y, const float* __restrict__ bias,
+                                                              float* __restrict__ y, float* stats, ReduceScratch scr, int B, int H, int W,
+                                                              int num_tiles) {
+  using Cfg = ConvCfg<CK, NOUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                                                  // [stages][128 rows][128 B] swizzled
+  uint8_t* sb = sa + Cfg::kStages * kStageBytes;                       // [chunks][NOUT rows][128 B] swizzled (TMA)
+  uint8_t* sy = sb + Cfg::kChunks * Cfg::kBChunkBytes;                 // [128 rows][128 B] swizzled output staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sy + kTileM * 128);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* b_full = bars + 2 * Cfg::kStages;
+  uint64_t* acc_full = b_full + 1;
+  uint64_t* acc_empty = b_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 3);
+  float* s_part = reinterpret_cast<float*>(tmem_slot + 2);             // [4 warps][2*NOUT] + [2*NOUT]
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = B * H * W;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_b);
+    if (FWD) tma_prefetch_desc(&tm_y);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    mbar_init(b_full, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    // ---- weights: one TMA box per K-chunk, resident for the CTA's lifetime -------------------------
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_full, Cfg::kChunks * Cfg::kBChunkBytes);
+      for (int c = 0; c < Cfg::kChunks; ++c) tma_load_2d(sb + c * Cfg::kBChunkBytes, &tm_b, b_full, c * kChunkK, 0);
+    }
+  } else if (warp == 4) {
+    // ---- MMA issuer ------------------------------------------------------------------------------------
+    constexpr uint32_t idesc = umma_idesc_tf32(kTileM, NOUT);
+    mbar_wait(b_full, 0);
+    int g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      mbar_wait(acc_empty, (it & 1) ^ 1);  // epilogue has drained the accumulator of the previous tile
+      tc_fence_after();
+      for (int c = 0; c < Cfg::kChunks; ++c, ++g) {
+        const int s = g % Cfg::kStages;
+        mbar_wait(&full[s], (g / Cfg::kStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = smem_u32(sa + s * kStageBytes), b0 = smem_u32(sb + c * Cfg::kBChunkBytes);
+#pragma unroll
+          for (int k = 0; k < kChunkK / 8; ++k)
+            umma_tf32(tmem_base, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (c | k) != 0);
+          umma_commit(&empty[s]);                       // smem stage may be refilled once these MMAs retire
+          if (c == Cfg::kChunks - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- warps 0-3: im2col producers, then epilogue ----------------------------------------------------
+    const int u = tid & 7;                       // 16-byte column inside the 128-byte K row
+    const int tap_in_chunk = (u * 4) / CK;       // which tap of the chunk this column belongs to
+    const int c4 = (u * 4) % CK;                 // channel offset inside the tap
+    int g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      // the 8 rows this thread fills: r = tid/8 + 16 j
+      int row_off[8], row_h[8], row_w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = (tid >> 3) + 16 * j;
+        const int p = tile * kTileM + r;
+        if (p < M) {
+          const int ow = p % W, oh = (p / W) % H, n = p / (W * H);
+          row_off[j] = ((n * H + oh) * W + ow) * CK;
+          row_h[j] = oh;
+          row_w[j] = ow;
+        } else {
+          row_off[j] = 0;
+          row_h[j] = -100000;  // every tap falls outside → zero fill
+          row_w[j] = 0;
+        }
+      }
+      for (int c = 0; c < Cfg::kChunks; ++c, ++g) {
+        const int s = g % Cfg::kStages;
+        mbar_wait(&empty[s], ((g / Cfg::kStages) & 1) ^ 1);
+        const int tap = c * Cfg::kTapsPerChunk + tap_in_chunk;
+        const int kh = tap / 5 - 2, kw = tap % 5 - 2;
+        const int delta = (kh * W + kw) * CK + c4;
+        const uint32_t stage = smem_u32(sa + s * kStageBytes);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = (tid >> 3) + 16 * j;
+          const int ih = row_h[j] + kh, iw = row_w[j] + kw;
+          const bool ok = tap < 25 && ih >= 0 && ih < H && iw >= 0 && iw < W;
+          const float* src = ok ? x + row_off[j] + delta : x;
+          cp_async_16(stage + r * 128 + ((u ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (c >= Cfg::kLag) {
+          cp_async_wait<Cfg::kLag>();            // chunk c-kLag of this thread has landed
+          fence_proxy_async_smem();              // generic-proxy writes → visible to the tensor core (async proxy)
+          mbar_arrive(&full[(g - Cfg::kLag) % Cfg::kStages]);
+        }
+      }
+      // drain this tile (its accumulator is needed now): signal the kLag chunks still in flight;
+      // the lag bookkeeping restarts with the next tile
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+#pragma unroll
+      for (int q = Cfg::kLag; q >= 1; --q) mbar_arrive(&full[(g - q) % Cfg::kStages]);
+      // ---- epilogue ----------------------------------------------------------------------------------
+      mbar_wait(acc_full, it & 1);
+      __syncwarp();
+      tc_fence_after();
+      float v[NOUT];
+#pragma unroll
+      for (int c0 = 0; c0 < NOUT; c0 += 16) {
+        float t[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c0 + j] = t[j];
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+      const int r = tid;  // 0..127 = tile row = TMEM lane
+      const int p = tile * kTileM + r;
+      const bool valid = p < M;
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) v[j] += bias[j];
+      }
+      if constexpr (FWD) {
+        // stage the tile (swizzled like the tensor map) for the TMA store and the column sums
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's TMA store has finished reading sy
+#pragma unroll
+        for (int q = 0; q < NOUT / 4; ++q) {
+          float4 o = valid ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(sy + r * 128 + ((q ^ (r & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) {
+          tma_store_2d(&tm_y, sy, 0, tile * kTileM);
+          tma_store_commit();
+        }
+        if (stats) {
+          // column sums over this warp's 32 rows: lane = channel
+          float s1 = 0.f, s2 = 0.f;
+          const int q = lane >> 2, e = lane & 3;
+          for (int rr = warp * 32; rr < warp * 32 + 32; ++rr) {
+            const float val = reinterpret_cast<const float*>(sy + rr * 128 + ((q ^ (rr & 7)) << 4))[e];
+            s1 += val;
+            s2 += val * val;
+          }
+          s_part[warp * 2 * NOUT + lane] = s1;
+          s_part[warp * 2 * NOUT + NOUT + lane] = s2;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (tid < 2 * NOUT) {
+            const float tot = s_part[tid] + s_part[2 * NOUT + tid] + s_part[4 * NOUT + tid] + s_part[6 * NOUT + tid];
+            scr.partials[static_cast<size_t>(tile) * 2 * NOUT + tid] = tot;
+          }
+          __threadfence();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (tid == 0) s_last = (atomicAdd(scr.counter, 1u) == static_cast<unsigned>(num_tiles - 1));
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (s_last) {
+            __threadfence();
+            if (tid < 2 * NOUT) {
+              float tot = 0.f;
+              for (int tl = 0; tl < num_tiles; ++tl) tot += __ldcg(&scr.partials[static_cast<size_t>(tl) * 2 * NOUT + tid]);
+              stats[tid] = tot;
+              if (tid == 0) {
+                stats[2 * NOUT] = static_cast<float>(M);
+                *scr.counter = 0u;
+              }
+            }
+          }
+        }
+        if (tid == 0) tma_store_wait_read();
+      } else {
+        if (valid) {
+          float* o = y + static_cast<size_t>(p) * NOUT;
+#pragma unroll
+          for (int q = 0; q < NOUT / 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+CUtensorMap make_tmap_2d(const float* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = driver().cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + cu_error(r));
+  return m;
+}
+
+void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("launch of ") + what + " failed: " + cudaGetErrorString(e));
+  count_kernel_launch();
+}
+
+template <typename K>
+void opt_in_smem(K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e));
+}
+
+// repacked-weight buffers, one per (device, direction); allocated on first use (outside graph capture)
+float* repack_buffer(int dir, size_t floats) {
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, std::pair<float*, size_t>> bufs;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  auto& slot = bufs[{dev, dir}];
+  if (slot.second < floats) {
+    if (slot.first) cudaFree(slot.first);
+    cudaError_t e = cudaMalloc(&slot.first, floats * sizeof(float));
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaMalloc(repack buffer): ") + cudaGetErrorString(e));
+    slot.second = floats;
+  }
+  return slot.first;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace
+
+bool conv_tcgen05_supported(const ConvShape& s) { return s.Cin == 16 && s.Cout == 32; }
+
+void launch_conv5x5_fwd_tcgen05(const float* x, const float* w, const float* bias, float* y, float* stats, ConvShape s, ReduceScratch scr,
+                                cudaStream_t st) {
+  if (!conv_tcgen05_supported(s)) throw std::invalid_argument("conv5x5 tcgen05: only 16→32 channels are implemented");
+  using Cfg = ConvCfg<16, 32>;
+  const int M = s.B * s.H * s.W;
+  const int tiles = (M + kTileM - 1) / kTileM;
+  if (stats && static_cast<long long>(tiles) * 64 > scr.capacity_floats) throw std::invalid_argument("conv5x5 tcgen05: scratch too small");
+  const int kpad = Cfg::kChunks * kChunkK;
+  float* bm = repack_buffer(0, static_cast<size_t>(32) * kpad);
+  repack_weights_kernel<true><<<(32 * kpad + 255) / 256, 256, 0, st>>>(w, bm, 32, 16);
+  check_launch("repack_weights(fwd)");
+  CUtensorMap tm_b = make_tmap_2d(bm, kpad, 32, kChunkK, 32);
+  CUtensorMap tm_y = make_tmap_2d(y, 32, static_cast<uint64_t>(M), 32, kTileM);
+  auto kern = conv5x5_umma_kernel<16, 32, true>;
+  opt_in_smem(kern, Cfg::kSmem);
+  const int grid = std::min(tiles, sm_count());
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(x, tm_b, tm_y, bias, y, stats, scr, s.B, s.H, s.W, tiles);
+  check_launch("conv5x5_umma(fwd)");
+}
+
+void launch_conv5x5_dgrad_tcgen05(const float* dy, const float* w, float* dx, ConvShape s, cudaStream_t st) {
+  if (!conv_tcgen05_supported(s)) throw std::invalid_argument("conv5x5 tcgen05 dgrad: only 16→32 channels are implemented");
+  using Cfg = ConvCfg<32, 16>;
+  const int M = s.B * s.H * s.W;
+  const int tiles = (M + kTileM - 1) / kTileM;
+  const int kpad = Cfg::kChunks * kChunkK;
+  float* bm = repack_buffer(1, static_cast<size_t>(16) * kpad);
+  repack_weights_kernel<false><<<(16 * kpad + 255) / 256, 256, 0, st>>>(w, bm, 32, 16);
+  check_launch("repack_weights(dgrad)");
+  CUtensorMap tm_b = make_tmap_2d(bm, kpad, 16, kChunkK, 16);
+  auto kern = conv5x5_umma_kernel<32, 16, false>;
+  opt_in_smem(kern, Cfg::kSmem);
+  const int grid = std::min(tiles, sm_count());
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(dy, tm_b, tm_b, nullptr, dx, nullptr, ReduceScratch{}, s.B, s.H, s.W, tiles);
+  check_launch("conv5x5_umma(dgrad)");
+}
+
+void launch_gemm_tf32_tcgen05(const float* a, const float* b, float* d, int M, int N, int K, cudaStream_t st) {
+  if (N % 16 != 0 || N < 16 || N > 256) throw std::invalid_argument("gemm_tf32_tcgen05: N must be a multiple of 16 in [16, 256]");
+  if (K % 4 != 0 || K < 4) throw std::invalid_argument("gemm_tf32_tcgen05: K must be a positive multiple of 4 (16-byte rows for TMA)");
+  CUtensorMap tm_a = make_tmap_2d(a, static_cast<uint64_t>(K), static_cast<uint64_t>(M), kChunkK, kTileM);
+  const int grid = (M + kTileM - 1) / kTileM;
+#define PDT_GEMM_CASE(NT)                                                                    \
+  if (N <= NT) {                                                                             \
+    CUtensorMap tm_b = make_tmap_2d(b, static_cast<uint64_t>(K), static_cast<uint64_t>(N), kChunkK, NT); \
+    auto kern = gemm_tf32_umma_kernel<NT>;                                                   \
+    opt_in_smem(kern, GemmCfg<NT>::kSmem);                                                   \
+    kern<<<grid, 128, GemmCfg<NT>::kSmem, st>>>(tm_a, tm_b, d, M, N, K);                     \
+    check_launch("gemm_tf32_umma");                                                          \
+    return;                                                                                  \
+  }
+  PDT_GEMM_CASE(16)
+  PDT_GEMM_CASE(32)
+  PDT_GEMM_CASE(64)
+  PDT_GEMM_CASE(128)
+  PDT_GEMM_CASE(256)
+#undef PDT_GEMM_CASE
+}
+
+}  // namespace pdt

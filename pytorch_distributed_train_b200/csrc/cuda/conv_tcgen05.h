@@ -1,0 +1,21 @@
+// tcgen05/TMEM/TMA kernels (sm_100a): TF32 GEMM self-test and the implicit-GEMM 5x5 convolution.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ops_kernels.h"
+
+namespace pdt {
+
+// True for the shapes the tensor-core convolution handles (the ConvNet's conv2: 16→32 channels).
+bool conv_tcgen05_supported(const ConvShape& s);
+
+// y NHWC [B,H,W,32] = conv5x5(x NHWC [B,H,W,16], w [32,16,5,5]) + bias; stats as in launch_conv5x5_fwd.
+void launch_conv5x5_fwd_tcgen05(const float* x, const float* w, const float* bias, float* y, float* stats, ConvShape s,
+                                ReduceScratch scr, cudaStream_t st);
+// dx NHWC [B,H,W,16] = conv_transpose(dy NHWC [B,H,W,32], w [32,16,5,5])
+void launch_conv5x5_dgrad_tcgen05(const float* dy, const float* w, float* dx, ConvShape s, cudaStream_t st);
+
+// D[M,N] = A[M,K] · B[N,K]^T, fp32 in/out, TF32 tensor-core math (K % 4 == 0, N % 16 == 0, N <= 256).
+void launch_gemm_tf32_tcgen05(const float* a, const float* b, float* d, int M, int N, int K, cudaStream_t st);
+
+}  // namespace pdt

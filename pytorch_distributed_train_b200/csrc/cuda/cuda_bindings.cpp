@@ -1,10 +1,317 @@
-// CUDA-side bindings (symmetric memory, NVLink collectives, NCCL baseline, sm_100a ops).
+// CUDA-side bindings: GPU communicators and the sm_100a operator library.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <pybind11/stl.h>
 #include <torch/extension.h>
+
+#include <map>
+#include <mutex>
+
+#include "conv_tcgen05.h"
+#include "cuda_comm.h"
+#include "cuda_utils.h"
+#include "ops_kernels.h"
 
 namespace py = pybind11;
 
 namespace pdt {
-void register_cuda_bindings(py::module_& m) {
-  (void)m;
+
+namespace {
+
+using NoGil = py::call_guard<py::gil_scoped_release>;
+
+cudaStream_t cur_stream(const at::Tensor& t) { return c10::cuda::getCurrentCUDAStream(t.device().index()).stream(); }
+
+void chk(const at::Tensor& t, const char* name, at::ScalarType dt = at::kFloat) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == dt, name, " must have dtype ", c10::toString(dt), " (got ", c10::toString(t.scalar_type()), ")");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
 }
+
+const float* opt_ptr(const c10::optional<at::Tensor>& t, const char* name) {
+  if (!t.has_value() || !t->defined()) return nullptr;
+  chk(*t, name);
+  return t->data_ptr<float>();
+}
+float* opt_mut(c10::optional<at::Tensor>& t, const char* name) {
+  if (!t.has_value() || !t->defined()) return nullptr;
+  chk(*t, name);
+  return t->data_ptr<float>();
+}
+
+// Per-device scratch for deterministic cross-CTA reductions. Kernels that use it run on one
+// stream at a time (the compute stream), which is what serialises access.
+struct Scratch {
+  at::Tensor partials, counter;
+};
+ReduceScratch scratch(const at::Tensor& like) {
+  static std::mutex mu;
+  static std::map<int, Scratch> per_dev;
+  std::lock_guard<std::mutex> g(mu);
+  const int dev = like.device().index();
+  auto it = per_dev.find(dev);
+  if (it == per_dev.end()) {
+    Scratch s;
+    const int64_t cap = 4 << 20;  // 4 Mi floats = 16 MiB
+    s.partials = at::empty({cap}, like.options().dtype(at::kFloat));
+    s.counter = at::zeros({4}, like.options().dtype(at::kInt));
+    it = per_dev.emplace(dev, std::move(s)).first;
+  }
+  ReduceScratch r;
+  r.partials = it->second.partials.data_ptr<float>();
+  r.counter = reinterpret_cast<unsigned int*>(it->second.counter.data_ptr<int>());
+  r.capacity_floats = static_cast<int>(it->second.partials.numel());
+  return r;
+}
+
+ConvShape conv_shape(const at::Tensor& x_nhwc, const at::Tensor& w) {
+  TORCH_CHECK(x_nhwc.dim() == 4 && w.dim() == 4 && w.size(2) == 5 && w.size(3) == 5, "conv5x5: x [B,H,W,Cin] and w [Cout,Cin,5,5] expected");
+  ConvShape s;
+  s.B = static_cast<int>(x_nhwc.size(0));
+  s.H = static_cast<int>(x_nhwc.size(1));
+  s.W = static_cast<int>(x_nhwc.size(2));
+  s.Cin = static_cast<int>(w.size(1));
+  s.Cout = static_cast<int>(w.size(0));
+  return s;
+}
+
+}  // namespace
+
+void register_cuda_bindings(py::module_& m) {
+  m.attr("ops_ready") = true;
+  m.def("kernel_launch_count", [] { return kernel_launch_count(); },
+        "number of kernels this library has launched (or recorded into CUDA graphs) so far");
+  m.def("nccl_available", [] { return NcclComm::available(); });
+  m.def("nccl_version", [] { return NcclComm::version(); });
+
+  py::class_<SymmComm, Comm, std::shared_ptr<SymmComm>>(m, "SymmComm")
+      .def(py::init([](std::shared_ptr<Store> store, int rank, int size, int device, double timeout_s, int64_t heap_bytes) {
+             py::gil_scoped_release r;
+             return std::make_shared<SymmComm>(std::move(store), rank, size, device, Millis(static_cast<int64_t>(timeout_s * 1000)),
+                                               static_cast<size_t>(heap_bytes));
+           }),
+           py::arg("store"), py::arg("rank"), py::arg("size"), py::arg("device"), py::arg("timeout") = 600.0,
+           py::arg("heap_bytes") = int64_t(1) << 30)
+      .def("allreduce_inline", &SymmComm::allreduce_inline, py::arg("tensor"), py::arg("op") = ReduceOp::SUM, py::arg("postscale") = 1.0)
+      .def("allreduce_sgd_inline", &SymmComm::allreduce_sgd_inline, py::arg("grad"), py::arg("param"), py::arg("momentum_buf") = py::none(),
+           py::arg("lr") = 0.0, py::arg("lr_tensor") = py::none(), py::arg("momentum") = 0.0, py::arg("dampening") = 0.0,
+           py::arg("weight_decay") = 0.0, py::arg("nesterov") = false, py::arg("first_step") = false)
+      .def_property_readonly("has_multicast", &SymmComm::has_multicast)
+      .def_property("algo", &SymmComm::algo, &SymmComm::set_algo)
+      .def("set_oneshot_max_bytes", &SymmComm::set_oneshot_max_bytes)
+      .def("set_launch", &SymmComm::set_launch, py::arg("blocks") = 0, py::arg("threads") = 0)
+      .def("describe", &SymmComm::describe)
+      .def("status", &SymmComm::status)
+      .def("heap_bytes_in_use", [](SymmComm& c) { return c.heap().user_bytes_in_use(); })
+      .def("is_symmetric", [](SymmComm& c, const at::Tensor& t) { return c.heap().contains(t.data_ptr(), t.nbytes()); });
+
+  py::class_<NcclComm, Comm, std::shared_ptr<NcclComm>>(m, "NcclComm")
+      .def(py::init([](std::shared_ptr<Store> store, int rank, int size, int device, double timeout_s) {
+             py::gil_scoped_release r;
+             return std::make_shared<NcclComm>(std::move(store), rank, size, device, Millis(static_cast<int64_t>(timeout_s * 1000)));
+           }),
+           py::arg("store"), py::arg("rank"), py::arg("size"), py::arg("device"), py::arg("timeout") = 600.0);
+
+  // ---- convolution ---------------------------------------------------------------------------------
+  m.def("conv5x5_fwd", [](const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, bool want_stats, const std::string& impl) {
+    chk(x, "x"); chk(w, "w");
+    c10::cuda::CUDAGuard g(x.device());
+    ConvShape s = conv_shape(x, w);
+    TORCH_CHECK(x.size(3) == s.Cin, "conv5x5_fwd: x channels ", x.size(3), " != weight Cin ", s.Cin);
+    at::Tensor y = at::empty({s.B, s.H, s.W, s.Cout}, x.options());
+    at::Tensor stats = want_stats ? at::empty({2 * s.Cout + 1}, x.options()) : at::Tensor();
+    const bool tc = impl == "tcgen05" || (impl == "auto" && conv_tcgen05_supported(s));
+    if (tc) launch_conv5x5_fwd_tcgen05(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
+                                       want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
+    else launch_conv5x5_fwd(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
+                            want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
+    return py::make_tuple(y, stats);
+  }, py::arg("x"), py::arg("w"), py::arg("bias") = py::none(), py::arg("want_stats") = true, py::arg("impl") = "auto");
+
+  m.def("conv5x5_dgrad", [](const at::Tensor& dy, const at::Tensor& w, const std::string& impl) {
+    chk(dy, "dy"); chk(w, "w");
+    c10::cuda::CUDAGuard g(dy.device());
+    ConvShape s = conv_shape(dy, w);
+    s.Cin = static_cast<int>(w.size(1));
+    TORCH_CHECK(dy.size(3) == s.Cout, "conv5x5_dgrad: dy channels must equal weight Cout");
+    at::Tensor dx = at::empty({s.B, s.H, s.W, s.Cin}, dy.options());
+    const bool tc = impl == "tcgen05" || (impl == "auto" && conv_tcgen05_supported(s));
+    if (tc) launch_conv5x5_dgrad_tcgen05(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
+    else launch_conv5x5_dgrad(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
+    return dx;
+  }, py::arg("dy"), py::arg("w"), py::arg("impl") = "auto");
+
+  m.def("conv5x5_wgrad", [](const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, c10::optional<at::Tensor> db, const std::string& impl) {
+    chk(dy, "dy"); chk(x, "x"); chk(dw, "dw");
+    c10::cuda::CUDAGuard g(dy.device());
+    ConvShape s = conv_shape(x, dw);
+    (void)impl;
+    launch_conv5x5_wgrad(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
+  }, py::arg("dy"), py::arg("x"), py::arg("dw"), py::arg("db") = py::none(), py::arg("impl") = "auto");
+
+  // ---- BN + ReLU + pool ------------------------------------------------------------------------------
+  m.def("bn_relu_pool_fwd", [](const at::Tensor& y, const at::Tensor& stats, c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta,
+                               c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
+                               c10::optional<at::Tensor> nbt, double momentum, double eps, bool out_nchw) {
+    chk(y, "y"); chk(stats, "stats");
+    c10::cuda::CUDAGuard g(y.device());
+    const int B = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
+    TORCH_CHECK(stats.numel() == 2 * C + 1, "bn_relu_pool_fwd: stats must have 2C+1 entries");
+    at::Tensor out = out_nchw ? at::empty({B, C, H / 2, W / 2}, y.options()) : at::empty({B, H / 2, W / 2, C}, y.options());
+    at::Tensor saved = at::empty({2 * C}, y.options());
+    long long* nbt_p = nullptr;
+    if (nbt.has_value() && nbt->defined()) { chk(*nbt, "num_batches_tracked", at::kLong); nbt_p = reinterpret_cast<long long*>(nbt->data_ptr<int64_t>()); }
+    launch_bn_relu_pool_fwd(y.data_ptr<float>(), stats.data_ptr<float>(), opt_ptr(gamma, "gamma"), opt_ptr(beta, "beta"), out.data_ptr<float>(),
+                            saved.data_ptr<float>(), opt_mut(running_mean, "running_mean"), opt_mut(running_var, "running_var"), nbt_p,
+                            static_cast<float>(momentum), static_cast<float>(eps), B, H, W, C, out_nchw, cur_stream(y));
+    return py::make_tuple(out, saved);
+  });
+  m.def("bn_relu_pool_bwd_reduce", [](const at::Tensor& dout, const at::Tensor& y, const at::Tensor& saved, c10::optional<at::Tensor> gamma,
+                                      c10::optional<at::Tensor> beta, bool dout_nchw, c10::optional<at::Tensor> dgamma_out,
+                                      c10::optional<at::Tensor> dbeta_out) {
+    chk(dout, "dout"); chk(y, "y"); chk(saved, "saved");
+    c10::cuda::CUDAGuard g(y.device());
+    const int B = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
+    at::Tensor sums = at::empty({2 * C}, y.options());
+    at::Tensor dgamma = dgamma_out.has_value() && dgamma_out->defined() ? *dgamma_out : at::empty({C}, y.options());
+    at::Tensor dbeta = dbeta_out.has_value() && dbeta_out->defined() ? *dbeta_out : at::empty({C}, y.options());
+    chk(dgamma, "dgamma"); chk(dbeta, "dbeta");
+    TORCH_CHECK(dgamma.numel() == C && dbeta.numel() == C, "bn_relu_pool_bwd_reduce: dgamma/dbeta must have C elements");
+    launch_bn_relu_pool_bwd_reduce(dout.data_ptr<float>(), y.data_ptr<float>(), saved.data_ptr<float>(), opt_ptr(gamma, "gamma"),
+                                   opt_ptr(beta, "beta"), sums.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), B, H, W, C,
+                                   dout_nchw, scratch(y), cur_stream(y));
+    return py::make_tuple(sums, dgamma, dbeta);
+  }, py::arg("dout"), py::arg("y"), py::arg("saved"), py::arg("gamma"), py::arg("beta"), py::arg("dout_nchw"),
+     py::arg("dgamma_out") = py::none(), py::arg("dbeta_out") = py::none());
+  m.def("bn_relu_pool_bwd_apply", [](const at::Tensor& dout, const at::Tensor& y, const at::Tensor& saved, c10::optional<at::Tensor> gamma,
+                                     c10::optional<at::Tensor> beta, const at::Tensor& sums, const at::Tensor& count, bool dout_nchw) {
+    chk(dout, "dout"); chk(y, "y"); chk(saved, "saved"); chk(sums, "sums"); chk(count, "count");
+    c10::cuda::CUDAGuard g(y.device());
+    const int B = y.size(0), H = y.size(1), W = y.size(2), C = y.size(3);
+    at::Tensor dy = at::empty_like(y);
+    launch_bn_relu_pool_bwd_apply(dout.data_ptr<float>(), y.data_ptr<float>(), saved.data_ptr<float>(), opt_ptr(gamma, "gamma"),
+                                  opt_ptr(beta, "beta"), sums.data_ptr<float>(), count.data_ptr<float>(), dy.data_ptr<float>(), B, H, W, C,
+                                  dout_nchw, cur_stream(y));
+    return dy;
+  });
+
+  // ---- generic NCHW BatchNorm (SyncBatchNorm) ----------------------------------------------------------
+  m.def("bn_stats_nchw", [](const at::Tensor& x) {
+    chk(x, "x");
+    TORCH_CHECK(x.dim() >= 2, "bn_stats: at least 2-D input");
+    c10::cuda::CUDAGuard g(x.device());
+    const int N = x.size(0), C = x.size(1);
+    const int HW = static_cast<int>(x.numel() / std::max<int64_t>(1, static_cast<int64_t>(N) * C));
+    at::Tensor stats = at::zeros({2 * C + 1}, x.options());
+    if (x.numel() > 0) launch_bn_stats_nchw(x.data_ptr<float>(), stats.data_ptr<float>(), N, C, HW, scratch(x), cur_stream(x));
+    return stats;
+  });
+  m.def("bn_apply_nchw", [](const at::Tensor& x, const at::Tensor& mean, const at::Tensor& invstd, c10::optional<at::Tensor> gamma,
+                            c10::optional<at::Tensor> beta) {
+    chk(x, "x"); chk(mean, "mean"); chk(invstd, "invstd");
+    c10::cuda::CUDAGuard g(x.device());
+    const int N = x.size(0), C = x.size(1);
+    const int HW = static_cast<int>(x.numel() / std::max<int64_t>(1, static_cast<int64_t>(N) * C));
+    at::Tensor out = at::empty_like(x);
+    if (x.numel() > 0) launch_bn_apply_nchw(x.data_ptr<float>(), mean.data_ptr<float>(), invstd.data_ptr<float>(), opt_ptr(gamma, "gamma"),
+                                            opt_ptr(beta, "beta"), out.data_ptr<float>(), N, C, HW, cur_stream(x));
+    return out;
+  });
+  m.def("bn_bwd_reduce_nchw", [](const at::Tensor& dy, const at::Tensor& x, const at::Tensor& mean, const at::Tensor& invstd) {
+    chk(dy, "dy"); chk(x, "x"); chk(mean, "mean"); chk(invstd, "invstd");
+    c10::cuda::CUDAGuard g(x.device());
+    const int N = x.size(0), C = x.size(1);
+    const int HW = static_cast<int>(x.numel() / std::max<int64_t>(1, static_cast<int64_t>(N) * C));
+    at::Tensor red = at::zeros({4 * C}, x.options());
+    if (x.numel() > 0) launch_bn_bwd_reduce_nchw(dy.data_ptr<float>(), x.data_ptr<float>(), mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                                                 red.data_ptr<float>(), N, C, HW, scratch(x), cur_stream(x));
+    return red;
+  });
+  m.def("bn_bwd_apply_nchw", [](const at::Tensor& dy, const at::Tensor& x, const at::Tensor& mean, const at::Tensor& invstd,
+                                c10::optional<at::Tensor> gamma, const at::Tensor& mean_dy, const at::Tensor& mean_dy_xmu) {
+    chk(dy, "dy"); chk(x, "x"); chk(mean_dy, "mean_dy"); chk(mean_dy_xmu, "mean_dy_xmu");
+    c10::cuda::CUDAGuard g(x.device());
+    const int N = x.size(0), C = x.size(1);
+    const int HW = static_cast<int>(x.numel() / std::max<int64_t>(1, static_cast<int64_t>(N) * C));
+    at::Tensor dx = at::empty_like(x);
+    if (x.numel() > 0) launch_bn_bwd_apply_nchw(dy.data_ptr<float>(), x.data_ptr<float>(), mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                                                opt_ptr(gamma, "gamma"), mean_dy.data_ptr<float>(), mean_dy_xmu.data_ptr<float>(),
+                                                dx.data_ptr<float>(), N, C, HW, cur_stream(x));
+    return dx;
+  });
+
+  // ---- head ---------------------------------------------------------------------------------------------
+  m.def("linear_fwd", [](const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> b) {
+    chk(x, "x"); chk(w, "w");
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1), "linear_fwd: x [B,K], w [N,K]");
+    at::Tensor out = at::empty({x.size(0), w.size(0)}, x.options());
+    launch_linear_fwd(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(b, "bias"), out.data_ptr<float>(), x.size(0), x.size(1), w.size(0), cur_stream(x));
+    return out;
+  });
+  m.def("linear_bwd", [](const at::Tensor& dout, const at::Tensor& x, const at::Tensor& w, bool need_dx, at::Tensor dw, c10::optional<at::Tensor> db) {
+    chk(dout, "dout"); chk(x, "x"); chk(w, "w"); chk(dw, "dw");
+    c10::cuda::CUDAGuard g(x.device());
+    at::Tensor dx = need_dx ? at::empty_like(x) : at::Tensor();
+    launch_linear_bwd(dout.data_ptr<float>(), x.data_ptr<float>(), w.data_ptr<float>(), need_dx ? dx.data_ptr<float>() : nullptr,
+                      dw.data_ptr<float>(), opt_mut(db, "db"), x.size(0), x.size(1), w.size(0), cur_stream(x));
+    return dx;
+  });
+  m.def("cross_entropy_fwd", [](const at::Tensor& logits, const at::Tensor& target) {
+    chk(logits, "logits"); chk(target, "target", at::kLong);
+    c10::cuda::CUDAGuard g(logits.device());
+    at::Tensor loss = at::empty({}, logits.options()), probs = at::empty_like(logits);
+    launch_cross_entropy_fwd(logits.data_ptr<float>(), reinterpret_cast<const long long*>(target.data_ptr<int64_t>()), loss.data_ptr<float>(),
+                             probs.data_ptr<float>(), logits.size(0), logits.size(1), cur_stream(logits));
+    return py::make_tuple(loss, probs);
+  });
+  m.def("cross_entropy_bwd", [](const at::Tensor& probs, const at::Tensor& target, const at::Tensor& dloss) {
+    chk(probs, "probs"); chk(target, "target", at::kLong); chk(dloss, "dloss");
+    c10::cuda::CUDAGuard g(probs.device());
+    at::Tensor d = at::empty_like(probs);
+    launch_cross_entropy_bwd(probs.data_ptr<float>(), reinterpret_cast<const long long*>(target.data_ptr<int64_t>()), dloss.data_ptr<float>(),
+                             d.data_ptr<float>(), probs.size(0), probs.size(1), cur_stream(probs));
+    return d;
+  });
+
+  // ---- optimizer ------------------------------------------------------------------------------------------
+  m.def("sgd_multi", [](std::vector<at::Tensor> params, std::vector<at::Tensor> grads, std::vector<at::Tensor> bufs, double lr,
+                        c10::optional<at::Tensor> lr_tensor, double momentum, double dampening, double weight_decay, bool nesterov,
+                        bool maximize, bool first_step) {
+    TORCH_CHECK(params.size() == grads.size(), "sgd_multi: params/grads length mismatch");
+    TORCH_CHECK(momentum == 0.0 || bufs.size() == params.size(), "sgd_multi: momentum buffers required");
+    if (params.empty()) return;
+    c10::cuda::CUDAGuard g(params[0].device());
+    SgdHyper h{static_cast<float>(lr), static_cast<float>(momentum), static_cast<float>(dampening), static_cast<float>(weight_decay),
+               nesterov ? 1 : 0, maximize ? 1 : 0, first_step ? 1 : 0, nullptr};
+    if (lr_tensor.has_value() && lr_tensor->defined()) { chk(*lr_tensor, "lr_tensor"); h.lr_dev = lr_tensor->data_ptr<float>(); }
+    cudaStream_t st = cur_stream(params[0]);
+    for (size_t base = 0; base < params.size(); base += SgdTensorList::kMax) {
+      SgdTensorList tl;
+      tl.count = static_cast<int>(std::min<size_t>(SgdTensorList::kMax, params.size() - base));
+      for (int i = 0; i < tl.count; ++i) {
+        at::Tensor& p = params[base + i];
+        at::Tensor& gr = grads[base + i];
+        chk(p, "param"); chk(gr, "grad");
+        TORCH_CHECK(p.numel() == gr.numel() && p.numel() < (int64_t(1) << 31), "sgd_multi: bad tensor sizes");
+        tl.p[i] = p.data_ptr<float>();
+        tl.g[i] = gr.data_ptr<float>();
+        tl.m[i] = momentum != 0.0 ? bufs[base + i].data_ptr<float>() : nullptr;
+        tl.n[i] = static_cast<int>(p.numel());
+      }
+      launch_sgd_multi(tl, h, st);
+    }
+  });
+
+  // ---- tcgen05 GEMM self-test (D[M,N] = A[M,K]·B[N,K]^T in TF32) — validates descriptors/TMEM/TMA ---------
+  m.def("gemm_tf32_tcgen05", [](const at::Tensor& a, const at::Tensor& b) {
+    chk(a, "a"); chk(b, "b");
+    c10::cuda::CUDAGuard g(a.device());
+    TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.size(1) == b.size(1), "gemm_tf32: A [M,K], B [N,K]");
+    at::Tensor d = at::empty({a.size(0), b.size(0)}, a.options());
+    launch_gemm_tf32_tcgen05(a.data_ptr<float>(), b.data_ptr<float>(), d.data_ptr<float>(), a.size(0), b.size(0), a.size(1), cur_stream(a));
+    return d;
+  });
+}
+
 }  // namespace pdt

@@ -1,0 +1,115 @@
+// GPU communicators: SymmComm (product: NVLink peer/multicast kernels) and NcclComm (baseline).
+#pragma once
+#include <ATen/cuda/CUDAEvent.h>
+#include <c10/cuda/CUDAStream.h>
+
+#include <memory>
+
+#include "../comm/comm.h"
+#include "symm_kernels.h"
+#include "symm_mem.h"
+
+namespace pdt {
+
+// Stream-ordered completion handle: wait() makes the *current* stream wait for the collective
+// (ProcessGroupNCCL semantics the reference relies on); never blocks the host.
+class CudaWork : public CommWork {
+ public:
+  CudaWork(int device, std::vector<at::Tensor> keep) : device_(device), keep_(std::move(keep)) {}
+  at::cuda::CUDAEvent& done() { return done_; }
+  void wait() override;
+  void synchronize() override;
+  bool is_completed() override;
+
+ private:
+  int device_;
+  at::cuda::CUDAEvent done_{cudaEventDisableTiming};
+  std::vector<at::Tensor> keep_;
+};
+
+class CudaCommBase : public Comm {
+ public:
+  CudaCommBase(int rank, int size, int device);
+  int rank() const override { return rank_; }
+  int size() const override { return size_; }
+  bool is_cuda() const override { return true; }
+  int device() const { return device_; }
+  c10::cuda::CUDAStream comm_stream() const { return comm_stream_; }
+
+ protected:
+  // Runs fn(stream) on the comm stream, ordered after the caller's current stream; the tensors
+  // are kept alive (and their blocks marked in use on the comm stream) until completion.
+  std::shared_ptr<CommWork> enqueue(const std::vector<at::Tensor>& tensors, const std::function<void(cudaStream_t)>& fn);
+  void check(const at::Tensor& t, const char* what) const;
+  int rank_, size_, device_;
+  c10::cuda::CUDAStream comm_stream_;
+};
+
+class SymmComm : public CudaCommBase {
+ public:
+  SymmComm(std::shared_ptr<Store> store, int rank, int size, int device, Millis timeout, size_t heap_bytes);
+  ~SymmComm() override;
+  std::string backend_name() const override { return "nvlink"; }
+  at::Tensor alloc_flat(int64_t numel, at::ScalarType dtype, const at::Device& device) override;
+  std::shared_ptr<CommWork> allreduce(at::Tensor t, ReduceOp op, double postscale) override;
+  std::shared_ptr<CommWork> broadcast(at::Tensor t, int root) override;
+  std::shared_ptr<CommWork> allgather(at::Tensor out, at::Tensor in) override;
+  std::shared_ptr<CommWork> reduce(at::Tensor t, ReduceOp op, int root) override;
+  std::shared_ptr<CommWork> reduce_scatter(at::Tensor out, at::Tensor in, ReduceOp op) override;
+  std::shared_ptr<CommWork> gather(at::Tensor out, at::Tensor in, int root) override;
+  std::shared_ptr<CommWork> scatter(at::Tensor out, at::Tensor in, int root) override;
+  std::shared_ptr<CommWork> alltoall(at::Tensor out, at::Tensor in) override;
+  std::shared_ptr<CommWork> barrier() override;
+  void shutdown() override;
+
+  // Same collective launched directly on the caller's current stream (channel kChanInline):
+  // no stream hop — used where the result is needed by the very next kernel (SyncBatchNorm).
+  void allreduce_inline(at::Tensor t, ReduceOp op, double postscale);
+  // Fused mean-allreduce(grad) + SGD(param) in one launch on the caller's stream.
+  void allreduce_sgd_inline(at::Tensor grad, at::Tensor param, c10::optional<at::Tensor> momentum_buf, double lr,
+                            c10::optional<at::Tensor> lr_tensor, double momentum, double dampening, double weight_decay,
+                            bool nesterov, bool first_step);
+
+  SymmetricHeap& heap() { return *heap_; }
+  bool has_multicast() const { return heap_->has_multicast(); }
+  // tuning knobs (also read from PDT_AR_* environment variables)
+  void set_algo(const std::string& algo) { algo_ = algo; }
+  std::string algo() const { return algo_; }
+  void set_oneshot_max_bytes(int64_t n) { oneshot_max_ = static_cast<size_t>(n); }
+  void set_launch(int blocks, int threads) { cfg_.blocks = blocks; cfg_.threads = threads; }
+  std::string describe() const;
+  int status() const { return heap_->status(); }
+
+ private:
+  void do_allreduce(at::Tensor& t, ReduceOp op, double scale, int channel, cudaStream_t s);
+  std::unique_ptr<SymmetricHeap> heap_;
+  std::string algo_ = "auto";   // auto | oneshot | oneshot_mc | twoshot | nvls
+  size_t oneshot_max_ = 512 * 1024;
+  SymmLaunchCfg cfg_;
+  bool down_ = false;
+};
+
+class NcclComm : public CudaCommBase {
+ public:
+  NcclComm(std::shared_ptr<Store> store, int rank, int size, int device, Millis timeout);
+  ~NcclComm() override;
+  std::string backend_name() const override { return "nccl-lib"; }
+  std::shared_ptr<CommWork> allreduce(at::Tensor t, ReduceOp op, double postscale) override;
+  std::shared_ptr<CommWork> broadcast(at::Tensor t, int root) override;
+  std::shared_ptr<CommWork> allgather(at::Tensor out, at::Tensor in) override;
+  std::shared_ptr<CommWork> reduce(at::Tensor t, ReduceOp op, int root) override;
+  std::shared_ptr<CommWork> reduce_scatter(at::Tensor out, at::Tensor in, ReduceOp op) override;
+  std::shared_ptr<CommWork> alltoall(at::Tensor out, at::Tensor in) override;
+  std::shared_ptr<CommWork> send(at::Tensor t, int dst) override;
+  std::shared_ptr<CommWork> recv(at::Tensor t, int src) override;
+  std::shared_ptr<CommWork> barrier() override;
+  void shutdown() override;
+  static bool available();
+  static std::string version();
+
+ private:
+  void* comm_ = nullptr;
+  at::Tensor barrier_buf_;
+};
+
+}  // namespace pdt

@@ -1,0 +1,322 @@
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDACachingAllocator.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include <cstdlib>
+#include <sstream>
+
+#include "cuda_comm.h"
+#include "cuda_utils.h"
+
+namespace pdt {
+
+// ---- CudaWork / CudaCommBase ----------------------------------------------------------------------
+void CudaWork::wait() {
+  done_.block(c10::cuda::getCurrentCUDAStream(device_));
+  // tensors stay referenced by `keep_` until this handle dies; the caching allocator has also
+  // been told about the comm stream (recordStream), so dropping them early is safe too.
+}
+void CudaWork::synchronize() {
+  done_.synchronize();
+  keep_.clear();
+}
+bool CudaWork::is_completed() { return done_.query(); }
+
+CudaCommBase::CudaCommBase(int rank, int size, int device)
+    : rank_(rank), size_(size), device_(device), comm_stream_(c10::cuda::getStreamFromPool(/*isHighPriority=*/true, device)) {}
+
+void CudaCommBase::check(const at::Tensor& t, const char* what) const {
+  TORCH_CHECK(t.is_cuda(), "pdt ", backend_name(), " backend: ", what, " tensor must be a CUDA tensor (got ", t.device(), ")");
+  TORCH_CHECK(t.device().index() == device_, "pdt ", backend_name(), " backend: ", what, " tensor lives on cuda:", t.device().index(),
+              " but this process group drives cuda:", device_);
+  TORCH_CHECK(t.is_contiguous(), "pdt ", backend_name(), " backend: ", what, " tensor must be contiguous");
+}
+
+std::shared_ptr<CommWork> CudaCommBase::enqueue(const std::vector<at::Tensor>& tensors,
+                                               const std::function<void(cudaStream_t)>& fn) {
+  c10::cuda::CUDAGuard guard(device_);
+  auto cur = c10::cuda::getCurrentCUDAStream(device_);
+  auto work = std::make_shared<CudaWork>(device_, tensors);
+  at::cuda::CUDAEvent ready(cudaEventDisableTiming);
+  ready.record(cur);
+  ready.block(comm_stream_);
+  for (auto& t : tensors)
+    if (t.defined() && t.is_cuda() && t.storage().data_ptr().get_deleter() == c10::cuda::CUDACachingAllocator::get()->raw_deleter())
+      c10::cuda::CUDACachingAllocator::recordStream(t.storage().data_ptr(), comm_stream_);
+  fn(comm_stream_.stream());
+  work->done().record(comm_stream_);
+  return work;
+}
+
+// ---- SymmComm ---------------------------------------------------------------------------------------
+SymmComm::SymmComm(std::shared_ptr<Store> store, int rank, int size, int device, Millis timeout, size_t heap_bytes)
+    : CudaCommBase(rank, size, device) {
+  c10::cuda::CUDAGuard guard(device);
+  heap_ = std::make_unique<SymmetricHeap>(std::move(store), rank, size, device, heap_bytes, timeout);
+  if (const char* a = getenv("PDT_AR_ALGO")) algo_ = a;
+  if (const char* m = getenv("PDT_AR_ONESHOT_MAX")) oneshot_max_ = static_cast<size_t>(atoll(m));
+  if (const char* b = getenv("PDT_AR_BLOCKS")) cfg_.blocks = atoi(b);
+  if (const char* t = getenv("PDT_AR_THREADS")) cfg_.threads = atoi(t);
+}
+
+SymmComm::~SymmComm() { shutdown(); }
+
+void SymmComm::shutdown() {
+  if (down_) return;
+  down_ = true;
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+}
+
+std::string SymmComm::describe() const {
+  std::ostringstream os;
+  os << "SymmComm(rank=" << rank_ << "/" << size_ << ", device=" << device_ << ", transport=" << heap_->transport()
+     << ", multicast=" << (heap_->has_multicast() ? "yes" : "no") << ", heap=" << (heap_->heap_bytes() >> 20) << "MiB, algo=" << algo_
+     << ", oneshot_max=" << oneshot_max_ << ")";
+  return os.str();
+}
+
+at::Tensor SymmComm::alloc_flat(int64_t numel, at::ScalarType dtype, const at::Device& device) {
+  TORCH_CHECK(device.is_cuda() && device.index() == device_, "alloc_flat: device mismatch");
+  const size_t nbytes = static_cast<size_t>(std::max<int64_t>(numel, 1)) * c10::elementSize(dtype);
+  void* p = heap_->alloc(nbytes, 256);
+  SymmetricHeap* heap = heap_.get();
+  // NOTE: tensors from the heap must not outlive the communicator.
+  at::Tensor t = at::from_blob(p, {numel}, [heap, p](void*) { heap->free(p); }, at::TensorOptions().dtype(dtype).device(device));
+  t.zero_();
+  return t;
+}
+
+static int to_symm_dtype(at::ScalarType t) { return static_cast<int>(to_dtype(t)); }
+
+void SymmComm::do_allreduce(at::Tensor& t, ReduceOp op, double scale, int channel, cudaStream_t s) {
+  const size_t nbytes = t.nbytes();
+  if (nbytes == 0) return;
+  if (op == ReduceOp::AVG) { scale *= 1.0 / size_; op = ReduceOp::SUM; }
+  const int dt = to_symm_dtype(t.scalar_type());
+  const bool floating = at::isFloatingType(t.scalar_type());
+  TORCH_CHECK(scale == 1.0 || floating, "postscale is only defined for floating-point tensors");
+  const bool aligned = (reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0) && (nbytes % 16 == 0);
+  const bool in_heap = aligned && heap_->contains(t.data_ptr(), nbytes);
+  const bool nvls_ok = heap_->has_multicast() && op == ReduceOp::SUM &&
+                       (t.scalar_type() == at::kFloat || t.scalar_type() == at::kHalf || t.scalar_type() == at::kBFloat16);
+  const size_t half = heap_->staging_half_bytes(channel);
+  const size_t slot_bytes = (nbytes + 15) / 16 * 16;
+  std::string algo = algo_;
+  if (algo == "auto") {
+    if (slot_bytes * size_ <= half && nbytes <= oneshot_max_) algo = heap_->has_multicast() ? "oneshot_mc" : "oneshot";
+    else algo = nvls_ok ? "nvls" : "twoshot";
+  }
+  if ((algo == "oneshot" || algo == "oneshot_mc") && slot_bytes * size_ > half) algo = nvls_ok ? "nvls" : "twoshot";
+  if (algo == "oneshot_mc" && !heap_->has_multicast()) algo = "oneshot";
+  if (algo == "nvls" && !nvls_ok) algo = "twoshot";
+  SymmDev d = heap_->dev(channel);
+  if (size_ == 1) {
+    if (scale != 1.0) t.mul_(scale);
+    return;
+  }
+  if (algo == "oneshot" || algo == "oneshot_mc") {
+    const int parity = heap_->next_parity(channel);
+    const size_t stage = heap_->staging_off(channel, parity);
+    if (aligned) {
+      launch_allreduce_oneshot_push(d, t.data_ptr(), t.data_ptr(), stage, static_cast<size_t>(t.numel()), dt, static_cast<int>(op), scale,
+                                    algo == "oneshot_mc", cfg_, s);
+    } else {
+      // odd size / alignment: bounce through a padded scratch vector
+      const int64_t es = static_cast<int64_t>(t.element_size());
+      const int64_t padded = static_cast<int64_t>(slot_bytes) / es;
+      at::Tensor tmp = at::zeros({padded}, t.options());
+      tmp.narrow(0, 0, t.numel()).copy_(t.view(-1));
+      launch_allreduce_oneshot_push(d, tmp.data_ptr(), tmp.data_ptr(), stage, static_cast<size_t>(padded), dt, static_cast<int>(op), scale,
+                                    algo == "oneshot_mc", cfg_, s);
+      t.view(-1).copy_(tmp.narrow(0, 0, t.numel()));
+    }
+    return;
+  }
+  // two-shot family works in place on symmetric memory
+  if (in_heap) {
+    launch_allreduce_twoshot(d, heap_->offset_of(t.data_ptr()), static_cast<size_t>(t.numel()), dt, static_cast<int>(op), scale,
+                             algo == "nvls", cfg_, s);
+    return;
+  }
+  // ordinary tensor: stream it through the staging area in chunks (copy-in, reduce in place, copy-out)
+  const size_t es = t.element_size();
+  const size_t chunk_elems = (half / 16 * 16) / es;
+  char* p = static_cast<char*>(t.data_ptr());
+  size_t done = 0;
+  const size_t total = static_cast<size_t>(t.numel());
+  while (done < total) {
+    const size_t n = std::min(chunk_elems, total - done);
+    const size_t n_pad = ((n * es + 15) / 16 * 16) / es;
+    const int parity = heap_->next_parity(channel);
+    const size_t stage = heap_->staging_off(channel, parity);
+    char* stg = heap_->local_base() + stage;
+    if (n_pad != n) PDT_CUDA_CHECK(cudaMemsetAsync(stg + n * es, 0, (n_pad - n) * es, s));
+    PDT_CUDA_CHECK(cudaMemcpyAsync(stg, p + done * es, n * es, cudaMemcpyDeviceToDevice, s));
+    launch_allreduce_twoshot(d, stage, n_pad, dt, static_cast<int>(op), scale, algo == "nvls", cfg_, s);
+    PDT_CUDA_CHECK(cudaMemcpyAsync(p + done * es, stg, n * es, cudaMemcpyDeviceToDevice, s));
+    done += n;
+  }
+}
+
+std::shared_ptr<CommWork> SymmComm::allreduce(at::Tensor t, ReduceOp op, double postscale) {
+  check(t, "allreduce");
+  record("allreduce", &t);
+  return enqueue({t}, [&](cudaStream_t s) {
+    c10::cuda::CUDAStreamGuard sg(comm_stream_);  // the odd-size bounce path issues ATen ops
+    do_allreduce(t, op, postscale, kChanComm, s);
+  });
+}
+
+void SymmComm::allreduce_inline(at::Tensor t, ReduceOp op, double postscale) {
+  check(t, "allreduce");
+  record("allreduce_inline", &t);
+  c10::cuda::CUDAGuard guard(device_);
+  do_allreduce(t, op, postscale, kChanInline, c10::cuda::getCurrentCUDAStream(device_).stream());
+}
+
+void SymmComm::allreduce_sgd_inline(at::Tensor grad, at::Tensor param, c10::optional<at::Tensor> momentum_buf, double lr,
+                                    c10::optional<at::Tensor> lr_tensor, double momentum, double dampening, double weight_decay,
+                                    bool nesterov, bool first_step) {
+  check(grad, "allreduce_sgd grad");
+  check(param, "allreduce_sgd param");
+  TORCH_CHECK(grad.scalar_type() == at::kFloat && param.scalar_type() == at::kFloat && grad.numel() == param.numel(),
+              "allreduce_sgd: flat fp32 grad/param vectors of equal length required");
+  TORCH_CHECK(grad.numel() % 4 == 0 && reinterpret_cast<uintptr_t>(grad.data_ptr()) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(param.data_ptr()) % 16 == 0,
+              "allreduce_sgd: vectors must be 16-byte aligned with length % 4 == 0");
+  float* mom = nullptr;
+  if (momentum != 0.0) {
+    TORCH_CHECK(momentum_buf.has_value() && momentum_buf->numel() == grad.numel(), "allreduce_sgd: momentum buffer required");
+    mom = momentum_buf->data_ptr<float>();
+  }
+  record("allreduce_sgd", &grad);
+  c10::cuda::CUDAGuard guard(device_);
+  cudaStream_t s = c10::cuda::getCurrentCUDAStream(device_).stream();
+  const size_t nbytes = grad.nbytes();
+  const int channel = kChanInline;
+  TORCH_CHECK(nbytes * size_ <= heap_->staging_half_bytes(channel),
+              "allreduce_sgd: flat gradient too large for the one-shot staging area (", nbytes, " B × ", size_, ")");
+  const int parity = heap_->next_parity(channel);
+  launch_allreduce_sgd_oneshot(heap_->dev(channel), grad.data_ptr<float>(), param.data_ptr<float>(), mom,
+                               heap_->staging_off(channel, parity), static_cast<size_t>(grad.numel()), 1.0f / size_,
+                               lr_tensor.has_value() ? lr_tensor->data_ptr<float>() : nullptr, static_cast<float>(lr),
+                               static_cast<float>(momentum), static_cast<float>(dampening), static_cast<float>(weight_decay), nesterov,
+                               first_step, heap_->has_multicast() && algo_ != "oneshot", cfg_, s);
+}
+
+std::shared_ptr<CommWork> SymmComm::broadcast(at::Tensor t, int root) {
+  check(t, "broadcast");
+  TORCH_CHECK(root >= 0 && root < size_, "broadcast: invalid root");
+  record("broadcast", &t);
+  return enqueue({t}, [&](cudaStream_t s) {
+    const size_t nbytes = t.nbytes();
+    if (nbytes == 0 || size_ == 1) return;
+    SymmDev d = heap_->dev(kChanComm);
+    if (heap_->contains(t.data_ptr(), nbytes)) {
+      launch_broadcast_pull(d, heap_->offset_of(t.data_ptr()), t.data_ptr(), nbytes, root, /*exit_barrier=*/true, cfg_, s);
+      return;
+    }
+    const size_t half = heap_->staging_half_bytes(kChanComm);
+    char* p = static_cast<char*>(t.data_ptr());
+    for (size_t done = 0; done < nbytes; done += half) {
+      const size_t n = std::min(half, nbytes - done);
+      const size_t stage = heap_->staging_off(kChanComm, heap_->next_parity(kChanComm));
+      if (rank_ == root) PDT_CUDA_CHECK(cudaMemcpyAsync(heap_->local_base() + stage, p + done, n, cudaMemcpyDeviceToDevice, s));
+      // the root's destination is its own (already correct) tensor: pull into it anyway would be a
+      // self-copy from staging — harmless and keeps every rank on the same barrier sequence
+      launch_broadcast_pull(d, stage, p + done, n, root, /*exit_barrier=*/false, cfg_, s);
+    }
+  });
+}
+
+std::shared_ptr<CommWork> SymmComm::allgather(at::Tensor out, at::Tensor in) {
+  check(out, "allgather output");
+  check(in, "allgather input");
+  TORCH_CHECK(out.numel() == in.numel() * size_ && out.scalar_type() == in.scalar_type(),
+              "allgather: output must hold world_size × input elements of the same dtype");
+  record("allgather", &in);
+  return enqueue({out, in}, [&](cudaStream_t s) {
+    const size_t nbytes = in.nbytes();
+    if (nbytes == 0) return;
+    if (size_ == 1) {
+      PDT_CUDA_CHECK(cudaMemcpyAsync(out.data_ptr(), in.data_ptr(), nbytes, cudaMemcpyDeviceToDevice, s));
+      return;
+    }
+    SymmDev d = heap_->dev(kChanComm);
+    const size_t half = heap_->staging_half_bytes(kChanComm);
+    const char* src = static_cast<const char*>(in.data_ptr());
+    char* dst = static_cast<char*>(out.data_ptr());
+    for (size_t done = 0; done < nbytes; done += half) {
+      const size_t n = std::min(half, nbytes - done);
+      const size_t stage = heap_->staging_off(kChanComm, heap_->next_parity(kChanComm));
+      PDT_CUDA_CHECK(cudaMemcpyAsync(heap_->local_base() + stage, src + done, n, cudaMemcpyDeviceToDevice, s));
+      launch_allgather_pull(d, stage, dst + done, n, nbytes, /*exit_barrier=*/false, cfg_, s);
+    }
+  });
+}
+
+std::shared_ptr<CommWork> SymmComm::alltoall(at::Tensor out, at::Tensor in) {
+  check(out, "alltoall output");
+  check(in, "alltoall input");
+  TORCH_CHECK(in.numel() == out.numel() && in.numel() % size_ == 0 && in.scalar_type() == out.scalar_type(), "alltoall: equal splits required");
+  record("alltoall", &in);
+  return enqueue({out, in}, [&](cudaStream_t s) {
+    const size_t total = in.nbytes(), blk = total / size_;
+    if (total == 0) return;
+    TORCH_CHECK(total <= heap_->staging_half_bytes(kChanComm), "alltoall: message larger than the staging area (", total, " B)");
+    const size_t stage = heap_->staging_off(kChanComm, heap_->next_parity(kChanComm));
+    PDT_CUDA_CHECK(cudaMemcpyAsync(heap_->local_base() + stage, in.data_ptr(), total, cudaMemcpyDeviceToDevice, s));
+    if (size_ == 1) {
+      PDT_CUDA_CHECK(cudaMemcpyAsync(out.data_ptr(), in.data_ptr(), total, cudaMemcpyDeviceToDevice, s));
+      return;
+    }
+    launch_alltoall_pull(heap_->dev(kChanComm), stage, out.data_ptr(), blk, blk, /*exit_barrier=*/false, cfg_, s);
+  });
+}
+
+// The remaining collectives are compositions; they are off the training hot path.
+std::shared_ptr<CommWork> SymmComm::reduce(at::Tensor t, ReduceOp op, int root) {
+  check(t, "reduce");
+  at::Tensor tmp = t.clone();
+  auto w = allreduce(tmp, op, 1.0);
+  w->wait();
+  if (rank_ == root) t.copy_(tmp);
+  return w;
+}
+std::shared_ptr<CommWork> SymmComm::reduce_scatter(at::Tensor out, at::Tensor in, ReduceOp op) {
+  check(out, "reduce_scatter output");
+  check(in, "reduce_scatter input");
+  TORCH_CHECK(in.numel() == out.numel() * size_, "reduce_scatter: input must hold world_size × output elements");
+  at::Tensor tmp = in.clone();
+  auto w = allreduce(tmp, op, 1.0);
+  w->wait();
+  out.copy_(tmp.view(-1).narrow(0, static_cast<int64_t>(rank_) * out.numel(), out.numel()).view_as(out));
+  return w;
+}
+std::shared_ptr<CommWork> SymmComm::gather(at::Tensor out, at::Tensor in, int root) {
+  check(in, "gather input");
+  at::Tensor all = at::empty({static_cast<int64_t>(size_) * in.numel()}, in.options());
+  auto w = allgather(all, in.view(-1));
+  w->wait();
+  if (rank_ == root) out.view(-1).copy_(all);
+  return w;
+}
+std::shared_ptr<CommWork> SymmComm::scatter(at::Tensor out, at::Tensor in, int root) {
+  check(out, "scatter output");
+  at::Tensor all = at::empty({static_cast<int64_t>(size_) * out.numel()}, out.options());
+  if (rank_ == root) all.copy_(in.view(-1));
+  auto w = broadcast(all, root);
+  w->wait();
+  out.view(-1).copy_(all.narrow(0, static_cast<int64_t>(rank_) * out.numel(), out.numel()));
+  return w;
+}
+
+std::shared_ptr<CommWork> SymmComm::barrier() {
+  record("barrier", nullptr);
+  return enqueue({}, [&](cudaStream_t s) {
+    if (size_ > 1) launch_barrier(heap_->dev(kChanComm), s);
+  });
+}
+
+}  // namespace pdt

@@ -1,0 +1,387 @@
+// sm_100a collective kernels over NVLink peer / multicast memory.
+//
+// These are the product's communication path (BASELINE.json north star): the DDP
+// bucket allreduce, the per-step BatchNorm-buffer broadcast and SyncBatchNorm's statistic
+// exchange all run here, as plain kernel launches with device-side cross-GPU barriers, so they
+// can be issued from an autograd hook on a side stream *and* captured in a CUDA graph.  What the
+// reference stack does with NCCL (ref: ddp_example.py:64 → c10d reducer → ncclAllReduce) plus
+// 10 per-parameter scale kernels is one launch here: flatten is free (gradients live in the
+// bucket), the 1/world scale — and optionally the SGD update — are fused into the reduce.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+
+#include "symm_kernels.h"
+
+namespace pdt {
+
+namespace {
+
+// ---- element traits -----------------------------------------------------------------------------
+template <typename T> struct Acc { using type = T; };
+template <> struct Acc<__half> { using type = float; };
+template <> struct Acc<__nv_bfloat16> { using type = float; };
+
+template <typename T> __device__ __forceinline__ typename Acc<T>::type to_acc(T v) { return v; }
+template <> __device__ __forceinline__ float to_acc<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_acc<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_acc(typename Acc<T>::type v) { return v; }
+template <> __device__ __forceinline__ __half from_acc<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_acc<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename A, int OP> __device__ __forceinline__ A combine(A a, A b) {
+  if constexpr (OP == SO_SUM || OP == SO_AVG) return a + b;
+  else if constexpr (OP == SO_PROD) return a * b;
+  else if constexpr (OP == SO_MIN) return b < a ? b : a;
+  else if constexpr (OP == SO_MAX) return b > a ? b : a;
+  else if constexpr (OP == SO_BAND) { if constexpr (std::is_integral<A>::value) return a & b; else return a; }
+  else if constexpr (OP == SO_BOR) { if constexpr (std::is_integral<A>::value) return a | b; else return a; }
+  else { if constexpr (std::is_integral<A>::value) return a ^ b; else return a; }
+}
+
+template <typename A> __device__ __forceinline__ A apply_scale(A v, float scale) {
+  if constexpr (std::is_floating_point<A>::value) return v * static_cast<A>(scale);
+  else return v;
+}
+
+__device__ __forceinline__ uint4 ld_vec(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+// peer / staging reads: bypass L1 (another GPU's writes must not be served from a stale line)
+__device__ __forceinline__ uint4 ld_vec_nc(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.relaxed.sys.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_vec(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ void st_vec_sys(void* p, uint4 v) {
+  asm volatile("st.global.relaxed.sys.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void mc_st_vec(void* p, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
+template <typename T> struct VecOf { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T, int OP>
+__device__ __forceinline__ void acc_init(typename Acc<T>::type (&a)[VecOf<T>::N], uint4 v) {
+  const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+  for (int k = 0; k < VecOf<T>::N; ++k) a[k] = to_acc<T>(e[k]);
+}
+template <typename T, int OP>
+__device__ __forceinline__ void acc_add(typename Acc<T>::type (&a)[VecOf<T>::N], uint4 v) {
+  const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+  for (int k = 0; k < VecOf<T>::N; ++k) a[k] = combine<typename Acc<T>::type, OP>(a[k], to_acc<T>(e[k]));
+}
+template <typename T>
+__device__ __forceinline__ uint4 acc_pack(typename Acc<T>::type (&a)[VecOf<T>::N], float scale) {
+  uint4 v;
+  T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+  for (int k = 0; k < VecOf<T>::N; ++k) e[k] = from_acc<T>(apply_scale(a[k], scale));
+  return v;
+}
+
+// ---- one-shot push allreduce -----------------------------------------------------------------------
+// nvec: number of 16-byte vectors (host pads the tail into a scratch vector); slot stride = nvec*16.
+template <typename T, int OP, bool MC>
+__global__ void __launch_bounds__(512) allreduce_oneshot_push_kernel(SymmDev d, const uint4* __restrict__ in, uint4* out,
+                                                                      size_t stage_off, size_t nvec, float scale) {
+  SymmEpoch ep(d, blockIdx.x);
+  const size_t slot_bytes = nvec * 16;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // phase 1: publish my vector into slot[rank] on every GPU
+  for (size_t i = first; i < nvec; i += stride) {
+    uint4 v = ld_vec(in + i);
+    const size_t off = stage_off + static_cast<size_t>(d.rank) * slot_bytes + i * 16;
+    if constexpr (MC) {
+      mc_st_vec(d.mc + off, v);
+    } else {
+#pragma unroll
+      for (int r = 0; r < kSymmMaxWorld; ++r)
+        if (r < d.world) st_vec_sys(d.peer[r] + off, v);
+    }
+  }
+  symm_barrier_block(d, blockIdx.x, ep.next());
+  // phase 2: every slot is now complete locally; reduce in rank order
+  const char* base = d.peer[d.rank] + stage_off;
+  for (size_t i = first; i < nvec; i += stride) {
+    typename Acc<T>::type a[VecOf<T>::N];
+    acc_init<T, OP>(a, ld_vec_nc(base + i * 16));
+    for (int r = 1; r < d.world; ++r) acc_add<T, OP>(a, ld_vec_nc(base + static_cast<size_t>(r) * slot_bytes + i * 16));
+    st_vec(out + i, acc_pack<T>(a, scale));
+  }
+  ep.commit(d, blockIdx.x);
+}
+
+// ---- fused one-shot allreduce + SGD ------------------------------------------------------------------
+template <bool MC>
+__global__ void __launch_bounds__(512) allreduce_sgd_oneshot_kernel(SymmDev d, float4* grad, float4* param, float4* mom,
+                                                                    size_t stage_off, size_t nvec, float scale,
+                                                                    const float* lr_dev, float lr_host, float momentum,
+                                                                    float dampening, float wd, int nesterov, int first_step) {
+  SymmEpoch ep(d, blockIdx.x);
+  const size_t slot_bytes = nvec * 16;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (size_t i = first; i < nvec; i += stride) {
+    uint4 v = ld_vec(grad + i);
+    const size_t off = stage_off + static_cast<size_t>(d.rank) * slot_bytes + i * 16;
+    if constexpr (MC) {
+      mc_st_vec(d.mc + off, v);
+    } else {
+#pragma unroll
+      for (int r = 0; r < kSymmMaxWorld; ++r)
+        if (r < d.world) st_vec_sys(d.peer[r] + off, v);
+    }
+  }
+  const float lr = lr_dev ? *lr_dev : lr_host;
+  symm_barrier_block(d, blockIdx.x, ep.next());
+  const char* base = d.peer[d.rank] + stage_off;
+  for (size_t i = first; i < nvec; i += stride) {
+    float a[4];
+    acc_init<float, SO_SUM>(a, ld_vec_nc(base + i * 16));
+    for (int r = 1; r < d.world; ++r) acc_add<float, SO_SUM>(a, ld_vec_nc(base + static_cast<size_t>(r) * slot_bytes + i * 16));
+    float4 g = make_float4(a[0] * scale, a[1] * scale, a[2] * scale, a[3] * scale);
+    grad[i] = g;  // .grad holds the averaged gradient, as after the reference's allreduce
+    float4 p = param[i];
+    if (wd != 0.f) { g.x += wd * p.x; g.y += wd * p.y; g.z += wd * p.z; g.w += wd * p.w; }
+    if (momentum != 0.f) {
+      float4 b;
+      if (first_step) b = g;
+      else {
+        b = mom[i];
+        const float k = 1.f - dampening;
+        b.x = momentum * b.x + k * g.x; b.y = momentum * b.y + k * g.y; b.z = momentum * b.z + k * g.z; b.w = momentum * b.w + k * g.w;
+      }
+      mom[i] = b;
+      if (nesterov) { g.x += momentum * b.x; g.y += momentum * b.y; g.z += momentum * b.z; g.w += momentum * b.w; }
+      else g = b;
+    }
+    p.x -= lr * g.x; p.y -= lr * g.y; p.z -= lr * g.z; p.w -= lr * g.w;
+    param[i] = p;
+  }
+  ep.commit(d, blockIdx.x);
+}
+
+// ---- two-shot allreduce, in place on a symmetric buffer ---------------------------------------------
+template <typename T> __device__ __forceinline__ uint4 nvls_ld_reduce(const void* p);
+template <> __device__ __forceinline__ uint4 nvls_ld_reduce<float>(const void* p) {
+  float4 f = multimem_ld_reduce_f32x4(p);
+  return make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
+}
+template <> __device__ __forceinline__ uint4 nvls_ld_reduce<__half>(const void* p) { return multimem_ld_reduce_f16x8(p); }
+template <> __device__ __forceinline__ uint4 nvls_ld_reduce<__nv_bfloat16>(const void* p) { return multimem_ld_reduce_bf16x8(p); }
+
+template <typename T, int OP, bool NVLS>
+__global__ void __launch_bounds__(512) allreduce_twoshot_kernel(SymmDev d, size_t buf_off, size_t nvec, float scale) {
+  SymmEpoch ep(d, blockIdx.x);
+  const size_t per = (nvec + d.world - 1) / d.world;  // vectors per slice
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  symm_barrier_block(d, blockIdx.x, ep.next());  // every rank's input is in place
+  {
+    const size_t lo = per * d.rank, hi = min(nvec, lo + per);
+    for (size_t j = first; lo + j < hi; j += stride) {
+      const size_t off = buf_off + (lo + j) * 16;
+      if constexpr (NVLS) {
+        uint4 v = nvls_ld_reduce<T>(d.mc + off);
+        if (scale != 1.f) {
+          typename Acc<T>::type a[VecOf<T>::N];
+          acc_init<T, OP>(a, v);
+          v = acc_pack<T>(a, scale);
+        }
+        mc_st_vec(d.mc + off, v);  // lands in every rank's buffer
+      } else {
+        typename Acc<T>::type a[VecOf<T>::N];
+        acc_init<T, OP>(a, ld_vec_nc(d.peer[0] + off));
+        for (int r = 1; r < d.world; ++r) acc_add<T, OP>(a, ld_vec_nc(d.peer[r] + off));
+        st_vec(d.peer[d.rank] + off, acc_pack<T>(a, scale));
+      }
+    }
+  }
+  symm_barrier_block(d, blockIdx.x, ep.next());  // all slices reduced (NVLS: and delivered)
+  if constexpr (!NVLS) {
+    for (int k = 1; k < d.world; ++k) {
+      const int q = (d.rank + k) % d.world;  // stagger peers so links are used evenly
+      const size_t lo = per * q, hi = min(nvec, lo + per);
+      for (size_t j = first; lo + j < hi; j += stride) {
+        const size_t off = buf_off + (lo + j) * 16;
+        st_vec(d.peer[d.rank] + off, ld_vec_nc(d.peer[q] + off));
+      }
+    }
+    symm_barrier_block(d, blockIdx.x, ep.next());  // nobody overwrites a slice a peer still reads
+  }
+  ep.commit(d, blockIdx.x);
+}
+
+// ---- pull-style data movement -------------------------------------------------------------------------
+// mode 0: broadcast (root → dst), 1: allgather, 2: alltoall
+__global__ void __launch_bounds__(512) pull_kernel(SymmDev d, size_t src_off, char* dst, size_t nbytes, size_t dst_stride,
+                                                   int root, int mode, int exit_barrier) {
+  SymmEpoch ep(d, blockIdx.x);
+  symm_barrier_block(d, blockIdx.x, ep.next());
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nvec = nbytes / 16, tail = nbytes % 16;
+  const int n_src = mode == 0 ? 1 : d.world;
+  for (int k = 0; k < n_src; ++k) {
+    const int q = mode == 0 ? root : (d.rank + k) % d.world;
+    if (mode == 0 && d.rank == root && dst == d.peer[root] + src_off) break;  // in place at the root
+    const char* src = d.peer[q] + src_off + (mode == 2 ? static_cast<size_t>(d.rank) * dst_stride : 0);
+    char* out = dst + (mode == 0 ? 0 : static_cast<size_t>(q) * dst_stride);
+    for (size_t i = first; i < nvec; i += stride) st_vec(out + i * 16, ld_vec_nc(src + i * 16));
+    if (tail && blockIdx.x == 0 && threadIdx.x < tail)
+      out[nvec * 16 + threadIdx.x] = *reinterpret_cast<const volatile char*>(src + nvec * 16 + threadIdx.x);
+  }
+  if (exit_barrier) symm_barrier_block(d, blockIdx.x, ep.next());
+  ep.commit(d, blockIdx.x);
+}
+
+__global__ void barrier_kernel(SymmDev d) {
+  SymmEpoch ep(d, 0);
+  symm_barrier_block(d, 0, ep.next());
+  ep.commit(d, 0);
+}
+
+// ---- launch helpers -------------------------------------------------------------------------------------
+int auto_blocks(size_t nvec, int threads, int cap) {
+  size_t b = (nvec + static_cast<size_t>(threads) * 2 - 1) / (static_cast<size_t>(threads) * 2);
+  return static_cast<int>(std::max<size_t>(1, std::min<size_t>(b, static_cast<size_t>(cap))));
+}
+
+void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("launch of ") + what + " failed: " + cudaGetErrorString(e));
+  count_kernel_launch();
+}
+
+#define PDT_DISPATCH_OP(T, OPV, ...)                                  \
+  switch (OPV) {                                                      \
+    case SO_SUM: case SO_AVG: { constexpr int OP = SO_SUM; __VA_ARGS__; break; } \
+    case SO_PROD: { constexpr int OP = SO_PROD; __VA_ARGS__; break; } \
+    case SO_MIN: { constexpr int OP = SO_MIN; __VA_ARGS__; break; }   \
+    case SO_MAX: { constexpr int OP = SO_MAX; __VA_ARGS__; break; }   \
+    case SO_BAND: { constexpr int OP = SO_BAND; __VA_ARGS__; break; } \
+    case SO_BOR: { constexpr int OP = SO_BOR; __VA_ARGS__; break; }   \
+    case SO_BXOR: { constexpr int OP = SO_BXOR; __VA_ARGS__; break; } \
+    default: throw std::invalid_argument("unsupported reduce op");    \
+  }
+
+#define PDT_DISPATCH_TYPE(DT, ...)                                             \
+  switch (DT) {                                                                \
+    case SD_F32: { using T = float; __VA_ARGS__; break; }                      \
+    case SD_F64: { using T = double; __VA_ARGS__; break; }                     \
+    case SD_F16: { using T = __half; __VA_ARGS__; break; }                     \
+    case SD_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }             \
+    case SD_I8: { using T = signed char; __VA_ARGS__; break; }                 \
+    case SD_U8: case SD_BOOL: { using T = unsigned char; __VA_ARGS__; break; } \
+    case SD_I16: { using T = short; __VA_ARGS__; break; }                      \
+    case SD_I32: { using T = int; __VA_ARGS__; break; }                        \
+    case SD_I64: { using T = long long; __VA_ARGS__; break; }                  \
+    default: throw std::invalid_argument("unsupported dtype for NVLink collectives"); \
+  }
+
+size_t elem_size(int dtype) {
+  switch (dtype) {
+    case SD_F32: case SD_I32: return 4;
+    case SD_F64: case SD_I64: return 8;
+    case SD_F16: case SD_BF16: case SD_I16: return 2;
+    default: return 1;
+  }
+}
+
+}  // namespace
+
+void launch_allreduce_oneshot_push(const SymmDev& d, const void* in, void* out, size_t stage_off, size_t count, int dtype,
+                                   int op, double scale, bool use_mc, SymmLaunchCfg cfg, cudaStream_t s) {
+  const size_t nbytes = count * elem_size(dtype);
+  if (nbytes % 16 != 0) throw std::invalid_argument("oneshot push: byte count must be a multiple of 16 (caller pads)");
+  const size_t nvec = nbytes / 16;
+  if (nvec == 0) return;
+  const int threads = cfg.threads ? cfg.threads : 256;
+  const int blocks = std::min(cfg.blocks ? cfg.blocks : auto_blocks(nvec, threads, 64), kSymmMaxBlocks);
+  const float sc = static_cast<float>(scale);
+  PDT_DISPATCH_TYPE(dtype, PDT_DISPATCH_OP(T, op, {
+    if (use_mc) allreduce_oneshot_push_kernel<T, OP, true><<<blocks, threads, 0, s>>>(d, static_cast<const uint4*>(in), static_cast<uint4*>(out), stage_off, nvec, sc);
+    else allreduce_oneshot_push_kernel<T, OP, false><<<blocks, threads, 0, s>>>(d, static_cast<const uint4*>(in), static_cast<uint4*>(out), stage_off, nvec, sc);
+  }));
+  check_launch("allreduce_oneshot_push");
+}
+
+void launch_allreduce_sgd_oneshot(const SymmDev& d, float* grad, float* param, float* momentum_buf, size_t stage_off,
+                                  size_t count, float scale, const float* lr_dev, float lr, float momentum, float dampening,
+                                  float weight_decay, bool nesterov, bool first_step, bool use_mc, SymmLaunchCfg cfg,
+                                  cudaStream_t s) {
+  if (count % 4 != 0) throw std::invalid_argument("allreduce_sgd: element count must be a multiple of 4");
+  const size_t nvec = count / 4;
+  if (nvec == 0) return;
+  const int threads = cfg.threads ? cfg.threads : 256;
+  const int blocks = std::min(cfg.blocks ? cfg.blocks : auto_blocks(nvec, threads, 64), kSymmMaxBlocks);
+  if (use_mc)
+    allreduce_sgd_oneshot_kernel<true><<<blocks, threads, 0, s>>>(d, reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(param),
+                                                                  reinterpret_cast<float4*>(momentum_buf), stage_off, nvec, scale, lr_dev, lr,
+                                                                  momentum, dampening, weight_decay, nesterov, first_step);
+  else
+    allreduce_sgd_oneshot_kernel<false><<<blocks, threads, 0, s>>>(d, reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(param),
+                                                                   reinterpret_cast<float4*>(momentum_buf), stage_off, nvec, scale, lr_dev, lr,
+                                                                   momentum, dampening, weight_decay, nesterov, first_step);
+  check_launch("allreduce_sgd_oneshot");
+}
+
+void launch_allreduce_twoshot(const SymmDev& d, size_t buf_off, size_t count, int dtype, int op, double scale, bool nvls,
+                              SymmLaunchCfg cfg, cudaStream_t s) {
+  const size_t nbytes = count * elem_size(dtype);
+  if (nbytes % 16 != 0 || buf_off % 16 != 0) throw std::invalid_argument("twoshot: buffer must be 16-byte aligned and sized");
+  const size_t nvec = nbytes / 16;
+  if (nvec == 0) return;
+  const int threads = cfg.threads ? cfg.threads : 512;
+  const size_t per = (nvec + d.world - 1) / d.world;
+  const int blocks = std::min(cfg.blocks ? cfg.blocks : auto_blocks(per, threads, 148), kSymmMaxBlocks);
+  const float sc = static_cast<float>(scale);
+  if (nvls) {
+    if (!d.mc) throw std::runtime_error("twoshot nvls requested but the heap has no multicast mapping");
+    if (!(op == SO_SUM || op == SO_AVG)) throw std::invalid_argument("NVLS reduction supports SUM only");
+    switch (dtype) {
+      case SD_F32: allreduce_twoshot_kernel<float, SO_SUM, true><<<blocks, threads, 0, s>>>(d, buf_off, nvec, sc); break;
+      case SD_F16: allreduce_twoshot_kernel<__half, SO_SUM, true><<<blocks, threads, 0, s>>>(d, buf_off, nvec, sc); break;
+      case SD_BF16: allreduce_twoshot_kernel<__nv_bfloat16, SO_SUM, true><<<blocks, threads, 0, s>>>(d, buf_off, nvec, sc); break;
+      default: throw std::invalid_argument("NVLS reduction supports f32/f16/bf16 only");
+    }
+  } else {
+    PDT_DISPATCH_TYPE(dtype, PDT_DISPATCH_OP(T, op, { allreduce_twoshot_kernel<T, OP, false><<<blocks, threads, 0, s>>>(d, buf_off, nvec, sc); }));
+  }
+  check_launch("allreduce_twoshot");
+}
+
+static void launch_pull(const SymmDev& d, size_t src_off, void* dst, size_t nbytes, size_t dst_stride, int root, int mode,
+                        bool exit_barrier, SymmLaunchCfg cfg, cudaStream_t s) {
+  const int threads = cfg.threads ? cfg.threads : 512;
+  const int blocks = std::min(cfg.blocks ? cfg.blocks : auto_blocks(nbytes / 16 + 1, threads, 64), kSymmMaxBlocks);
+  pull_kernel<<<blocks, threads, 0, s>>>(d, src_off, static_cast<char*>(dst), nbytes, dst_stride, root, mode, exit_barrier ? 1 : 0);
+  check_launch("pull_kernel");
+}
+void launch_broadcast_pull(const SymmDev& d, size_t src_off, void* dst, size_t nbytes, int root, bool exit_barrier,
+                           SymmLaunchCfg cfg, cudaStream_t s) {
+  launch_pull(d, src_off, dst, nbytes, 0, root, 0, exit_barrier, cfg, s);
+}
+void launch_allgather_pull(const SymmDev& d, size_t src_off, void* dst, size_t nbytes, size_t dst_stride, bool exit_barrier,
+                           SymmLaunchCfg cfg, cudaStream_t s) {
+  launch_pull(d, src_off, dst, nbytes, dst_stride, 0, 1, exit_barrier, cfg, s);
+}
+void launch_alltoall_pull(const SymmDev& d, size_t src_off, void* dst, size_t nbytes, size_t stride, bool exit_barrier,
+                          SymmLaunchCfg cfg, cudaStream_t s) {
+  launch_pull(d, src_off, dst, nbytes, stride, 0, 2, exit_barrier, cfg, s);
+}
+void launch_barrier(const SymmDev& d, cudaStream_t s) {
+  barrier_kernel<<<1, 32, 0, s>>>(d);
+  check_launch("barrier_kernel");
+}
+
+}  // namespace pdt

@@ -387,6 +387,14 @@ std::vector<at::Tensor> Reducer::bucket_buffers() const {
   return out;
 }
 
+std::vector<at::Tensor> Reducer::grad_views() const {
+  std::lock_guard<std::mutex> g(mu_);
+  std::vector<at::Tensor> out;
+  out.reserve(params_.size());
+  for (size_t i = 0; i < params_.size(); ++i) out.push_back(buckets_[locs_[i].bucket].views[locs_[i].slot]);
+  return out;
+}
+
 bool Reducer::grads_are_views() const {
   std::lock_guard<std::mutex> g(mu_);
   for (size_t i = 0; i < params_.size(); ++i) {

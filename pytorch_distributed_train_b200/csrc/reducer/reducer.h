@@ -76,6 +76,8 @@ class Reducer {
   void register_comm_hook(py::object hook);
   ReducerStats stats() const;
   std::vector<at::Tensor> bucket_buffers() const;
+  // Per-parameter bucket slot (param order): kernels may write gradients straight into these.
+  std::vector<at::Tensor> grad_views() const;
   // True when every parameter's .grad currently aliases its bucket slot.
   bool grads_are_views() const;
   // Re-point every param.grad at its bucket view (zeroing the bucket): used by the graph

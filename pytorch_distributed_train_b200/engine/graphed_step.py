@@ -48,9 +48,14 @@ class GraphedTrainStep:
                 self._eager_step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        from .. import _C
+
         self.graph = torch.cuda.CUDAGraph()
+        before = _C.kernel_launch_count()
         with torch.cuda.graph(self.graph):
             self.static_loss = self._eager_step()
+        # how many of *our* kernels one replay runs (ATen glue kernels are not counted)
+        self.kernels_per_replay = int(_C.kernel_launch_count() - before)
         torch.cuda.synchronize(dev)
 
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,209 @@
+"""Autograd bindings for the sm_100a kernels in ``_C`` (csrc/cuda/ops_simt.cu, conv_tcgen05.cu).
+
+Layout convention: activations between fused layers are NHWC in memory and are handed to PyTorch
+as ``channels_last`` tensors (logical NCHW shape), so module hooks / user code see ordinary tensors.
+
+Gradient placement: when a parameter's ``.grad`` is ``None`` at backward time (the reference's
+``optimizer.zero_grad()`` default, ref: ddp_example.py:90) and DDP has published a bucket view for it
+(``param._pdt_grad_view``), the weight-gradient kernels write **directly into the DDP bucket** and
+return an alias of that view; autograd adopts it as ``.grad`` and the reducer finds the gradient
+already in place — no per-parameter copy or scale kernels (the reference path spends ~20 tiny kernels
+per step there).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from .. import _C
+from .. import distributed as dist
+
+
+def _grad_dst(param: Optional[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
+    """Where a parameter gradient should be written: the DDP bucket slot when that is safe."""
+    view = getattr(param, "_pdt_grad_view", None) if param is not None else None
+    if view is not None and param.grad is None and view.shape == like.shape and view.is_contiguous():
+        return view.detach().view(like.shape)  # fresh alias: autograd may adopt it without copying
+    return torch.empty_like(like, memory_format=torch.contiguous_format)
+
+
+def _inline_allreduce(group, t: torch.Tensor) -> None:
+    comm = group.comm
+    if hasattr(comm, "allreduce_inline"):
+        comm.allreduce_inline(t, dist.ReduceOp.SUM, 1.0)   # our kernel, on the current stream
+    else:
+        comm.allreduce(t, dist.ReduceOp.SUM, 1.0).wait()   # NCCL baseline: stream hop + wait
+
+
+def _to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] (any strides) → contiguous [B,H,W,C] without a copy when already channels_last."""
+    if x.shape[1] == 1:
+        return x.contiguous().view(x.shape[0], x.shape[2], x.shape[3], 1)
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+class _ConvBnReluPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, training, group, out_nchw, impl):
+        xh = _to_nhwc(x)
+        C = w.shape[0]
+        if training:
+            y, stats = _C.conv5x5_fwd(xh, w, b, True, impl)
+            if group is not None:
+                _inline_allreduce(group, stats)   # Σy, Σy², n across the group: SyncBatchNorm
+            out, saved = _C.bn_relu_pool_fwd(y, stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, out_nchw)
+            count = stats[2 * C:2 * C + 1]
+        else:
+            y, _ = _C.conv5x5_fwd(xh, w, b, False, impl)
+            stats = torch.cat([running_mean, running_var + running_mean * running_mean, running_mean.new_ones(1)])
+            out, saved = _C.bn_relu_pool_fwd(y, stats, gamma, beta, None, None, None, 0.0, eps, out_nchw)
+            count = stats[2 * C:2 * C + 1]
+        ctx.save_for_backward(xh, w, y, saved, gamma, beta, count)
+        ctx.group, ctx.out_nchw, ctx.impl, ctx.training = group, out_nchw, impl, training
+        ctx.params = (w, b, gamma, beta)
+        ctx.x_is_image = x.shape[1] == 1
+        ctx.x_shape = x.shape
+        return out if out_nchw else out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xh, w, y, saved, gamma, beta, count = ctx.saved_tensors
+        w_p, b_p, g_p, be_p = ctx.params
+        if not ctx.training:
+            raise RuntimeError("conv_bn_relu_pool: backward through eval-mode BatchNorm is not supported by the fused op")
+        d = dout.contiguous() if ctx.out_nchw else dout.permute(0, 2, 3, 1).contiguous()
+        gview = _grad_dst(g_p, gamma) if g_p is not None else None
+        bview = _grad_dst(be_p, beta) if be_p is not None else None
+        sums, dgamma, dbeta = _C.bn_relu_pool_bwd_reduce(d, y, saved, gamma, beta, ctx.out_nchw, gview, bview)
+        if ctx.group is not None:
+            _inline_allreduce(ctx.group, sums)     # Σdz, Σdz·x̂ across the group
+        dy = _C.bn_relu_pool_bwd_apply(d, y, saved, gamma, beta, sums, count, ctx.out_nchw)
+        dw = _grad_dst(w_p, w)
+        db = _grad_dst(b_p, w.new_empty(w.shape[0])) if b_p is not None else None
+        _C.conv5x5_wgrad(dy, xh, dw, db, ctx.impl)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _C.conv5x5_dgrad(dy, w, ctx.impl).permute(0, 3, 1, 2)
+        return dx, dw, db, (dgamma if g_p is not None else None), (dbeta if be_p is not None else None), None, None, None, None, None, None, None, None, None
+
+
+def conv_bn_relu_pool(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.Module, out_nchw: Optional[bool] = None,
+                      impl: str = "auto") -> torch.Tensor:
+    """Conv5×5(pad 2) → BatchNorm (batch stats, optionally synchronised) → ReLU → MaxPool2×2 as two
+    kernels forward / four backward (ref layers: ddp_example.py:25-33)."""
+    if conv.kernel_size != (5, 5) or conv.stride != (1, 1) or conv.padding != (2, 2) or conv.groups != 1:
+        raise ValueError("conv_bn_relu_pool: only 5x5 / stride 1 / pad 2 convolutions are fused")
+    if impl == "auto":
+        impl = os.environ.get("PDT_CONV_IMPL", "auto")  # auto = tcgen05 where implemented, SIMT elsewhere
+    group = None
+    training = bn.training
+    if training and type(bn).__name__ == "SyncBatchNorm" and dist.is_initialized():
+        g = getattr(bn, "process_group", None) or dist.get_default_group()
+        if g.size() > 1:
+            group = g
+    if out_nchw is None:
+        out_nchw = conv.out_channels >= 32  # last fused layer feeds the flatten: plain NCHW keeps it a view
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if training and bn.momentum is None and bn.num_batches_tracked is not None:
+        momentum = 1.0 / float(bn.num_batches_tracked + 1)
+    track = bn.track_running_stats
+    return _ConvBnReluPool.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean if track else None,
+                                 bn.running_var if track else None, bn.num_batches_tracked if (track and training) else None,
+                                 momentum, bn.eps, training or not track, group, out_nchw, impl)
+
+
+class _Conv5x5(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, impl):
+        xh = _to_nhwc(x)
+        y, _ = _C.conv5x5_fwd(xh, w, b, False, impl)
+        ctx.save_for_backward(xh, w)
+        ctx.params, ctx.impl = (w, b), impl
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xh, w = ctx.saved_tensors
+        w_p, b_p = ctx.params
+        dy = dout.permute(0, 2, 3, 1).contiguous()
+        dw = _grad_dst(w_p, w)
+        db = _grad_dst(b_p, w.new_empty(w.shape[0])) if b_p is not None else None
+        _C.conv5x5_wgrad(dy, xh, dw, db, ctx.impl)
+        dx = _C.conv5x5_dgrad(dy, w, ctx.impl).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
+        return dx, dw, db, None
+
+
+def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, impl: str = "auto") -> torch.Tensor:
+    """5×5 / stride 1 / pad 2 convolution on our kernels (tcgen05 for 16→32 channels); returns a
+    channels_last tensor."""
+    return _Conv5x5.apply(x, weight, bias, impl)
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xc = x.contiguous()
+        ctx.save_for_backward(xc, w)
+        ctx.params = (w, b)
+        return _C.linear_fwd(xc, w, b)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        w_p, b_p = ctx.params
+        dw = _grad_dst(w_p, w)
+        db = _grad_dst(b_p, w.new_empty(w.shape[0])) if b_p is not None else None
+        dx = _C.linear_bwd(dout.contiguous(), x, w, ctx.needs_input_grad[0], dw, db)
+        return (dx if ctx.needs_input_grad[0] else None), dw, db
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Classifier head ``x·Wᵀ + b`` for narrow outputs (N ≤ 16) (ref: ddp_example.py:34,40)."""
+    if weight.shape[0] > 16:
+        return torch.nn.functional.linear(x, weight, bias)
+    return _Linear.apply(x, weight, bias)
+
+
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target):
+        loss, probs = _C.cross_entropy_fwd(logits.contiguous(), target.contiguous())
+        ctx.save_for_backward(probs, target)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        probs, target = ctx.saved_tensors
+        return _C.cross_entropy_bwd(probs, target, dloss.contiguous()), None
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """Mean cross-entropy over the batch: fused log-softmax + NLL (ref: ddp_example.py:61,87)."""
+    return _CrossEntropy.apply(logits, target)
+
+
+def sgd_step(params, grads, momentum_bufs, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False,
+             maximize=False, first_step=False, lr_tensor=None) -> None:
+    _C.sgd_multi(list(params), list(grads), list(momentum_bufs) if momentum_bufs else [], float(lr), lr_tensor, float(momentum),
+                 float(dampening), float(weight_decay), bool(nesterov), bool(maximize), bool(first_step))
+
+
+# ---- generic (NCHW) BatchNorm pieces used by parallel.SyncBatchNorm ------------------------------------------
+def bn_local_stats(x: torch.Tensor) -> torch.Tensor:
+    """[2C+1] = per-channel Σx, Σx², then the per-channel element count."""
+    return _C.bn_stats_nchw(x)
+
+
+def bn_apply(x, mean, invstd, weight, bias):
+    return _C.bn_apply_nchw(x, mean.contiguous(), invstd.contiguous(), weight, bias)
+
+
+def bn_backward_reduce(dy, x, mean, invstd):
+    """[4C] = Σdy, Σdy·(x−μ), dγ, dβ (local batch)."""
+    return _C.bn_bwd_reduce_nchw(dy, x, mean.contiguous(), invstd.contiguous())
+
+
+def bn_backward_apply(dy, x, mean, invstd, weight, mean_dy, mean_dy_xmu):
+    return _C.bn_bwd_apply_nchw(dy, x, mean.contiguous(), invstd.contiguous(), weight, mean_dy.contiguous(), mean_dy_xmu.contiguous())

@@ -276,6 +276,14 @@ class DistributedDataParallel(nn.Module):
                                   self.first_bucket_bytes_cap, self.find_unused_parameters,
                                   self.gradient_as_bucket_view, self.static_graph)
         self._rebuild_checked = False
+        self._publish_grad_views()
+
+    def _publish_grad_views(self):
+        """Let our backward kernels write weight gradients straight into the bucket (ops.functional._grad_dst)."""
+        if not self.gradient_as_bucket_view:
+            return
+        for p, v in zip(self._params, self.reducer.grad_views()):
+            p._pdt_grad_view = v
 
     # ---- forward -----------------------------------------------------------------------------
     def _maybe_rebuild_buckets(self):
@@ -286,6 +294,7 @@ class DistributedDataParallel(nn.Module):
         proposal = self.reducer.propose_rebuild() if g.rank() == 0 else None
         layout = dist.broadcast_object(proposal, 0, g) if g.size() > 1 else proposal  # C6: agree on rank 0's layout
         self.reducer.apply_rebuild(layout)
+        self._publish_grad_views()
 
     def _pre_forward(self, inputs, kwargs):
         sync = torch.is_grad_enabled() and self.require_backward_grad_sync

@@ -26,6 +26,16 @@ import torch.nn.functional as F
 from .. import distributed as dist
 
 
+def _allreduce_now(group, t: torch.Tensor) -> None:
+    """SUM-allreduce whose result the very next kernel consumes: on the NVLink backend this is one
+    fused peer-memory kernel on the *current* stream (no stream hop, no host sync)."""
+    comm = group.comm
+    if hasattr(comm, "allreduce_inline"):
+        comm.allreduce_inline(t, dist.ReduceOp.SUM, 1.0)
+    else:
+        comm.allreduce(t, dist.ReduceOp.SUM, 1.0).wait()
+
+
 def _reduce_dims(x: torch.Tensor):
     return [0] + list(range(2, x.dim()))
 
@@ -50,7 +60,7 @@ class _SyncBatchNormFn(torch.autograd.Function):
             xf = xc.float()
             dims = _reduce_dims(xf)
             stats = torch.cat([xf.sum(dims), (xf * xf).sum(dims), xf.new_full((1,), float(count))])
-        group.comm.allreduce(stats, dist.ReduceOp.SUM, 1.0).wait()
+        _allreduce_now(group, stats)
         total = stats[2 * C]
         # every rank holding zero samples is legal as long as somebody has data
         n = total.clamp_min(1.0)
@@ -99,7 +109,7 @@ class _SyncBatchNormFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             sums = red[:2 * C].contiguous()
-            ctx.group.comm.allreduce(sums, dist.ReduceOp.SUM, 1.0).wait()
+            _allreduce_now(ctx.group, sums)
             n = total.clamp_min(1.0)
             mean_dy = sums[:C] / n
             mean_dy_xmu = sums[C:] / n

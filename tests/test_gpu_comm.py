@@ -1,0 +1,201 @@
+"""Multi-GPU tests of the NVLink backend (SymmComm) against NCCL / closed-form results, and of DDP /
+SyncBatchNorm end to end against the torch stack (SURVEY §4.3 "GPU distributed tests")."""
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+import pytorch_distributed_train_b200 as pdt
+from mp_helpers import free_port, run_ranks
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+dist = pdt.distributed
+
+
+def _world():
+    return min(torch.cuda.device_count(), int(os.environ.get("PDT_TEST_WORLD", "8")))
+
+
+def _collectives(rank, world):
+    dev = torch.device("cuda", rank)
+    comm = dist.get_default_group().comm
+    info = {"desc": comm.describe(), "mc": comm.has_multicast}
+    algos = ["oneshot", "twoshot"] + (["oneshot_mc", "nvls"] if comm.has_multicast else [])
+    total = sum(range(1, world + 1))
+    for algo in algos + ["auto"]:
+        comm.algo = algo
+        for n in (4, 1000, 29036, 262144, 1 << 20, (1 << 22) + 4):
+            # symmetric (heap) buffer: zero-copy path
+            t = comm.alloc_flat(n, torch.float32, dev)
+            t.copy_(torch.arange(n, device=dev, dtype=torch.float32) % 97 * (rank + 1))
+            dist.all_reduce(t)
+            exp = torch.arange(n, device=dev, dtype=torch.float32) % 97 * total
+            assert torch.equal(t, exp), f"{algo} heap n={n}"
+            # ordinary tensor (staged path), odd length, averaged
+            u = torch.full((n - 1,), float(rank + 1), device=dev)
+            dist.all_reduce(u, dist.ReduceOp.AVG)
+            assert torch.allclose(u, torch.full_like(u, total / world)), f"{algo} plain n={n - 1}"
+            del t
+    comm.algo = "auto"
+    for dt in (torch.bfloat16, torch.float16, torch.float64, torch.int32, torch.int64):
+        v = torch.ones(777, dtype=dt, device=dev) * (rank + 1)
+        dist.all_reduce(v)
+        assert torch.equal(v, torch.ones(777, dtype=dt, device=dev) * total), str(dt)
+    m = torch.tensor([float(rank)], device=dev)
+    dist.all_reduce(m, dist.ReduceOp.MAX)
+    assert m.item() == world - 1
+    # bitwise identical on every rank for random data, every algorithm
+    sums = {}
+    for algo in algos:
+        comm.algo = algo
+        g = torch.Generator(device=dev).manual_seed(rank)
+        r = comm.alloc_flat(1 << 18, torch.float32, dev)
+        r.copy_(torch.randn(1 << 18, device=dev, generator=g))
+        dist.all_reduce(r)
+        sums[algo] = r.view(torch.int32).sum().item()
+    comm.algo = "auto"
+    for root in range(world):
+        b = torch.arange(1001, device=dev, dtype=torch.float32) + 7 * root if rank == root else torch.zeros(1001, device=dev)
+        dist.broadcast(b, root)
+        assert torch.equal(b, torch.arange(1001, device=dev, dtype=torch.float32) + 7 * root)
+    nb = torch.zeros(3, dtype=torch.int64, device=dev) + (rank == 0) * 5
+    dist.broadcast(nb, 0)
+    assert nb.tolist() == [5, 5, 5]
+    o = torch.empty(world * 5, device=dev)
+    dist.all_gather_into_tensor(o, torch.full((5,), float(rank), device=dev))
+    assert torch.equal(o, torch.arange(world, device=dev, dtype=torch.float32).repeat_interleave(5))
+    a2a = torch.empty(world * 2, device=dev)
+    dist.all_to_all_single(a2a, (torch.arange(world * 2, device=dev) // 2 + 10 * rank).float())
+    assert torch.equal(a2a, torch.tensor([10.0 * r + rank for r in range(world) for _ in range(2)], device=dev))
+    dist.barrier()
+    torch.cuda.synchronize()
+    info["sums"] = sums
+    info["status"] = comm.status()
+    return info
+
+
+def test_symm_collectives():
+    w = _world()
+    res = run_ranks(_collectives, w, backend="nccl")
+    for algo in res[0]["sums"]:
+        assert len({r["sums"][algo] for r in res}) == 1, f"{algo}: results differ between ranks"
+    assert all(r["status"] == 0 for r in res)
+    print(res[0]["desc"])
+
+
+def _vs_nccl(rank, world):
+    """Same inputs through SymmComm and through the libnccl binding."""
+    dev = torch.device("cuda", rank)
+    g = dist.get_default_group()
+    ref = dist.new_group(comm="nccl")
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    out = []
+    for n in (29034, 1 << 16, 3_000_001):
+        x = torch.randn(n, device=dev, generator=gen)
+        a, b = x.clone(), x.clone()
+        dist.all_reduce(a, group=g)
+        dist.all_reduce(b, group=ref)
+        out.append((a - b).abs().max().item() / (b.abs().max().item() + 1e-9))
+    return out
+
+
+def test_allreduce_matches_nccl():
+    for errs in run_ranks(_vs_nccl, _world(), backend="nccl"):
+        assert max(errs) < 1e-5, errs
+
+
+def _data(rank, step, bs=100):
+    g = torch.Generator().manual_seed(1000 * step + rank)
+    return torch.rand(bs, 1, 28, 28, generator=g), torch.randint(0, 10, (bs,), generator=g)
+
+
+def _ddp_vs_torch(rank, world, syncbn, port):
+    import torch.distributed as td
+
+    dev = torch.device("cuda", rank)
+    torch.backends.cudnn.allow_tf32 = False
+    steps = 4
+    torch.manual_seed(0)
+    model = pdt.models.ConvNet()
+    if syncbn:
+        model = pdt.SyncBatchNorm.convert_sync_batchnorm(model)
+    model.to(dev)
+    opt = pdt.optim.SGD(model.parameters(), 0.05)
+    ddp = pdt.DistributedDataParallel(model, device_ids=[rank])
+    crit = pdt.nn.CrossEntropyLoss()
+    ours = []
+    for s in range(steps):
+        x, y = _data(rank, s)
+        loss = crit(ddp(x.to(dev)), y.to(dev))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ours.append(loss.item())
+    info = ddp._get_ddp_logging_data()
+    td.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
+    torch.manual_seed(0)
+    ref = pdt.models.ConvNet(fused=False)
+    if syncbn:
+        ref = nn.SyncBatchNorm.convert_sync_batchnorm(ref)
+    ref.to(dev)
+    ropt = torch.optim.SGD(ref.parameters(), 0.05)
+    rddp = nn.parallel.DistributedDataParallel(ref, device_ids=[rank])
+    theirs = []
+    for s in range(steps):
+        x, y = _data(rank, s)
+        loss = nn.functional.cross_entropy(rddp(x.to(dev)), y.to(dev))
+        ropt.zero_grad()
+        loss.backward()
+        ropt.step()
+        theirs.append(loss.item())
+    worst = 0.0
+    for (n, p), (_, q) in zip(ddp.module.named_parameters(), rddp.module.named_parameters()):
+        worst = max(worst, (p - q).abs().max().item() / (q.abs().max().item() + 1e-6))
+    bufw = 0.0
+    for (n, p), (_, q) in zip(ddp.module.named_buffers(), rddp.module.named_buffers()):
+        bufw = max(bufw, (p.float() - q.float()).abs().max().item())
+    flat = torch.cat([p.detach().reshape(-1) for p in ddp.parameters()])
+    td.destroy_process_group()
+    return {"ours": ours, "theirs": theirs, "param_rel": worst, "buf_abs": bufw, "psum": flat.double().sum().item(),
+            "copies": info["copies_into_bucket"], "buckets": info["bucket_sizes"]}
+
+
+@pytest.mark.parametrize("syncbn", [False, True])
+def test_ddp_convnet_matches_torch_ddp_nccl(syncbn):
+    res = run_ranks(_ddp_vs_torch, _world(), syncbn, free_port(), backend="nccl")
+    assert len({r["psum"] for r in res}) == 1, "parameters diverged between ranks"
+    for r in res:
+        assert max(abs(a - b) for a, b in zip(r["ours"], r["theirs"])) < 5e-3, (r["ours"], r["theirs"])
+        assert r["param_rel"] < 5e-3 and r["buf_abs"] < 5e-3, r
+        assert r["copies"] == 0 and sum(r["buckets"]) == 116136
+
+
+def _graphed(rank, world, syncbn):
+    from pytorch_distributed_train_b200.engine import GraphedTrainStep
+
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)
+    model = pdt.models.ConvNet()
+    if syncbn:
+        model = pdt.SyncBatchNorm.convert_sync_batchnorm(model)
+    model.to(dev)
+    opt = pdt.optim.SGD(model.parameters(), 0.05)
+    ddp = pdt.DistributedDataParallel(model, device_ids=[rank])
+    crit = pdt.nn.CrossEntropyLoss()
+    x, y = _data(rank, 0)
+    step = GraphedTrainStep(ddp, crit, opt, (x.to(dev), y.to(dev)))
+    losses = []
+    for s in range(50):
+        x, y = _data(rank, s % 5)
+        losses.append(step(x.pin_memory(), y.pin_memory()).item())
+    flat = torch.cat([p.detach().reshape(-1) for p in ddp.parameters()])
+    return losses[0], losses[-1], flat.double().sum().item(), step.kernels_per_replay
+
+
+@pytest.mark.parametrize("syncbn", [False, True])
+def test_graph_captured_step_keeps_ranks_in_lockstep(syncbn):
+    res = run_ranks(_graphed, _world(), syncbn, backend="nccl")
+    assert len({r[2] for r in res}) == 1
+    assert all(r[1] < r[0] for r in res), res
+    print("kernels per replay:", res[0][3])

@@ -1,0 +1,255 @@
+"""Single-GPU numerics of every sm_100a kernel against a plain PyTorch fp32 reference of the same op
+(SURVEY §4.3 "GPU single-device kernel tests"; tolerance policy: TF32 level for the tensor-core
+convolution, fp32 level for everything else)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import pytorch_distributed_train_b200 as pdt
+from pytorch_distributed_train_b200 import _C, ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    # the oracle must be true fp32: no TF32 inside cuDNN/cuBLAS
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def test_native_runtime_is_loaded():
+    assert ops.native_available() and hasattr(_C, "SymmComm") and hasattr(_C, "gemm_tf32_tcgen05")
+    assert torch.cuda.get_device_capability(0)[0] == 10, "these kernels are built for sm_100a only"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 32), (128, 32, 416), (256, 16, 800), (19600, 32, 416), (1000, 64, 100), (77, 256, 64)])
+def test_gemm_tf32_tcgen05(M, N, K):
+    a = torch.randn(M, K, device=dev())
+    b = torch.randn(N, K, device=dev())
+    d = _C.gemm_tf32_tcgen05(a, b)
+    ref = a.double() @ b.double().t()
+    err = (d.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, f"tf32 gemm error {err} (scale {scale})"
+    # exactness on tf32-representable inputs: proves operand layout / descriptors, not just "close"
+    ai = torch.randint(-4, 5, (M, K), device=dev()).float()
+    bi = torch.randint(-4, 5, (N, K), device=dev()).float()
+    assert torch.equal(_C.gemm_tf32_tcgen05(ai, bi), ai @ bi.t())
+
+
+@pytest.mark.parametrize("cin,cout,H,impl", [(1, 16, 28, "simt"), (16, 32, 14, "simt"), (16, 32, 14, "tcgen05")])
+@pytest.mark.parametrize("B", [100, 3])
+def test_conv5x5_forward_and_stats(cin, cout, H, impl, B):
+    x = torch.randn(B, cin, H, H, device=dev())
+    w = torch.randn(cout, cin, 5, 5, device=dev()) * 0.1
+    b = torch.randn(cout, device=dev())
+    y, stats = _C.conv5x5_fwd(nhwc(x), w, b, True, impl)
+    ref = F.conv2d(x, w, b, padding=2)
+    tol = 2e-2 if impl == "tcgen05" else 1e-4
+    assert torch.allclose(y.permute(0, 3, 1, 2), ref, atol=tol, rtol=tol), (y.permute(0, 3, 1, 2) - ref).abs().max()
+    yn = y.double()
+    assert torch.allclose(stats[:cout].double(), yn.sum((0, 1, 2)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[cout:2 * cout].double(), (yn * yn).sum((0, 1, 2)), rtol=1e-4, atol=1e-2)
+    assert stats[2 * cout].item() == B * H * H
+    # deterministic: bitwise identical on a second run
+    y2, stats2 = _C.conv5x5_fwd(nhwc(x), w, b, True, impl)
+    assert torch.equal(y, y2) and torch.equal(stats, stats2)
+
+
+def test_conv_tcgen05_exact_on_small_integers():
+    x = torch.randint(-3, 4, (5, 16, 14, 14), device=dev()).float()
+    w = torch.randint(-2, 3, (32, 16, 5, 5), device=dev()).float()
+    y, _ = _C.conv5x5_fwd(nhwc(x), w, None, False, "tcgen05")
+    assert torch.equal(y.permute(0, 3, 1, 2), F.conv2d(x, w, padding=2))
+    dy = torch.randint(-3, 4, (5, 32, 14, 14), device=dev()).float()
+    dx = _C.conv5x5_dgrad(nhwc(dy), w, "tcgen05")
+    ref = torch.autograd.grad(F.conv2d(x.requires_grad_(), w, padding=2), x, dy)[0]
+    assert torch.equal(dx.permute(0, 3, 1, 2), ref)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+def test_conv5x5_backward(impl):
+    B = 100
+    x = torch.randn(B, 16, 14, 14, device=dev(), requires_grad=True)
+    w = (torch.randn(32, 16, 5, 5, device=dev()) * 0.1).requires_grad_()
+    b = torch.randn(32, device=dev(), requires_grad=True)
+    dy = torch.randn(B, 32, 14, 14, device=dev())
+    gx, gw, gb = torch.autograd.grad(F.conv2d(x, w, b, padding=2), (x, w, b), dy)
+    dx = _C.conv5x5_dgrad(nhwc(dy), w.detach(), impl)
+    tol = 3e-2 if impl == "tcgen05" else 2e-4
+    assert torch.allclose(dx.permute(0, 3, 1, 2), gx, atol=tol, rtol=tol)
+    dw, db = torch.empty_like(w), torch.empty_like(b)
+    _C.conv5x5_wgrad(nhwc(dy), nhwc(x.detach()), dw, db, impl)
+    assert torch.allclose(dw, gw, atol=2e-3, rtol=1e-3), (dw - gw).abs().max()
+    assert torch.allclose(db, gb, atol=2e-3, rtol=1e-4)
+    # conv1 weight gradient (no data gradient: the input needs none)
+    x1 = torch.randn(B, 1, 28, 28, device=dev())
+    w1 = torch.randn(16, 1, 5, 5, device=dev(), requires_grad=True)
+    b1 = torch.randn(16, device=dev(), requires_grad=True)
+    dy1 = torch.randn(B, 16, 28, 28, device=dev())
+    gw1, gb1 = torch.autograd.grad(F.conv2d(x1, w1, b1, padding=2), (w1, b1), dy1)
+    dw1, db1 = torch.empty_like(w1), torch.empty_like(b1)
+    _C.conv5x5_wgrad(nhwc(dy1), nhwc(x1), dw1, db1, "simt")
+    assert torch.allclose(dw1, gw1, atol=5e-3, rtol=1e-3) and torch.allclose(db1, gb1, atol=5e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("C,H,out_nchw", [(16, 28, False), (32, 14, True)])
+def test_bn_relu_pool_forward_backward(C, H, out_nchw):
+    B = 100
+    y = torch.randn(B, C, H, H, device=dev()) * 2 + 0.5
+    gamma = torch.rand(C, device=dev()) + 0.5
+    beta = torch.randn(C, device=dev()) * 0.1
+    bn = nn.BatchNorm2d(C).to(dev())
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    yr = y.clone().requires_grad_()
+    ref = F.max_pool2d(F.relu(bn(yr)), 2, 2)
+    yh = nhwc(y)
+    stats = torch.cat([yh.sum((0, 1, 2)), (yh * yh).sum((0, 1, 2)), yh.new_full((1,), B * H * H)])
+    rm, rv, nbt = torch.zeros(C, device=dev()), torch.ones(C, device=dev()), torch.zeros((), dtype=torch.int64, device=dev())
+    out, saved = _C.bn_relu_pool_fwd(yh, stats, gamma, beta, rm, rv, nbt, 0.1, 1e-5, out_nchw)
+    got = out if out_nchw else out.permute(0, 3, 1, 2)
+    assert torch.allclose(got, ref, atol=2e-4, rtol=1e-4), (got - ref).abs().max()
+    assert torch.allclose(rm, bn.running_mean, atol=1e-5) and torch.allclose(rv, bn.running_var, atol=1e-4) and int(nbt) == 1
+    dout = torch.randn_like(ref)
+    ref.backward(dout)
+    d = dout.contiguous() if out_nchw else nhwc(dout)
+    sums, dgamma, dbeta = _C.bn_relu_pool_bwd_reduce(d, yh, saved, gamma, beta, out_nchw)
+    assert torch.allclose(dgamma, bn.weight.grad, atol=2e-2, rtol=1e-3) and torch.allclose(dbeta, bn.bias.grad, atol=2e-2, rtol=1e-3)
+    dy = _C.bn_relu_pool_bwd_apply(d, yh, saved, gamma, beta, sums, stats[2 * C:], out_nchw)
+    assert torch.allclose(dy.permute(0, 3, 1, 2), yr.grad, atol=2e-4, rtol=1e-3), (dy.permute(0, 3, 1, 2) - yr.grad).abs().max()
+
+
+def test_linear_and_cross_entropy():
+    B, K, N = 100, 1568, 10
+    x = torch.randn(B, K, device=dev(), requires_grad=True)
+    lin = nn.Linear(K, N).to(dev())
+    t = torch.randint(0, N, (B,), device=dev())
+    ref_loss = F.cross_entropy(lin(x), t)
+    gx, gw, gb = torch.autograd.grad(ref_loss, (x, lin.weight, lin.bias))
+    x2 = x.detach().clone().requires_grad_()
+    w2, b2 = lin.weight.detach().clone().requires_grad_(), lin.bias.detach().clone().requires_grad_()
+    loss = ops.cross_entropy(ops.linear(x2, w2, b2), t)
+    assert torch.allclose(loss, ref_loss, atol=1e-5)
+    loss.backward()
+    assert torch.allclose(x2.grad, gx, atol=1e-6, rtol=1e-4)
+    assert torch.allclose(w2.grad, gw, atol=1e-5, rtol=1e-4) and torch.allclose(b2.grad, gb, atol=1e-6, rtol=1e-4)
+    crit = pdt.nn.CrossEntropyLoss()
+    assert torch.allclose(crit(lin(x).detach(), t), ref_loss.detach(), atol=1e-5)
+
+
+@pytest.mark.parametrize("momentum,nesterov,wd", [(0.0, False, 0.0), (0.9, False, 1e-3), (0.9, True, 0.0)])
+def test_fused_sgd_matches_torch(momentum, nesterov, wd):
+    shapes = [(16, 1, 5, 5), (16,), (32, 16, 5, 5), (10, 1568), (10,)]
+    ps = [torch.randn(s, device=dev()) for s in shapes]
+    ours = [p.clone().requires_grad_() for p in ps]
+    ref = [p.clone().requires_grad_() for p in ps]
+    o1 = pdt.optim.SGD(ours, lr=0.05, momentum=momentum, nesterov=nesterov, weight_decay=wd)
+    o2 = torch.optim.SGD(ref, lr=0.05, momentum=momentum, nesterov=nesterov, weight_decay=wd)
+    for step in range(3):
+        for a, b in zip(ours, ref):
+            g = torch.randn_like(a)
+            a.grad, b.grad = g.clone(), g.clone()
+        o1.step()
+        o2.step()
+    for a, b in zip(ours, ref):
+        assert torch.allclose(a, b, atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("syncbn_module", [False, True])
+def test_convnet_fused_matches_unfused(syncbn_module):
+    torch.manual_seed(1)
+    ref = pdt.models.ConvNet(fused=False).to(dev())
+    net = pdt.models.ConvNet(fused=True).to(dev())
+    net.load_state_dict(ref.state_dict())
+    if syncbn_module:  # world of one: SyncBatchNorm must degrade to local statistics
+        net = pdt.SyncBatchNorm.convert_sync_batchnorm(net)
+    x = torch.rand(100, 1, 28, 28, device=dev())
+    t = torch.randint(0, 10, (100,), device=dev())
+    l_ref = F.cross_entropy(ref(x), t)
+    l_ref.backward()
+    l = pdt.nn.CrossEntropyLoss()(net(x), t)
+    l.backward()
+    assert torch.allclose(l, l_ref, atol=2e-3), (l.item(), l_ref.item())
+    for (n1, p1), (_, p2) in zip(net.named_parameters(), ref.named_parameters()):
+        scale = p2.grad.abs().max().item() + 1e-6
+        assert (p1.grad - p2.grad).abs().max().item() <= 3e-2 * scale + 1e-4, n1
+    for (n1, b1), (_, b2) in zip(net.named_buffers(), ref.named_buffers()):
+        assert torch.allclose(b1.float(), b2.float(), atol=2e-3, rtol=1e-3), n1
+    net.eval(), ref.eval()
+    assert torch.allclose(net(x), ref(x), atol=3e-2, rtol=1e-2)
+
+
+def test_generic_bn_kernels_match_torch():
+    x = torch.randn(8, 12, 9, 7, device=dev()) * 3 + 1
+    st = ops.bn_local_stats(x)
+    assert torch.allclose(st[:12], x.sum((0, 2, 3)), rtol=1e-4, atol=1e-3) and st[24].item() == 8 * 63
+    mean = x.mean((0, 2, 3))
+    invstd = (x.var((0, 2, 3), unbiased=False) + 1e-5).rsqrt()
+    w, b = torch.rand(12, device=dev()) + 0.5, torch.randn(12, device=dev())
+    xr = x.clone().requires_grad_()
+    ref = F.batch_norm(xr, None, None, w, b, True, 0.0, 1e-5)
+    assert torch.allclose(ops.bn_apply(x, mean, invstd, w, b), ref, atol=1e-4, rtol=1e-4)
+    dy = torch.randn_like(x)
+    ref.backward(dy)
+    red = ops.bn_backward_reduce(dy, x, mean, invstd)
+    n = 8 * 63
+    dx = ops.bn_backward_apply(dy, x, mean, invstd, w, red[:12] / n, red[12:24] / n)
+    assert torch.allclose(dx, xr.grad, atol=1e-4, rtol=1e-3)
+
+
+def _one_rank_group():
+    from mp_helpers import free_port
+
+    pdt.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{free_port()}", world_size=1, rank=0)
+
+
+def test_single_gpu_ddp_and_graphed_step():
+    """One process, one GPU: the whole product path (SymmComm heap, reducer, fused ops, CUDA graph)."""
+    torch.cuda.set_device(0)
+    _one_rank_group()
+    try:
+        g = pdt.distributed.get_default_group()
+        assert g.comm.backend_name == "nvlink" and "SymmComm" in g.comm.describe()
+        torch.manual_seed(0)
+        model = pdt.models.ConvNet().to(dev())
+        opt = pdt.optim.SGD(model.parameters(), 1e-2)
+        ddp = pdt.DistributedDataParallel(model, device_ids=[0])
+        assert ddp.param_arena is not None and g.comm.is_symmetric(ddp.param_arena)
+        crit = pdt.nn.CrossEntropyLoss()
+        x = torch.rand(100, 1, 28, 28, device=dev())
+        t = torch.randint(0, 10, (100,), device=dev())
+        eager = []
+        for _ in range(3):
+            loss = crit(ddp(x), t)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            eager.append(loss.item())
+        assert eager[2] < eager[0]
+        info = ddp._get_ddp_logging_data()
+        assert info["copies_into_bucket"] == 0, "gradients must be produced in place inside the bucket"
+        assert ddp.reducer.grads_are_views()
+        from pytorch_distributed_train_b200.engine import GraphedTrainStep
+
+        step = GraphedTrainStep(ddp, crit, opt, (x, t))
+        l0 = step(x, t).item()
+        l1 = step(x, t).item()
+        assert l1 < l0 < eager[2] + 1e-3
+    finally:
+        pdt.destroy_process_group()
