@@ -190,7 +190,7 @@ def run_ours(args):
             "gpu_launches": int(gpu_launches),
             "gpu_launches_per_step": launches_per_step if launches_per_step is not None else eager_launches / K,
             "clocks": clock_block(clocks),
-            "final_loss": float(last["loss"]),
+            "final_loss": float(last["loss"].detach()),
         }
         if e2e is not None:
             out["e2e"] = {"value": imgs / (e2e["ms"] / 1e3), "unit": "images/s", "ms_per_step": e2e["ms"] / K,
@@ -274,7 +274,7 @@ def run_reference(args):
         t = torch.tensor([a.elapsed_time(b)], device=dev)
         dist.all_reduce(t, dist.ReduceOp.MAX)
         ms_dev = float(t.item())
-        final_loss = float(loss)
+        final_loss = float(loss.detach())
         del model, optimizer
         dist.destroy_process_group()
 

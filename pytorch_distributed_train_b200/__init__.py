@@ -33,6 +33,10 @@ def _load_native():
 import torch as _torch  # noqa: E402  (libtorch must be loaded before _C.so)
 
 _C = _load_native()
+if hasattr(_C, "_mark_exiting"):
+    import atexit as _atexit
+
+    _atexit.register(_C._mark_exiting)
 
 from . import data, distributed, launcher, models, nn, ops, optim, parallel, utils  # noqa: E402
 from .data import DataLoader, DistributedSampler  # noqa: E402

@@ -46,7 +46,7 @@ struct Scratch {
 };
 ReduceScratch scratch(const at::Tensor& like) {
   static std::mutex mu;
-  static std::map<int, Scratch> per_dev;
+  static auto& per_dev = *new std::map<int, Scratch>();  // leaked on purpose: CUDA tensors must not die at static teardown
   std::lock_guard<std::mutex> g(mu);
   const int dev = like.device().index();
   auto it = per_dev.find(dev);
@@ -79,6 +79,7 @@ ConvShape conv_shape(const at::Tensor& x_nhwc, const at::Tensor& w) {
 
 void register_cuda_bindings(py::module_& m) {
   m.attr("ops_ready") = true;
+  m.def("_mark_exiting", [] { mark_process_exiting(); });
   m.def("kernel_launch_count", [] { return kernel_launch_count(); },
         "number of kernels this library has launched (or recorded into CUDA graphs) so far");
   m.def("nccl_available", [] { return NcclComm::available(); });

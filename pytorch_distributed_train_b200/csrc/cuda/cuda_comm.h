@@ -82,7 +82,7 @@ class SymmComm : public CudaCommBase {
 
  private:
   void do_allreduce(at::Tensor& t, ReduceOp op, double scale, int channel, cudaStream_t s);
-  std::unique_ptr<SymmetricHeap> heap_;
+  std::shared_ptr<SymmetricHeap> heap_;  // shared with every tensor carved out of it (see alloc_flat)
   std::string algo_ = "auto";   // auto | oneshot | oneshot_mc | twoshot | nvls
   size_t oneshot_max_ = 512 * 1024;
   SymmLaunchCfg cfg_;

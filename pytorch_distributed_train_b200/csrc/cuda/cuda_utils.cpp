@@ -63,6 +63,9 @@ const DriverApi& driver() {
 }
 
 static std::atomic<long long> g_launches{0};
+static std::atomic<bool> g_exiting{false};
+void mark_process_exiting() { g_exiting.store(true); }
+bool process_exiting() { return g_exiting.load(); }
 void count_kernel_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long kernel_launch_count() { return g_launches.load(std::memory_order_relaxed); }
 

@@ -52,7 +52,7 @@ std::shared_ptr<CommWork> CudaCommBase::enqueue(const std::vector<at::Tensor>& t
 SymmComm::SymmComm(std::shared_ptr<Store> store, int rank, int size, int device, Millis timeout, size_t heap_bytes)
     : CudaCommBase(rank, size, device) {
   c10::cuda::CUDAGuard guard(device);
-  heap_ = std::make_unique<SymmetricHeap>(std::move(store), rank, size, device, heap_bytes, timeout);
+  heap_ = std::make_shared<SymmetricHeap>(std::move(store), rank, size, device, heap_bytes, timeout);
   if (const char* a = getenv("PDT_AR_ALGO")) algo_ = a;
   if (const char* m = getenv("PDT_AR_ONESHOT_MAX")) oneshot_max_ = static_cast<size_t>(atoll(m));
   if (const char* b = getenv("PDT_AR_BLOCKS")) cfg_.blocks = atoi(b);
@@ -80,8 +80,8 @@ at::Tensor SymmComm::alloc_flat(int64_t numel, at::ScalarType dtype, const at::D
   TORCH_CHECK(device.is_cuda() && device.index() == device_, "alloc_flat: device mismatch");
   const size_t nbytes = static_cast<size_t>(std::max<int64_t>(numel, 1)) * c10::elementSize(dtype);
   void* p = heap_->alloc(nbytes, 256);
-  SymmetricHeap* heap = heap_.get();
-  // NOTE: tensors from the heap must not outlive the communicator.
+  // the tensor co-owns the heap: parameters/buckets may outlive the communicator object
+  std::shared_ptr<SymmetricHeap> heap = heap_;
   at::Tensor t = at::from_blob(p, {numel}, [heap, p](void*) { heap->free(p); }, at::TensorOptions().dtype(dtype).device(device));
   t.zero_();
   return t;

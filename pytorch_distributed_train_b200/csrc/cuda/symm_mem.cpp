@@ -79,6 +79,7 @@ SymmetricHeap::SymmetricHeap(std::shared_ptr<Store> store, int rank, int world, 
 }
 
 SymmetricHeap::~SymmetricHeap() {
+  if (process_exiting()) return;  // interpreter shutdown: the driver reclaims everything
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   if (epochs_) cudaFree(epochs_);

@@ -41,18 +41,23 @@ class GraphedTrainStep:
 
     def _capture(self, warmup: int):
         dev = self.static_inputs[0].device
+        from .. import _C
+
         side = torch.cuda.Stream(device=dev)
+        self.capture_stream = side
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
+            # AccumulateGrad nodes run on the stream they were created on: give the reducer (which
+            # pins them) a fresh start on the stream that will be captured
+            if hasattr(self.model, "_reset_reducer"):
+                self.model._reset_reducer()
             for _ in range(max(warmup, 2)):  # ≥2: the reducer rebuilds its buckets after iteration 1
                 self._eager_step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        from .. import _C
-
         self.graph = torch.cuda.CUDAGraph()
         before = _C.kernel_launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.static_loss = self._eager_step()
         # how many of *our* kernels one replay runs (ATen glue kernels are not counted)
         self.kernels_per_replay = int(_C.kernel_launch_count() - before)

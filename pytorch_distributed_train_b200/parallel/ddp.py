@@ -278,6 +278,26 @@ class DistributedDataParallel(nn.Module):
         self._rebuild_checked = False
         self._publish_grad_views()
 
+    def _reset_reducer(self):
+        """Re-create the native reducer (and with it the parameters' AccumulateGrad nodes) under the
+        *current* CUDA stream.  Autograd runs an AccumulateGrad node on the stream it was created
+        on; a whole-step CUDA graph is captured on a side stream, so the nodes must be born there
+        (the reference's DDP has the same constraint: "DDP must be constructed on the capture stream")."""
+        st = self.reducer.stats()
+        layout, rebuilt = st["bucket_indices"], st["has_rebuilt_buckets"]
+        for p in self._params:
+            p.grad = None
+            if hasattr(p, "_pdt_grad_view"):
+                del p._pdt_grad_view
+        del self.reducer
+        self.reducer = _C.Reducer([p for p in self._params], layout, self.comm, self.bucket_bytes_cap,
+                                  self.first_bucket_bytes_cap, self.find_unused_parameters,
+                                  self.gradient_as_bucket_view, self.static_graph)
+        if rebuilt:
+            self.reducer.apply_rebuild(layout)
+            self._rebuild_checked = True
+        self._publish_grad_views()
+
     def _publish_grad_views(self):
         """Let our backward kernels write weight gradients straight into the bucket (ops.functional._grad_dst)."""
         if not self.gradient_as_bucket_view:
