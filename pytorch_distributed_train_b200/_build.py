@@ -63,6 +63,35 @@ def _headers_digest() -> str:
     return h.hexdigest()
 
 
+_INC_RE = None
+
+
+def _deps_digest(src: Path, _cache={}) -> str:
+    """Hash of every project header the TU includes (transitively, quoted includes only)."""
+    global _INC_RE
+    import re
+
+    if _INC_RE is None:
+        _INC_RE = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+    seen, stack = set(), [src]
+    while stack:
+        f = stack.pop()
+        for inc in _INC_RE.findall(f.read_text()):
+            for base in (f.parent, CSRC):
+                cand = (base / inc).resolve()
+                if cand.exists() and cand not in seen:
+                    seen.add(cand)
+                    stack.append(cand)
+                    break
+    h = hashlib.sha256()
+    for p in sorted(seen):
+        if p not in _cache:
+            _cache[p] = hashlib.sha256(p.read_bytes()).hexdigest()
+        h.update(str(p).encode())
+        h.update(_cache[p].encode())
+    return h.hexdigest()
+
+
 def _needs_torch(src: Path) -> bool:
     txt = src.read_text()
     return ("ATen/" in txt) or ("torch/" in txt) or ("c10/" in txt) or ("comm/comm.h" in txt) or ("reducer.h" in txt)
@@ -80,7 +109,7 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
     t0 = time.time()
     BUILD.mkdir(parents=True, exist_ok=True)
     cpp, cu = _sources()
-    hdr = _headers_digest()
+    _ = _headers_digest  # (kept for tooling; object keys use per-TU dependency digests)
     tinc, tlib = _torch_paths()
     pyinc = sysconfig.get_paths()["include"]
     common_inc = [f"-I{CSRC}", f"-I{CUDA_HOME}/include"]
@@ -103,7 +132,7 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
 
     objs, todo, keys = [], [], []
     for src, cmd in jobs:
-        key = hashlib.sha256((src.read_text() + "\0" + " ".join(cmd) + "\0" + hdr).encode()).hexdigest()[:20]
+        key = hashlib.sha256((src.read_text() + "\0" + " ".join(cmd) + "\0" + _deps_digest(src)).encode()).hexdigest()[:20]
         keys.append(key)
         obj = BUILD / f"{src.relative_to(CSRC).as_posix().replace('/', '__')}.{key}.o"
         objs.append(obj)

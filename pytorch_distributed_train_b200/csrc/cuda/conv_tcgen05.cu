@@ -268,12 +268,17 @@ template <int CK, int NOUT>
 struct ConvCfg {
   static constexpr int kTapsPerChunk = kChunkK / CK;                           // 2 (fwd) / 1 (dgrad)
   static constexpr int kChunks = (25 + kTapsPerChunk - 1) / kTapsPerChunk;     // 13 / 25
-  static constexpr int kStages = 4;
-  static constexpr int kLag = kStages - 1;
+  // 8 smem stages but only 3 cp.async groups in flight per thread: a chunk is signalled "full"
+  // kLag iterations after it was issued, so stages - kLag is the slack the MMA warp has to drain a
+  // stage before the producers need it back (4 stages / lag 3 left a slack of one stage and the
+  // mainloop ran at ~1.8k cycles per chunk — profiles/conv_umma_v1.md).
+  static constexpr int kStages = 8;
+  static constexpr int kLag = 3;
   static constexpr int kBChunkBytes = NOUT * 128;
   static constexpr int kTmemCols = 32;
   static constexpr int kThreads = 192;                                         // 4 producer/epilogue warps + MMA warp + TMA warp
-  static constexpr size_t kSmem = 1024 + kStages * kStageBytes + kChunks * kBChunkBytes + kTileM * 128 + 1024;
+  // alignment slack + A ring + resident B + output staging + (barriers, tmem slot, stat partials)
+  static constexpr size_t kSmem = 1024 + kStages * kStageBytes + kChunks * kBChunkBytes + kTileM * 128 + 2048;
 };
 
 template <int CK, int NOUT, bool FWD>
@@ -479,6 +484,208 @@ __global__ void __launch_bounds__(192, 1) conv5x5_umma_kernel(const float* __res
   if (warp == 4) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
+// =====================================================================================================
+// conv2 weight gradient on tcgen05:   dWᵀ[m = tap·16+ci][co] = Σ_pixels xcol[p][m] · dy[p][co]
+//
+// The reduction runs over output pixels, i.e. over the *slow* dimension of both operands, so both
+// are fed to the tensor core MN-major (the 128-byte swizzle atom is 8 pixels × 32 contiguous
+// M/N values):
+//   A = im2col(x)   [128 pixels][128 of the 416 im2col columns]  gathered by cp.async (zero fill)
+//   B = dy tile     [128 pixels][32 channels]                    one TMA box per tile
+// M = 416 is covered by four 128-row accumulators living in TMEM for the CTA's whole lifetime
+// (persistent split-K over pixel tiles); column 400 of the im2col is a column of ones, so the
+// bias gradient Σ_p dy[p][co] falls out of the same MMAs.  Each CTA deposits one partial
+// [416][32]; wgrad_fold_kernel sums the ≤148 partials in CTA order (deterministic) and scatters
+// into torch's [co][ci][5][5] layout.
+// =====================================================================================================
+struct WgradCfg {
+  static constexpr int kMUsed = 416;                  // 25 taps × 16 ch, + ones column (400), + pad
+  static constexpr int kMTiles = 4;
+  static constexpr int kHalfPix = 64;                 // pixels per A stage
+  static constexpr int kStages = 4, kLag = 1;
+  static constexpr int kAStageBytes = 4 * 8 * 1024;   // [4 MN atoms][8 K blocks][8 rows][128 B]
+  static constexpr int kBStages = 2, kBStageBytes = kTileM * 128;
+  static constexpr int kTmemCols = 128;
+  static constexpr int kThreads = 192;
+  static constexpr size_t kSmem = 1024 + kStages * kAStageBytes + kBStages * kBStageBytes + 1024;
+};
+
+// MN-major SWIZZLE_128B descriptor: LBO = byte stride between 32-element MN atoms, SBO = byte stride
+// between 8-row K atoms.  [cf. make_umma_desc<Major::MN>, cute/atom/mma_traits_sm100.hpp]
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(192, 1) conv5x5_wgrad_umma_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap tm_dy,
+                                                                    const float* __restrict__ ones, float* __restrict__ partials, int B,
+                                                                    int H, int W, int num_tiles) {
+  using Cfg = WgradCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;
+  uint8_t* sb = sa + Cfg::kStages * Cfg::kAStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb + Cfg::kBStages * Cfg::kBStageBytes);
+  uint64_t* afull = bars;
+  uint64_t* aempty = afull + Cfg::kStages;
+  uint64_t* bfull = aempty + Cfg::kStages;
+  uint64_t* bempty = bfull + Cfg::kBStages;
+  uint64_t* acc_full = bempty + Cfg::kBStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int M = B * H * W;
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_dy);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&afull[s], 128); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int s = it % Cfg::kBStages;
+        mbar_wait(&bempty[s], ((it / Cfg::kBStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bfull[s], Cfg::kBStageBytes);
+        tma_load_2d(sb + s * Cfg::kBStageBytes, &tm_dy, &bfull[s], 0, tile * kTileM);   // rows ≥ M arrive as zeros
+      }
+    }
+  } else if (warp == 4) {
+    constexpr uint32_t idesc = umma_idesc_tf32(kTileM, 32) | (1u << 15) | (1u << 16);  // A and B are MN-major
+    int g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int bs = it % Cfg::kBStages;
+      mbar_wait(&bfull[bs], (it / Cfg::kBStages) & 1);
+      for (int mt = 0; mt < Cfg::kMTiles; ++mt) {
+        for (int h = 0; h < 2; ++h, ++g) {
+          const int s = g % Cfg::kStages;
+          mbar_wait(&afull[s], (g / Cfg::kStages) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a0 = smem_u32(sa + s * Cfg::kAStageBytes), b0 = smem_u32(sb + bs * Cfg::kBStageBytes) + h * 8 * 1024;
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb)
+              umma_tf32(tmem_base + mt * 32, umma_desc_mn_sw128(a0 + kb * 1024, 8 * 1024, 1024), umma_desc_mn_sw128(b0 + kb * 1024, 1024, 1024),
+                        idesc, (it | h | kb) != 0);
+            umma_commit(&aempty[s]);
+            if (mt == Cfg::kMTiles - 1 && h == 1) umma_commit(&bempty[bs]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
+  } else {
+    // ---- producers: im2col gather, 64 pixels × 128 columns per stage -------------------------------------
+    const int u = tid & 31;                 // 16-byte unit inside the 128-column row: tap_local = u/4, channels 4(u%4)..
+    const int tap_local = u >> 2, c4 = (u & 3) * 4;
+    const uint32_t unit_off = static_cast<uint32_t>(tap_local >> 1) * 8192u;
+    const int chunk = ((tap_local & 1) << 2) | (c4 >> 2);
+    int g = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int mt = 0; mt < Cfg::kMTiles; ++mt) {
+        const int tap = mt * 8 + tap_local;
+        const int kh = tap / 5 - 2, kw = tap % 5 - 2;
+        for (int h = 0; h < 2; ++h, ++g) {
+          const int s = g % Cfg::kStages;
+          mbar_wait(&aempty[s], ((g / Cfg::kStages) & 1) ^ 1);
+          const uint32_t stage = smem_u32(sa + s * Cfg::kAStageBytes) + unit_off;
+#pragma unroll 4
+          for (int j = 0; j < 16; ++j) {
+            const int r = (tid >> 5) + 4 * j;                  // pixel row inside the 64-pixel half
+            const int p = tile * kTileM + h * Cfg::kHalfPix + r;
+            const float* src = x;
+            uint32_t bytes = 0;
+            if (p < M) {
+              if (tap < 25) {
+                const int ow = p % W, oh = (p / W) % H, n = p / (W * H);
+                const int ih = oh + kh, iw = ow + kw;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+                  src = x + ((static_cast<size_t>(n) * H + ih) * W + iw) * 16 + c4;
+                  bytes = 16;
+                }
+              } else if (tap == 25 && c4 == 0) {
+                src = ones;  // {1,0,0,0}: im2col column 400 ≡ 1 → row 400 of dWᵀ is the bias gradient
+                bytes = 16;
+              }
+            }
+            cp_async_16(stage + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4), src, bytes);
+          }
+          cp_async_commit();
+          if (g >= Cfg::kLag) {
+            cp_async_wait<Cfg::kLag>();
+            fence_proxy_async_smem();
+            mbar_arrive(&afull[(g - Cfg::kLag) % Cfg::kStages]);
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+#pragma unroll
+    for (int q = Cfg::kLag; q >= 1; --q) mbar_arrive(&afull[(g - q) % Cfg::kStages]);
+    // ---- epilogue: four accumulators → this CTA's partial [416][32] --------------------------------------
+    mbar_wait(acc_full, 0);
+    __syncwarp();
+    tc_fence_after();
+    for (int mt = 0; mt < Cfg::kMTiles; ++mt) {
+      const int m = mt * kTileM + tid;
+      float v[32];
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float t[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + mt * 32 + c0, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c0 + j] = t[j];
+      }
+      if (m < Cfg::kMUsed) {
+        float* o = partials + (static_cast<size_t>(blockIdx.x) * Cfg::kMUsed + m) * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// dw[co][ci][tap] = Σ_cta partial[cta][tap*16+ci][co];  db[co] = Σ_cta partial[cta][400][co]
+__global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ dw,
+                                                         float* __restrict__ db) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = t >> 5, co = t & 31;
+  if (m > 400) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const float* p = partials + static_cast<size_t>(m) * 32 + co;
+  const size_t stride = static_cast<size_t>(WgradCfg::kMUsed) * 32;
+  int c = 0;
+  for (; c + 4 <= nparts; c += 4) {   // four independent loads in flight; summation order stays fixed
+    s0 += p[(c + 0) * stride];
+    s1 += p[(c + 1) * stride];
+    s2 += p[(c + 2) * stride];
+    s3 += p[(c + 3) * stride];
+  }
+  for (; c < nparts; ++c) s0 += p[c * stride];
+  const float s = (s0 + s1) + (s2 + s3);
+  if (m < 400) dw[(co * 16 + (m & 15)) * 25 + (m >> 4)] = s;
+  else if (db) db[co] = s;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -573,6 +780,36 @@ void launch_conv5x5_dgrad_tcgen05(const float* dy, const float* w, float* dx, Co
   const int grid = std::min(tiles, sm_count());
   kern<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(dy, tm_b, tm_b, nullptr, dx, nullptr, ReduceScratch{}, s.B, s.H, s.W, tiles);
   check_launch("conv5x5_umma(dgrad)");
+}
+
+void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, float* db, ConvShape s, ReduceScratch scr, cudaStream_t st) {
+  if (!conv_tcgen05_supported(s)) throw std::invalid_argument("conv5x5 tcgen05 wgrad: only 16→32 channels are implemented");
+  using Cfg = WgradCfg;
+  const int M = s.B * s.H * s.W;
+  const int tiles = (M + kTileM - 1) / kTileM;
+  const int grid = std::min(tiles, sm_count());
+  if (static_cast<long long>(grid) * Cfg::kMUsed * 32 > scr.capacity_floats) throw std::invalid_argument("conv5x5 tcgen05 wgrad: scratch too small");
+  // {1,0,0,0}: source of the im2col "ones" column; written once per device, outside any graph capture
+  static std::mutex mu;
+  static std::map<int, bool> ones_ready;
+  float* ones = repack_buffer(2, 4);
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    if (!ones_ready[dev]) {
+      const float h[4] = {1.f, 0.f, 0.f, 0.f};
+      cudaError_t e = cudaMemcpy(ones, h, sizeof(h), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) throw std::runtime_error(std::string("cudaMemcpy(ones): ") + cudaGetErrorString(e));
+      ones_ready[dev] = true;
+    }
+  }
+  CUtensorMap tm_dy = make_tmap_2d(dy, 32, static_cast<uint64_t>(M), 32, kTileM);
+  opt_in_smem(conv5x5_wgrad_umma_kernel, Cfg::kSmem);
+  conv5x5_wgrad_umma_kernel<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(x, tm_dy, ones, scr.partials, s.B, s.H, s.W, tiles);
+  check_launch("conv5x5_wgrad_umma");
+  wgrad_fold_kernel<<<(401 * 32 + 255) / 256, 256, 0, st>>>(scr.partials, grid, dw, db);
+  check_launch("wgrad_fold");
 }
 
 void launch_gemm_tf32_tcgen05(const float* a, const float* b, float* d, int M, int N, int K, cudaStream_t st) {

@@ -146,8 +146,9 @@ void register_cuda_bindings(py::module_& m) {
     chk(dy, "dy"); chk(x, "x"); chk(dw, "dw");
     c10::cuda::CUDAGuard g(dy.device());
     ConvShape s = conv_shape(x, dw);
-    (void)impl;
-    launch_conv5x5_wgrad(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
+    const bool tc = impl == "tcgen05" || (impl == "auto" && conv_tcgen05_supported(s));
+    if (tc) launch_conv5x5_wgrad_tcgen05(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
+    else launch_conv5x5_wgrad(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
   }, py::arg("dy"), py::arg("x"), py::arg("dw"), py::arg("db") = py::none(), py::arg("impl") = "auto");
 
   // ---- BN + ReLU + pool ------------------------------------------------------------------------------

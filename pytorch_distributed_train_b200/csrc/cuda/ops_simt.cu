@@ -237,13 +237,31 @@ __global__ void __launch_bounds__(256) conv5x5_wgrad_kernel(const float* __restr
   }
 }
 
-__global__ void fold_partials_kernel(const float* __restrict__ partials, int nblk, int width, int split, float* out_a, float* out_b) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= width) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partials[static_cast<size_t>(b) * width + i];
-  if (i < split) out_a[i] = s;
-  else if (out_b) out_b[i - split] = s;
+// out[i] = Σ_b partials[b][i] in a fixed order: a CTA owns 32 outputs (lane = output), its 8 warps
+// stride over the partial rows (coalesced 128-byte reads), then the 8 sub-sums are added in warp order.
+__global__ void __launch_bounds__(256) fold_partials_kernel(const float* __restrict__ partials, int nblk, int width, int split,
+                                                            float* out_a, float* out_b) {
+  __shared__ float s_sub[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (i < width) {
+    int b = warp;
+    for (; b + 8 < nblk; b += 16) {
+      s0 += partials[static_cast<size_t>(b) * width + i];
+      s1 += partials[static_cast<size_t>(b + 8) * width + i];
+    }
+    if (b < nblk) s0 += partials[static_cast<size_t>(b) * width + i];
+  }
+  s_sub[warp][lane] = s0 + s1;
+  __syncthreads();
+  if (warp == 0 && i < width) {
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += s_sub[w8][lane];
+    if (i < split) out_a[i] = s;
+    else if (out_b) out_b[i - split] = s;
+  }
 }
 
 // =====================================================================================================
@@ -576,10 +594,14 @@ __global__ void __launch_bounds__(256) linear_bwd_kernel(const float* __restrict
     }
     return;
   }
-  // dw[n, k] = Σ_b dout[b, n] x[b, k] for a slab of k; batch in smem-sized chunks
+  // dw[n, k] = Σ_b dout[b, n] x[b, k]: a CTA owns a slab of 32 k-columns (lane = column); its 8 warps
+  // split the batch rows (8-way shorter dependency chain than one thread per column), the 8 sub-sums
+  // are folded in warp order.  Batch is staged through smem in chunks of BC rows.
   extern __shared__ float s_d[];  // [BC][N]
+  __shared__ float s_fold[8][NMAX][32];  // lane-contiguous: conflict-free stores and loads
   constexpr int BC = 128;
-  const int k = (blockIdx.x - dx_blocks) * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = (blockIdx.x - dx_blocks) * 32 + lane;
   float acc[NMAX];
 #pragma unroll
   for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
@@ -590,7 +612,7 @@ __global__ void __launch_bounds__(256) linear_bwd_kernel(const float* __restrict
     for (int i = threadIdx.x; i < nb * N; i += blockDim.x) s_d[i] = dout[static_cast<size_t>(b0) * N + i];
     __syncthreads();
     if (k < K) {
-      for (int b = 0; b < nb; ++b) {
+      for (int b = warp; b < nb; b += 8) {
         const float xv = x[static_cast<size_t>(b0 + b) * K + k];
 #pragma unroll
         for (int n = 0; n < NMAX; ++n)
@@ -600,10 +622,19 @@ __global__ void __launch_bounds__(256) linear_bwd_kernel(const float* __restrict
     if (static_cast<int>(blockIdx.x) == dx_blocks && threadIdx.x < N)
       for (int b = 0; b < nb; ++b) bsum += s_d[b * N + threadIdx.x];
   }
-  if (k < K) {
 #pragma unroll
-    for (int n = 0; n < NMAX; ++n)
-      if (n < N) dw[static_cast<size_t>(n) * K + k] = acc[n];
+  for (int n = 0; n < NMAX; ++n) s_fold[warp][n][lane] = acc[n];
+  __syncthreads();
+  // 32 columns × N outputs folded by the CTA's threads
+  for (int i = threadIdx.x; i < 32 * N; i += blockDim.x) {
+    const int n = i / 32, l = i % 32;
+    const int kk = (blockIdx.x - dx_blocks) * 32 + l;
+    if (kk < K) {
+      float s = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += s_fold[w8][n][l];
+      dw[static_cast<size_t>(n) * K + kk] = s;
+    }
   }
   if (db && static_cast<int>(blockIdx.x) == dx_blocks && threadIdx.x < N) db[threadIdx.x] = bsum;
 }
@@ -735,7 +766,7 @@ void launch_conv5x5_wgrad(const float* dy, const float* x, float* dw, float* db,
     throw std::invalid_argument("conv5x5_wgrad: supported channel configs are 1→16 and 16→32");
   }
   check_launch("conv5x5_wgrad");
-  fold_partials_kernel<<<(width + 127) / 128, 128, 0, st>>>(scr.partials, blocks, width, 25 * s.Cin * s.Cout, dw, db);
+  fold_partials_kernel<<<(width + 31) / 32, 256, 0, st>>>(scr.partials, blocks, width, 25 * s.Cin * s.Cout, dw, db);
   check_launch("fold_partials");
 }
 
@@ -811,7 +842,7 @@ void launch_linear_fwd(const float* x, const float* w, const float* b, float* ou
 void launch_linear_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, float* db, int B, int K, int N,
                        cudaStream_t st) {
   if (N > 16) throw std::invalid_argument("linear_bwd (fused head): N <= 16 supported");
-  const int dw_blocks = (K + 255) / 256;
+  const int dw_blocks = (K + 31) / 32;
   linear_bwd_kernel<16><<<B + dw_blocks, 256, 128 * N * sizeof(float), st>>>(dout, x, w, dx, dw, db, B, K, N, B);
   check_launch("linear_bwd");
 }

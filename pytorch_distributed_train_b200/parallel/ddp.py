@@ -290,6 +290,9 @@ class DistributedDataParallel(nn.Module):
             if hasattr(p, "_pdt_grad_view"):
                 del p._pdt_grad_view
         del self.reducer
+        import gc
+
+        gc.collect()  # drop dead autograd graphs that may still pin the old AccumulateGrad nodes
         self.reducer = _C.Reducer([p for p in self._params], layout, self.comm, self.bucket_bytes_cap,
                                   self.first_bucket_bytes_cap, self.find_unused_parameters,
                                   self.gradient_as_bucket_view, self.static_graph)

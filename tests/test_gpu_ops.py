@@ -80,6 +80,13 @@ def test_conv_tcgen05_exact_on_small_integers():
     dx = _C.conv5x5_dgrad(nhwc(dy), w, "tcgen05")
     ref = torch.autograd.grad(F.conv2d(x.requires_grad_(), w, padding=2), x, dy)[0]
     assert torch.equal(dx.permute(0, 3, 1, 2), ref)
+    # weight/bias gradient: MN-major operands, four TMEM accumulators, "ones" column for db
+    wd = w.double().requires_grad_()
+    bd = torch.zeros(32, dtype=torch.float64, device=dev(), requires_grad=True)
+    gw, gb = torch.autograd.grad(F.conv2d(x.detach().double(), wd, bd, padding=2), (wd, bd), dy.double())
+    dw, db = torch.empty_like(w), torch.empty(32, device=dev())
+    _C.conv5x5_wgrad(nhwc(dy), nhwc(x.detach()), dw, db, "tcgen05")
+    assert torch.equal(dw.double(), gw) and torch.equal(db.double(), gb)
 
 
 @pytest.mark.parametrize("impl", ["simt", "tcgen05"])
@@ -96,8 +103,10 @@ def test_conv5x5_backward(impl):
     assert torch.allclose(dx.permute(0, 3, 1, 2), gx, atol=tol, rtol=tol)
     dw, db = torch.empty_like(w), torch.empty_like(b)
     _C.conv5x5_wgrad(nhwc(dy), nhwc(x.detach()), dw, db, impl)
-    assert torch.allclose(dw, gw, atol=1e-2, rtol=1e-3), (dw - gw).abs().max()
-    assert torch.allclose(db, gb, atol=1e-2, rtol=1e-4)
+    # TF32 operands: ~1e-3 relative per product, random-walk over 19,600 pixels
+    wa, wr = (1.0, 5e-3) if impl == "tcgen05" else (1e-2, 1e-3)
+    assert torch.allclose(dw, gw, atol=wa, rtol=wr), (dw - gw).abs().max()
+    assert torch.allclose(db, gb, atol=wa, rtol=wr), (db - gb).abs().max()
     # conv1 weight gradient (no data gradient: the input needs none)
     x1 = torch.randn(B, 1, 28, 28, device=dev())
     w1 = torch.randn(16, 1, 5, 5, device=dev(), requires_grad=True)
@@ -252,6 +261,9 @@ def test_single_gpu_ddp_and_graphed_step():
         assert ddp.reducer.grads_are_views()
         from pytorch_distributed_train_b200.engine import GraphedTrainStep
 
+        # the old loss keeps last iteration's autograd graph — and with it AccumulateGrad nodes that
+        # were created on the default stream — alive; drop it before capturing on a side stream
+        del loss
         step = GraphedTrainStep(ddp, crit, opt, (x, t))
         l0 = step(x, t).item()
         l1 = step(x, t).item()
