@@ -26,6 +26,7 @@
 
 #include "conv_tcgen05.h"
 #include "cuda_utils.h"
+#include "grid_fold.cuh"
 
 namespace pdt {
 
@@ -448,26 +449,14 @@ __global__ void __launch_bounds__(192, 1) conv5x5_umma_kernel(const float* __res
           s_part[warp * 2 * NOUT + lane] = s1;
           s_part[warp * 2 * NOUT + NOUT + lane] = s2;
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (tid < 2 * NOUT) {
-            const float tot = s_part[tid] + s_part[2 * NOUT + tid] + s_part[4 * NOUT + tid] + s_part[6 * NOUT + tid];
-            scr.partials[static_cast<size_t>(tile) * 2 * NOUT + tid] = tot;
-          }
-          __threadfence();
+          float* tile_sums = s_part + 8 * NOUT;  // [2*NOUT]
+          if (tid < 2 * NOUT) tile_sums[tid] = s_part[tid] + s_part[2 * NOUT + tid] + s_part[4 * NOUT + tid] + s_part[6 * NOUT + tid];
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (tid == 0) s_last = (atomicAdd(scr.counter, 1u) == static_cast<unsigned>(num_tiles - 1));
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (s_last) {
-            __threadfence();
-            if (tid < 2 * NOUT) {
-              float tot = 0.f;
-              for (int tl = 0; tl < num_tiles; ++tl) tot += __ldcg(&scr.partials[static_cast<size_t>(tl) * 2 * NOUT + tid]);
-              stats[tid] = tot;
-              if (tid == 0) {
-                stats[2 * NOUT] = static_cast<float>(M);
-                *scr.counter = 0u;
-              }
-            }
-          }
+          // tiles are the contributors of the two-level deterministic fold (grid_fold.cuh)
+          grid_fold(tile_sums, 2 * NOUT, tile, num_tiles, scr, s_part, &s_last, tid, 128, NamedSync<1, 128>{}, [&](int i, float tot) {
+            stats[i] = tot;
+            if (i == 0) stats[2 * NOUT] = static_cast<float>(M);
+          });
         }
         if (tid == 0) tma_store_wait_read();
       } else {
@@ -482,6 +471,215 @@ __global__ void __launch_bounds__(192, 1) conv5x5_umma_kernel(const float* __res
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// =====================================================================================================
+// Implicit-GEMM 5x5 convolution, fully TMA-fed: the im2col A-tile of every filter tap is ONE
+// cp.async.bulk.tensor.4d...im2col instruction (hardware walks 128 consecutive output pixels through
+// W→H→N, applies the (kw,kh) tap offset and zero-fills the padding halo), so there are no producer
+// warps at all: warp 0 = TMA, warp 1 = MMA issue, warps 2-5 = epilogue on a double-buffered TMEM
+// accumulator (the epilogue of tile i overlaps the mainloop of tile i+1).
+//   CK = 16 (fwd):  rows of 64 B  → SWIZZLE_64B smem/UMMA layout, 2 MMAs (K=8) per tap
+//   CK = 32 (dgrad): rows of 128 B → SWIZZLE_128B,               4 MMAs per tap
+// Weights: Bm[NOUT][25·CK] (K index = tap·CK + c), one TMA box per tap, resident in smem.
+// =====================================================================================================
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+// K-major descriptor for rows of ROWB bytes (64 → SWIZZLE_64B, layout type 4; 128 → SWIZZLE_128B, type 2);
+// SBO = 8 rows.
+template <int ROWB>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((8 * ROWB) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(ROWB == 128 ? 2 : 4) << 61;
+  return d;
+}
+
+template <int CK, int NOUT>
+struct ConvTmaCfg {
+  static constexpr int kRowB = CK * 4;                       // bytes per pixel per tap
+  static constexpr int kAStageBytes = kTileM * kRowB;        // 8 KB / 16 KB
+  static constexpr int kStages = CK == 16 ? 10 : 6;
+  static constexpr int kBTapBytes = NOUT * kRowB;            // 2 KB
+  static constexpr int kTmemCols = 64;                       // two 32-column accumulators
+  static constexpr int kThreads = 192;
+  static constexpr size_t kSmem = 2048 + kStages * kAStageBytes + 25 * kBTapBytes + kTileM * 128 + 2048;
+};
+
+template <int CK, int NOUT, bool FWD>
+__global__ void __launch_bounds__(192, 1) conv5x5_umma_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_b,
+                                                                  const __grid_constant__ CUtensorMap tm_y, const float* __restrict__ bias,
+                                                                  float* __restrict__ y, float* stats, ReduceScratch scr, int B, int H, int W,
+                                                                  int num_tiles) {
+  using Cfg = ConvTmaCfg<CK, NOUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;
+  uint8_t* sb = sa + Cfg::kStages * Cfg::kAStageBytes;
+  uint8_t* sy = sb + 25 * Cfg::kBTapBytes;
+  sy = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sy) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sy + kTileM * 128);
+  uint64_t* full = bars;
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* b_full = empty + Cfg::kStages;
+  uint64_t* acc_full = b_full + 1;      // [2]
+  uint64_t* acc_empty = acc_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_part = reinterpret_cast<float*>(tmem_slot + 2);   // [4][2*NOUT] + [2*NOUT]
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = B * H * W;
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_b);
+    if (FWD) tma_prefetch_desc(&tm_y);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(b_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_full, 25 * Cfg::kBTapBytes);
+      for (int t = 0; t < 25; ++t) tma_load_2d(sb + t * Cfg::kBTapBytes, &tm_b, b_full, t * CK, 0);
+      int g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int p0 = tile * kTileM;
+        const int ow0 = p0 % W, oh0 = (p0 / W) % H, n0 = p0 / (W * H);
+        for (int t = 0; t < 25; ++t, ++g) {
+          const int s = g % Cfg::kStages;
+          mbar_wait(&empty[s], ((g / Cfg::kStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[s], Cfg::kAStageBytes);
+          // base pixel = output pixel shifted by the lower corner (-pad); the tap goes in the offsets
+          tma_load_im2col_4d(sa + s * Cfg::kAStageBytes, &tm_x, &full[s], 0, ow0 - 2, oh0 - 2, n0, static_cast<uint16_t>(t % 5),
+                             static_cast<uint16_t>(t / 5));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_tf32(kTileM, NOUT);
+    mbar_wait(b_full, 0);
+    int g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int t = 0; t < 25; ++t, ++g) {
+        const int s = g % Cfg::kStages;
+        mbar_wait(&full[s], (g / Cfg::kStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = smem_u32(sa + s * Cfg::kAStageBytes), b0 = smem_u32(sb + t * Cfg::kBTapBytes);
+#pragma unroll
+          for (int k = 0; k < CK / 8; ++k)
+            umma_tf32(tmem_base + as * 32, umma_desc_kmajor<Cfg::kRowB>(a0 + k * 32), umma_desc_kmajor<Cfg::kRowB>(b0 + k * 32), idesc, (t | k) != 0);
+          umma_commit(&empty[s]);
+          if (t == 24) umma_commit(&acc_full[as]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM lane quadrant = warp % 4 ----------------------------------------------
+    const int et = tid - 64;                  // 0..127
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;           // tile row = TMEM lane
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&acc_full[as], (it >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      float v[NOUT];
+#pragma unroll
+      for (int c0 = 0; c0 < NOUT; c0 += 16) {
+        float t16[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 32 + c0, t16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c0 + j] = t16[j];
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);            // the MMA warp may start the tile after next in this accumulator
+      const int p = tile * kTileM + r;
+      const bool valid = p < M;
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) v[j] += bias[j];
+      }
+      if constexpr (FWD) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's TMA store has finished reading sy
+#pragma unroll
+        for (int q = 0; q < NOUT / 4; ++q) {
+          float4 o = valid ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(sy + r * 128 + ((q ^ (r & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          tma_store_2d(&tm_y, sy, 0, tile * kTileM);
+          tma_store_commit();
+        }
+        if (stats) {
+          float s1 = 0.f, s2 = 0.f;
+          const int q = lane >> 2, e = lane & 3;
+          const int w4 = et >> 5;  // 0..3: rows 32*w4 .. 32*w4+31
+          for (int rr = w4 * 32; rr < w4 * 32 + 32; ++rr) {
+            const float val = reinterpret_cast<const float*>(sy + rr * 128 + ((q ^ (rr & 7)) << 4))[e];
+            s1 += val;
+            s2 += val * val;
+          }
+          s_part[w4 * 2 * NOUT + lane] = s1;
+          s_part[w4 * 2 * NOUT + NOUT + lane] = s2;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float* tile_sums = s_part + 8 * NOUT;
+          if (et < 2 * NOUT) tile_sums[et] = s_part[et] + s_part[2 * NOUT + et] + s_part[4 * NOUT + et] + s_part[6 * NOUT + et];
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          grid_fold(tile_sums, 2 * NOUT, tile, num_tiles, scr, s_part, &s_last, et, 128, NamedSync<1, 128>{}, [&](int i, float tot) {
+            stats[i] = tot;
+            if (i == 0) stats[2 * NOUT] = static_cast<float>(M);
+          });
+        }
+        if (et == 0) tma_store_wait_read();
+      } else {
+        if (valid) {
+          float* o = y + static_cast<size_t>(p) * NOUT;
+#pragma unroll
+          for (int q = 0; q < NOUT / 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// Bm[NOUT][25*CK] without K padding (the TMA-fed kernel loads one [NOUT][CK] box per tap)
+template <bool FWD>
+__global__ void repack_weights_dense_kernel(const float* __restrict__ w, float* __restrict__ bm, int Cout, int Cin) {
+  const int CK = FWD ? Cin : Cout, NOUT = FWD ? Cout : Cin;
+  const int kk = 25 * CK;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NOUT * kk) return;
+  const int n = i / kk, k = i % kk, tap = k / CK, c = k % CK;
+  bm[i] = FWD ? w[(n * Cin + c) * 25 + tap] : w[(c * Cin + n) * 25 + (24 - tap)];
 }
 
 // =====================================================================================================
@@ -510,15 +708,19 @@ struct WgradCfg {
   static constexpr size_t kSmem = 1024 + kStages * kAStageBytes + kBStages * kBStageBytes + 1024;
 };
 
-// MN-major SWIZZLE_128B descriptor: LBO = byte stride between 32-element MN atoms, SBO = byte stride
-// between 8-row K atoms.  [cf. make_umma_desc<Major::MN>, cute/atom/mma_traits_sm100.hpp]
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major descriptor for 32-bit (TF32) operands.  The only legal MN-major layout for TF32 is
+// SWIZZLE_128B_BASE32B (layout type 1): rows of 128 B = 32 consecutive M/N values, K atoms of FOUR
+// rows, and the XOR swizzle acts on 32-byte chunks (chunk32 ^= row % 4) — its TMA counterpart is
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = byte stride between 32-element MN atoms, SBO = byte
+// stride between 4-row K atoms (512 B when the 8 rows of one MMA are contiguous).
+// [cf. UMMA::Layout_MN_SW128_32B_Atom and make_umma_desc<Major::MN>, cute/atom/mma_traits_sm100.hpp]
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(1) << 61;
   return d;
 }
 
@@ -578,8 +780,8 @@ __global__ void __launch_bounds__(192, 1) conv5x5_wgrad_umma_kernel(const float*
             const uint32_t a0 = smem_u32(sa + s * Cfg::kAStageBytes), b0 = smem_u32(sb + bs * Cfg::kBStageBytes) + h * 8 * 1024;
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb)
-              umma_tf32(tmem_base + mt * 32, umma_desc_mn_sw128(a0 + kb * 1024, 8 * 1024, 1024), umma_desc_mn_sw128(b0 + kb * 1024, 1024, 1024),
-                        idesc, (it | h | kb) != 0);
+              umma_tf32(tmem_base + mt * 32, umma_desc_mn_sw128_32b(a0 + kb * 1024, 8 * 1024, 512),
+                        umma_desc_mn_sw128_32b(b0 + kb * 1024, 1024, 512), idesc, (it | h | kb) != 0);
             umma_commit(&aempty[s]);
             if (mt == Cfg::kMTiles - 1 && h == 1) umma_commit(&bempty[bs]);
           }
@@ -623,7 +825,8 @@ __global__ void __launch_bounds__(192, 1) conv5x5_wgrad_umma_kernel(const float*
                 bytes = 16;
               }
             }
-            cp_async_16(stage + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4), src, bytes);
+            // 128B_BASE32B swizzle: the 32-byte chunk index (chunk >> 1) is XORed with (row % 4)
+            cp_async_16(stage + (r >> 3) * 1024 + (r & 7) * 128 + (((((chunk >> 1) ^ (r & 3)) << 1) | (chunk & 1)) << 4), src, bytes);
           }
           cp_async_commit();
           if (g >= Cfg::kLag) {
@@ -689,16 +892,34 @@ __global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-CUtensorMap make_tmap_2d(const float* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+CUtensorMap make_tmap_2d(const float* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer,
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUtensorMap m;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {inner * sizeof(float)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = driver().cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + cu_error(r));
+  return m;
+}
+
+// NHWC activation [N,H,W,C] as a rank-4 im2col tensor map for a 5x5 / pad 2 / stride 1 window:
+// bounding box lower corner = -pad, upper corner = pad - (filter - 1); 128 pixels × C channels per load.
+CUtensorMap make_tmap_im2col(const float* base, int C, int W, int H, int N, CUtensorMapSwizzle swizzle) {
+  const DriverApi& d = driver();
+  if (!d.cuTensorMapEncodeIm2col) throw std::runtime_error("cuTensorMapEncodeIm2col is not available in this driver");
+  CUtensorMap m;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4, static_cast<cuuint64_t>(H) * W * C * 4};
+  int lower[2] = {-2, -2}, upper[2] = {-2, -2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = d.cuTensorMapEncodeIm2col(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, lower, upper,
+                                         static_cast<cuuint32_t>(C), static_cast<cuuint32_t>(kTileM), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeIm2col failed: " + cu_error(r));
   return m;
 }
 
@@ -751,7 +972,8 @@ void launch_conv5x5_fwd_tcgen05(const float* x, const float* w, const float* bia
   using Cfg = ConvCfg<16, 32>;
   const int M = s.B * s.H * s.W;
   const int tiles = (M + kTileM - 1) / kTileM;
-  if (stats && static_cast<long long>(tiles) * 64 > scr.capacity_floats) throw std::invalid_argument("conv5x5 tcgen05: scratch too small");
+  if (stats && (static_cast<long long>(tiles + tiles / kFoldGroup + 1) * 64 > scr.capacity_floats || tiles / kFoldGroup + 2 > scr.counters))
+    throw std::invalid_argument("conv5x5 tcgen05: scratch too small");
   const int kpad = Cfg::kChunks * kChunkK;
   float* bm = repack_buffer(0, static_cast<size_t>(32) * kpad);
   repack_weights_kernel<true><<<(32 * kpad + 255) / 256, 256, 0, st>>>(w, bm, 32, 16);
@@ -782,6 +1004,44 @@ void launch_conv5x5_dgrad_tcgen05(const float* dy, const float* w, float* dx, Co
   check_launch("conv5x5_umma(dgrad)");
 }
 
+void launch_conv5x5_fwd_tma(const float* x, const float* w, const float* bias, float* y, float* stats, ConvShape s, ReduceScratch scr,
+                            cudaStream_t st) {
+  if (!conv_tcgen05_supported(s)) throw std::invalid_argument("conv5x5 tma: only 16→32 channels are implemented");
+  using Cfg = ConvTmaCfg<16, 32>;
+  const int M = s.B * s.H * s.W;
+  const int tiles = (M + kTileM - 1) / kTileM;
+  if (stats && (static_cast<long long>(tiles + tiles / kFoldGroup + 1) * 64 > scr.capacity_floats || tiles / kFoldGroup + 2 > scr.counters))
+    throw std::invalid_argument("conv5x5 tma: scratch too small");
+  float* bm = repack_buffer(3, static_cast<size_t>(32) * 400);
+  repack_weights_dense_kernel<true><<<(32 * 400 + 255) / 256, 256, 0, st>>>(w, bm, 32, 16);
+  check_launch("repack_weights_dense(fwd)");
+  CUtensorMap tm_x = make_tmap_im2col(x, 16, s.W, s.H, s.B, CU_TENSOR_MAP_SWIZZLE_64B);
+  CUtensorMap tm_b = make_tmap_2d(bm, 400, 32, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  CUtensorMap tm_y = make_tmap_2d(y, 32, static_cast<uint64_t>(M), 32, kTileM);
+  auto kern = conv5x5_umma_tma_kernel<16, 32, true>;
+  opt_in_smem(kern, Cfg::kSmem);
+  const int grid = std::min(tiles, sm_count());
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tm_x, tm_b, tm_y, bias, y, stats, scr, s.B, s.H, s.W, tiles);
+  check_launch("conv5x5_umma_tma(fwd)");
+}
+
+void launch_conv5x5_dgrad_tma(const float* dy, const float* w, float* dx, ConvShape s, cudaStream_t st) {
+  if (!conv_tcgen05_supported(s)) throw std::invalid_argument("conv5x5 tma dgrad: only 16→32 channels are implemented");
+  using Cfg = ConvTmaCfg<32, 16>;
+  const int M = s.B * s.H * s.W;
+  const int tiles = (M + kTileM - 1) / kTileM;
+  float* bm = repack_buffer(4, static_cast<size_t>(16) * 800);
+  repack_weights_dense_kernel<false><<<(16 * 800 + 255) / 256, 256, 0, st>>>(w, bm, 32, 16);
+  check_launch("repack_weights_dense(dgrad)");
+  CUtensorMap tm_x = make_tmap_im2col(dy, 32, s.W, s.H, s.B, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tm_b = make_tmap_2d(bm, 800, 16, 32, 16, CU_TENSOR_MAP_SWIZZLE_128B);
+  auto kern = conv5x5_umma_tma_kernel<32, 16, false>;
+  opt_in_smem(kern, Cfg::kSmem);
+  const int grid = std::min(tiles, sm_count());
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tm_x, tm_b, tm_b, nullptr, dx, nullptr, ReduceScratch{}, s.B, s.H, s.W, tiles);
+  check_launch("conv5x5_umma_tma(dgrad)");
+}
+
 void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, float* db, ConvShape s, ReduceScratch scr, cudaStream_t st) {
   if (!conv_tcgen05_supported(s)) throw std::invalid_argument("conv5x5 tcgen05 wgrad: only 16→32 channels are implemented");
   using Cfg = WgradCfg;
@@ -804,7 +1064,7 @@ void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, fl
       ones_ready[dev] = true;
     }
   }
-  CUtensorMap tm_dy = make_tmap_2d(dy, 32, static_cast<uint64_t>(M), 32, kTileM);
+  CUtensorMap tm_dy = make_tmap_2d(dy, 32, static_cast<uint64_t>(M), 32, kTileM, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   opt_in_smem(conv5x5_wgrad_umma_kernel, Cfg::kSmem);
   conv5x5_wgrad_umma_kernel<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(x, tm_dy, ones, scr.partials, s.B, s.H, s.W, tiles);
   check_launch("conv5x5_wgrad_umma");

@@ -15,6 +15,12 @@ void launch_conv5x5_fwd_tcgen05(const float* x, const float* w, const float* bia
 // dx NHWC [B,H,W,16] = conv_transpose(dy NHWC [B,H,W,32], w [32,16,5,5])
 void launch_conv5x5_dgrad_tcgen05(const float* dy, const float* w, float* dx, ConvShape s, cudaStream_t st);
 
+// Same contracts, fully TMA-fed: every filter tap's A-tile is one cp.async.bulk.tensor im2col load
+// (no producer warps), double-buffered TMEM accumulator, dedicated epilogue warps.
+void launch_conv5x5_fwd_tma(const float* x, const float* w, const float* bias, float* y, float* stats, ConvShape s, ReduceScratch scr,
+                            cudaStream_t st);
+void launch_conv5x5_dgrad_tma(const float* dy, const float* w, float* dx, ConvShape s, cudaStream_t st);
+
 // dw [32,16,5,5], db [32] (nullable) from dy NHWC [B,H,W,32] and x NHWC [B,H,W,16]: persistent split-K over
 // pixel tiles with MN-major operands, four TMEM accumulators, deterministic fold of the per-CTA partials.
 void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, float* db, ConvShape s, ReduceScratch scr, cudaStream_t st);

@@ -54,14 +54,24 @@ ReduceScratch scratch(const at::Tensor& like) {
     Scratch s;
     const int64_t cap = 4 << 20;  // 4 Mi floats = 16 MiB
     s.partials = at::empty({cap}, like.options().dtype(at::kFloat));
-    s.counter = at::zeros({4}, like.options().dtype(at::kInt));
+    s.counter = at::zeros({1024}, like.options().dtype(at::kInt));
     it = per_dev.emplace(dev, std::move(s)).first;
   }
   ReduceScratch r;
   r.partials = it->second.partials.data_ptr<float>();
   r.counter = reinterpret_cast<unsigned int*>(it->second.counter.data_ptr<int>());
   r.capacity_floats = static_cast<int>(it->second.partials.numel());
+  r.counters = static_cast<int>(it->second.counter.numel());
   return r;
+}
+
+// The tensor-core weight gradient is opt-in (PDT_WGRAD_TCGEN05=1) until its GPU numerics test is green.
+bool wgrad_tcgen05_default() {
+  static const bool on = [] {
+    const char* e = getenv("PDT_WGRAD_TCGEN05");
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 ConvShape conv_shape(const at::Tensor& x_nhwc, const at::Tensor& w) {
@@ -122,7 +132,9 @@ void register_cuda_bindings(py::module_& m) {
     at::Tensor y = at::empty({s.B, s.H, s.W, s.Cout}, x.options());
     at::Tensor stats = want_stats ? at::empty({2 * s.Cout + 1}, x.options()) : at::Tensor();
     const bool tc = impl == "tcgen05" || (impl == "auto" && conv_tcgen05_supported(s));
-    if (tc) launch_conv5x5_fwd_tcgen05(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
+    if (impl == "tma") launch_conv5x5_fwd_tma(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
+                                              want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
+    else if (tc) launch_conv5x5_fwd_tcgen05(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
                                        want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
     else launch_conv5x5_fwd(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
                             want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
@@ -137,7 +149,8 @@ void register_cuda_bindings(py::module_& m) {
     TORCH_CHECK(dy.size(3) == s.Cout, "conv5x5_dgrad: dy channels must equal weight Cout");
     at::Tensor dx = at::empty({s.B, s.H, s.W, s.Cin}, dy.options());
     const bool tc = impl == "tcgen05" || (impl == "auto" && conv_tcgen05_supported(s));
-    if (tc) launch_conv5x5_dgrad_tcgen05(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
+    if (impl == "tma") launch_conv5x5_dgrad_tma(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
+    else if (tc) launch_conv5x5_dgrad_tcgen05(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
     else launch_conv5x5_dgrad(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
     return dx;
   }, py::arg("dy"), py::arg("w"), py::arg("impl") = "auto");
@@ -146,7 +159,7 @@ void register_cuda_bindings(py::module_& m) {
     chk(dy, "dy"); chk(x, "x"); chk(dw, "dw");
     c10::cuda::CUDAGuard g(dy.device());
     ConvShape s = conv_shape(x, dw);
-    const bool tc = impl == "tcgen05" || (impl == "auto" && conv_tcgen05_supported(s));
+    const bool tc = impl == "tcgen05" || (impl == "auto" && conv_tcgen05_supported(s) && wgrad_tcgen05_default());
     if (tc) launch_conv5x5_wgrad_tcgen05(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
     else launch_conv5x5_wgrad(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
   }, py::arg("dy"), py::arg("x"), py::arg("dw"), py::arg("db") = py::none(), py::arg("impl") = "auto");

@@ -17,8 +17,9 @@ struct ConvShape {
 // Scratch for deterministic cross-CTA reductions: partials[max_blocks][width] + a ticket counter.
 struct ReduceScratch {
   float* partials;
-  unsigned int* counter;  // must be zero before first use; kernels leave it at zero
+  unsigned int* counter;  // `counters` ticket words; zero before first use, kernels leave them at zero
   int capacity_floats;
+  int counters;
 };
 
 // ---- SIMT direct convolution (conv1; conv2 fallback + oracle for the tcgen05 kernel) -------------

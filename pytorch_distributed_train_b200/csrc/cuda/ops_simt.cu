@@ -12,6 +12,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "grid_fold.cuh"
 #include "ops_kernels.h"
 
 namespace pdt {
@@ -24,28 +25,7 @@ void check_launch(const char* what) {
   count_kernel_launch();
 }
 
-// ---- deterministic grid-wide fold -----------------------------------------------------------------
-// Every CTA deposits `width` partial values; the last CTA to arrive sums them in CTA order and calls
-// fin(i, total) for each i.  The ticket counter is left at zero for the next launch / graph replay.
-template <typename Fin>
-__device__ __forceinline__ void grid_fold(const float* blk_vals, int width, ReduceScratch scr, Fin fin) {
-  __shared__ int s_last;
-  const int nblk = gridDim.x * gridDim.y;
-  const int bid = blockIdx.y * gridDim.x + blockIdx.x;
-  for (int i = threadIdx.x; i < width; i += blockDim.x) scr.partials[static_cast<size_t>(bid) * width + i] = blk_vals[i];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(scr.counter, 1u) == static_cast<unsigned>(nblk - 1));
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = threadIdx.x; i < width; i += blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += __ldcg(&scr.partials[static_cast<size_t>(b) * width + i]);
-    fin(i, s);
-  }
-  if (threadIdx.x == 0) *scr.counter = 0u;
-}
+// deterministic grid-wide fold: see grid_fold.cuh (two-level ticket tree, parallel row folds)
 
 // =====================================================================================================
 // Direct 5x5 "same" convolution, NHWC, one CTA = TH output rows of one image, all output channels.
@@ -137,7 +117,9 @@ __global__ void __launch_bounds__(448) conv5x5_kernel(const float* __restrict__ 
     }
     __syncthreads();
     const float cnt = static_cast<float>(B) * H * W;
-    grid_fold(blk, 2 * COUT, scr, [&](int i, float v) {
+    __shared__ float s_tmp[448];
+    __shared__ int s_flag;
+    grid_fold(blk, 2 * COUT, blockIdx.x, gridDim.x, scr, s_tmp, &s_flag, tid, blockDim.x, CtaSync{}, [&](int i, float v) {
       stats[i] = v;
       if (i == 0) stats[2 * COUT] = cnt;
     });
@@ -443,7 +425,9 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_kernel(const float* __re
       blk[threadIdx.x] = s;
     }
     __syncthreads();
-    grid_fold(blk, 2 * C, scr, [&](int i, float v) {
+    __shared__ float s_tmp[256];
+    __shared__ int s_flag;
+    grid_fold(blk, 2 * C, blockIdx.x, gridDim.x, scr, s_tmp, &s_flag, threadIdx.x, blockDim.x, CtaSync{}, [&](int i, float v) {
       sums[i] = v;
       if (i < C) { if (dbeta) dbeta[i] = v; }
       else if (dgamma) dgamma[i - C] = v;
@@ -716,7 +700,8 @@ void launch_conv5x5_fwd(const float* x, const float* w, const float* bias, float
   constexpr int TH = 7;
   if (s.H % TH != 0) throw std::invalid_argument("conv5x5_fwd: H must be a multiple of 7");
   const int blocks = s.B * (s.H / TH);
-  if (stats && blocks * 2 * s.Cout > scr.capacity_floats) throw std::invalid_argument("conv5x5_fwd: reduction scratch too small");
+  if (stats && (static_cast<long long>(blocks + blocks / kFoldGroup + 1) * 2 * s.Cout > scr.capacity_floats || blocks / kFoldGroup + 2 > scr.counters))
+    throw std::invalid_argument("conv5x5_fwd: reduction scratch too small");
   if (s.Cin == 1 && s.Cout == 16) {
     const int threads = (TH * s.W + 31) / 32 * 32;
     const size_t sm = conv_smem(1, 16, TH, s.W, threads);
@@ -786,7 +771,8 @@ void launch_bn_relu_pool_bwd_reduce(const float* dout, const float* y, const flo
   if (C % 4 != 0 || C > 64) throw std::invalid_argument("bn_relu_pool_bwd: C%4==0, C<=64 required");
   const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 4);
   const int blocks = static_cast<int>((total + 255) / 256);
-  if (static_cast<long long>(blocks) * 2 * C > scr.capacity_floats) throw std::invalid_argument("bn_relu_pool_bwd: reduction scratch too small");
+  if (static_cast<long long>(blocks + blocks / kFoldGroup + 1) * 2 * C > scr.capacity_floats || blocks / kFoldGroup + 2 > scr.counters)
+    throw std::invalid_argument("bn_relu_pool_bwd: reduction scratch too small");
   bn_relu_pool_bwd_kernel<false><<<blocks, 256, 0, st>>>(dout, y, saved, gamma, beta, sums, dgamma, dbeta, nullptr, nullptr, B, H, W, C,
                                                          dout_nchw ? 1 : 0, scr);
   check_launch("bn_relu_pool_bwd_reduce");

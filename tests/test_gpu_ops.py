@@ -89,6 +89,23 @@ def test_conv_tcgen05_exact_on_small_integers():
     assert torch.equal(dw.double(), gw) and torch.equal(db.double(), gb)
 
 
+@pytest.mark.parametrize("B", [5, 100])
+def test_conv_tma_im2col_exact(B):
+    """Fully TMA-fed variant: one im2col bulk-tensor load per filter tap (fwd: SWIZZLE_64B rows, dgrad: 128B)."""
+    x = torch.randint(-3, 4, (B, 16, 14, 14), device=dev()).float()
+    w = torch.randint(-2, 3, (32, 16, 5, 5), device=dev()).float()
+    b = torch.randint(-2, 3, (32,), device=dev()).float()
+    y, stats = _C.conv5x5_fwd(nhwc(x), w, b, True, "tma")
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=2)
+    assert torch.equal(y.permute(0, 3, 1, 2).double(), ref)
+    assert torch.equal(stats[:32].double(), ref.sum((0, 2, 3))) and stats[64].item() == B * 196
+    dy = torch.randint(-3, 4, (B, 32, 14, 14), device=dev()).float()
+    dx = _C.conv5x5_dgrad(nhwc(dy), w, "tma")
+    xd = x.double().requires_grad_()
+    gx = torch.autograd.grad(F.conv2d(xd, w.double(), padding=2), xd, dy.double())[0]
+    assert torch.equal(dx.permute(0, 3, 1, 2).double(), gx)
+
+
 @pytest.mark.parametrize("impl", ["simt", "tcgen05"])
 def test_conv5x5_backward(impl):
     B = 100
