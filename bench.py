@@ -230,6 +230,9 @@ def run_reference(args):
     rank, local_rank, world = env_rank()
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    import faulthandler
+
+    faulthandler.dump_traceback_later(240, repeat=True, file=sys.stderr)  # say where we are if something wedges
     W, K = max(args.warmup, 3), args.steps
     base_port = int(os.environ.get("MASTER_PORT", "29500"))
     dev = torch.device("cuda", local_rank)

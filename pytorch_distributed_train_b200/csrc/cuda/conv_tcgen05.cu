@@ -508,12 +508,18 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
 template <int CK, int NOUT>
 struct ConvTmaCfg {
   static constexpr int kRowB = CK * 4;                       // bytes per pixel per tap
-  static constexpr int kAStageBytes = kTileM * kRowB;        // 8 KB / 16 KB
-  static constexpr int kStages = CK == 16 ? 10 : 6;
+  static constexpr int kATapBytes = kTileM * kRowB;          // 8 KB / 16 KB
+  // One pipeline stage = one filter ROW (5 taps, 5 TMA loads on one mbarrier): the per-stage
+  // handshake (TMA issue → full → MMA wake-up → commit → empty) costs ~0.25 µs whatever the payload,
+  // and 25 one-tap stages per tile made the mainloop handshake-bound (profiles/op_bench.md).
+  static constexpr int kTapsPerStage = 5;
+  static constexpr int kAStageBytes = kTapsPerStage * kATapBytes;   // 40 KB / 80 KB
+  static constexpr int kStages = CK == 16 ? 3 : 2;
   static constexpr int kBTapBytes = NOUT * kRowB;            // 2 KB
+  static constexpr int kSyBytes = CK == 16 ? kTileM * 128 : 0;  // output staging only for the TMA-stored forward
   static constexpr int kTmemCols = 64;                       // two 32-column accumulators
   static constexpr int kThreads = 192;
-  static constexpr size_t kSmem = 2048 + kStages * kAStageBytes + 25 * kBTapBytes + kTileM * 128 + 2048;
+  static constexpr size_t kSmem = 2048 + kStages * kAStageBytes + 25 * kBTapBytes + kSyBytes + 2048;
 };
 
 template <int CK, int NOUT, bool FWD>
@@ -528,7 +534,7 @@ __global__ void __launch_bounds__(192, 1) conv5x5_umma_tma_kernel(const __grid_c
   uint8_t* sb = sa + Cfg::kStages * Cfg::kAStageBytes;
   uint8_t* sy = sb + 25 * Cfg::kBTapBytes;
   sy = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sy) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sy + kTileM * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sy + Cfg::kSyBytes);
   uint64_t* full = bars;
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* b_full = empty + Cfg::kStages;
@@ -563,13 +569,15 @@ __global__ void __launch_bounds__(192, 1) conv5x5_umma_tma_kernel(const __grid_c
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int p0 = tile * kTileM;
         const int ow0 = p0 % W, oh0 = (p0 / W) % H, n0 = p0 / (W * H);
-        for (int t = 0; t < 25; ++t, ++g) {
+        for (int kh = 0; kh < 5; ++kh, ++g) {
           const int s = g % Cfg::kStages;
           mbar_wait(&empty[s], ((g / Cfg::kStages) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], Cfg::kAStageBytes);
           // base pixel = output pixel shifted by the lower corner (-pad); the tap goes in the offsets
-          tma_load_im2col_4d(sa + s * Cfg::kAStageBytes, &tm_x, &full[s], 0, ow0 - 2, oh0 - 2, n0, static_cast<uint16_t>(t % 5),
-                             static_cast<uint16_t>(t / 5));
+#pragma unroll
+          for (int kw = 0; kw < 5; ++kw)
+            tma_load_im2col_4d(sa + s * Cfg::kAStageBytes + kw * Cfg::kATapBytes, &tm_x, &full[s], 0, ow0 - 2, oh0 - 2, n0,
+                               static_cast<uint16_t>(kw), static_cast<uint16_t>(kh));
         }
       }
     }
@@ -581,17 +589,20 @@ __global__ void __launch_bounds__(192, 1) conv5x5_umma_tma_kernel(const __grid_c
       const int as = it & 1;
       mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      for (int t = 0; t < 25; ++t, ++g) {
+      for (int kh = 0; kh < 5; ++kh, ++g) {
         const int s = g % Cfg::kStages;
         mbar_wait(&full[s], (g / Cfg::kStages) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a0 = smem_u32(sa + s * Cfg::kAStageBytes), b0 = smem_u32(sb + t * Cfg::kBTapBytes);
+          const uint32_t a0 = smem_u32(sa + s * Cfg::kAStageBytes), b0 = smem_u32(sb + kh * 5 * Cfg::kBTapBytes);
 #pragma unroll
-          for (int k = 0; k < CK / 8; ++k)
-            umma_tf32(tmem_base + as * 32, umma_desc_kmajor<Cfg::kRowB>(a0 + k * 32), umma_desc_kmajor<Cfg::kRowB>(b0 + k * 32), idesc, (t | k) != 0);
+          for (int kw = 0; kw < 5; ++kw)
+#pragma unroll
+            for (int k = 0; k < CK / 8; ++k)
+              umma_tf32(tmem_base + as * 32, umma_desc_kmajor<Cfg::kRowB>(a0 + kw * Cfg::kATapBytes + k * 32),
+                        umma_desc_kmajor<Cfg::kRowB>(b0 + kw * Cfg::kBTapBytes + k * 32), idesc, (kh | kw | k) != 0);
           umma_commit(&empty[s]);
-          if (t == 24) umma_commit(&acc_full[as]);
+          if (kh == 4) umma_commit(&acc_full[as]);
         }
         __syncwarp();
       }
@@ -805,19 +816,22 @@ __global__ void __launch_bounds__(192, 1) conv5x5_wgrad_umma_kernel(const float*
         for (int h = 0; h < 2; ++h, ++g) {
           const int s = g % Cfg::kStages;
           mbar_wait(&aempty[s], ((g / Cfg::kStages) & 1) ^ 1);
-          const uint32_t stage = smem_u32(sa + s * Cfg::kAStageBytes) + unit_off;
+          // rows r = t4 + 4j (t4 = tid/32): r/8 = j/2, r%8 = 4(j%2)+t4, r%4 = t4 ⇒ the swizzle term is a
+          // per-thread constant.  128B_BASE32B: the 32-byte chunk index (chunk >> 1) is XORed with (row % 4).
+          const int t4 = tid >> 5;
+          const uint32_t dst0 = smem_u32(sa + s * Cfg::kAStageBytes) + unit_off + t4 * 128 + (((((chunk >> 1) ^ t4) << 1) | (chunk & 1)) << 4);
+          int p = tile * kTileM + h * Cfg::kHalfPix + t4;
+          int ow = p % W, oh = (p / W) % H;               // NHWC: pixel p lives at x + 16 p, so only bounds need (oh, ow)
+          const int tap_delta = (kh * W + kw) * 16 + c4;
 #pragma unroll 4
           for (int j = 0; j < 16; ++j) {
-            const int r = (tid >> 5) + 4 * j;                  // pixel row inside the 64-pixel half
-            const int p = tile * kTileM + h * Cfg::kHalfPix + r;
             const float* src = x;
             uint32_t bytes = 0;
             if (p < M) {
               if (tap < 25) {
-                const int ow = p % W, oh = (p / W) % H, n = p / (W * H);
                 const int ih = oh + kh, iw = ow + kw;
                 if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-                  src = x + ((static_cast<size_t>(n) * H + ih) * W + iw) * 16 + c4;
+                  src = x + static_cast<size_t>(p) * 16 + tap_delta;
                   bytes = 16;
                 }
               } else if (tap == 25 && c4 == 0) {
@@ -825,8 +839,10 @@ __global__ void __launch_bounds__(192, 1) conv5x5_wgrad_umma_kernel(const float*
                 bytes = 16;
               }
             }
-            // 128B_BASE32B swizzle: the 32-byte chunk index (chunk >> 1) is XORed with (row % 4)
-            cp_async_16(stage + (r >> 3) * 1024 + (r & 7) * 128 + (((((chunk >> 1) ^ (r & 3)) << 1) | (chunk & 1)) << 4), src, bytes);
+            cp_async_16(dst0 + (j >> 1) * 1024 + (j & 1) * 512, src, bytes);
+            p += 4;
+            ow += 4;
+            if (ow >= W) { ow -= W; oh = (oh + 1 == H) ? 0 : oh + 1; }
           }
           cp_async_commit();
           if (g >= Cfg::kLag) {
@@ -870,23 +886,28 @@ __global__ void __launch_bounds__(192, 1) conv5x5_wgrad_umma_kernel(const float*
 // dw[co][ci][tap] = Σ_cta partial[cta][tap*16+ci][co];  db[co] = Σ_cta partial[cta][400][co]
 __global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ dw,
                                                          float* __restrict__ db) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m = t >> 5, co = t & 31;
-  if (m > 400) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  // one CTA per im2col row m (401 of them): lane = output channel, the 8 warps stride over the
+  // per-CTA partials (≤ 148/8 = 19 loads each, two in flight), sub-sums folded in warp order
+  __shared__ float s_sub[8][32];
+  const int m = blockIdx.x, co = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* p = partials + static_cast<size_t>(m) * 32 + co;
   const size_t stride = static_cast<size_t>(WgradCfg::kMUsed) * 32;
-  int c = 0;
-  for (; c + 4 <= nparts; c += 4) {   // four independent loads in flight; summation order stays fixed
-    s0 += p[(c + 0) * stride];
-    s1 += p[(c + 1) * stride];
-    s2 += p[(c + 2) * stride];
-    s3 += p[(c + 3) * stride];
+  float s0 = 0.f, s1 = 0.f;
+  int c = warp;
+  for (; c + 8 < nparts; c += 16) {
+    s0 += p[c * stride];
+    s1 += p[(c + 8) * stride];
   }
-  for (; c < nparts; ++c) s0 += p[c * stride];
-  const float s = (s0 + s1) + (s2 + s3);
-  if (m < 400) dw[(co * 16 + (m & 15)) * 25 + (m >> 4)] = s;
-  else if (db) db[co] = s;
+  if (c < nparts) s0 += p[c * stride];
+  s_sub[warp][co] = s0 + s1;
+  __syncthreads();
+  if (warp == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += s_sub[w8][co];
+    if (m < 400) dw[(co * 16 + (m & 15)) * 25 + (m >> 4)] = s;
+    else if (db) db[co] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1068,7 +1089,7 @@ void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, fl
   opt_in_smem(conv5x5_wgrad_umma_kernel, Cfg::kSmem);
   conv5x5_wgrad_umma_kernel<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(x, tm_dy, ones, scr.partials, s.B, s.H, s.W, tiles);
   check_launch("conv5x5_wgrad_umma");
-  wgrad_fold_kernel<<<(401 * 32 + 255) / 256, 256, 0, st>>>(scr.partials, grid, dw, db);
+  wgrad_fold_kernel<<<401, 256, 0, st>>>(scr.partials, grid, dw, db);
   check_launch("wgrad_fold");
 }
 

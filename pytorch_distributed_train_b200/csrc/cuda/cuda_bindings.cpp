@@ -131,8 +131,11 @@ void register_cuda_bindings(py::module_& m) {
     TORCH_CHECK(x.size(3) == s.Cin, "conv5x5_fwd: x channels ", x.size(3), " != weight Cin ", s.Cin);
     at::Tensor y = at::empty({s.B, s.H, s.W, s.Cout}, x.options());
     at::Tensor stats = want_stats ? at::empty({2 * s.Cout + 1}, x.options()) : at::Tensor();
-    const bool tc = impl == "tcgen05" || (impl == "auto" && conv_tcgen05_supported(s));
-    if (impl == "tma") launch_conv5x5_fwd_tma(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
+    // auto / tma → fully TMA-fed tcgen05 kernel; tcgen05 → cp.async-gather tcgen05 kernel; simt → CUDA cores.
+    // Shapes the tensor-core kernels do not cover (conv1: K = 25) always take the SIMT kernel.
+    const bool sup = conv_tcgen05_supported(s);
+    const bool tc = sup && impl == "tcgen05";
+    if (sup && (impl == "tma" || impl == "auto")) launch_conv5x5_fwd_tma(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
                                               want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
     else if (tc) launch_conv5x5_fwd_tcgen05(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
                                        want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
@@ -148,8 +151,9 @@ void register_cuda_bindings(py::module_& m) {
     s.Cin = static_cast<int>(w.size(1));
     TORCH_CHECK(dy.size(3) == s.Cout, "conv5x5_dgrad: dy channels must equal weight Cout");
     at::Tensor dx = at::empty({s.B, s.H, s.W, s.Cin}, dy.options());
-    const bool tc = impl == "tcgen05" || (impl == "auto" && conv_tcgen05_supported(s));
-    if (impl == "tma") launch_conv5x5_dgrad_tma(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
+    const bool sup = conv_tcgen05_supported(s);
+    const bool tc = sup && impl == "tcgen05";
+    if (sup && (impl == "tma" || impl == "auto")) launch_conv5x5_dgrad_tma(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
     else if (tc) launch_conv5x5_dgrad_tcgen05(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
     else launch_conv5x5_dgrad(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
     return dx;
@@ -159,7 +163,8 @@ void register_cuda_bindings(py::module_& m) {
     chk(dy, "dy"); chk(x, "x"); chk(dw, "dw");
     c10::cuda::CUDAGuard g(dy.device());
     ConvShape s = conv_shape(x, dw);
-    const bool tc = impl == "tcgen05" || (impl == "auto" && conv_tcgen05_supported(s) && wgrad_tcgen05_default());
+    const bool sup = conv_tcgen05_supported(s);
+    const bool tc = sup && (impl == "tcgen05" || ((impl == "auto" || impl == "tma") && wgrad_tcgen05_default()));
     if (tc) launch_conv5x5_wgrad_tcgen05(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
     else launch_conv5x5_wgrad(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
   }, py::arg("dy"), py::arg("x"), py::arg("dw"), py::arg("db") = py::none(), py::arg("impl") = "auto");

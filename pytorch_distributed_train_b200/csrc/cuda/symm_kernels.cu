@@ -90,7 +90,7 @@ __device__ __forceinline__ uint4 acc_pack(typename Acc<T>::type (&a)[VecOf<T>::N
 // ---- one-shot push allreduce -----------------------------------------------------------------------
 // nvec: number of 16-byte vectors (host pads the tail into a scratch vector); slot stride = nvec*16.
 template <typename T, int OP, bool MC>
-__global__ void __launch_bounds__(512) allreduce_oneshot_push_kernel(SymmDev d, const uint4* __restrict__ in, uint4* out,
+__global__ void __launch_bounds__(512) allreduce_oneshot_push_kernel(const __grid_constant__ SymmDev d, const uint4* __restrict__ in, uint4* out,
                                                                       size_t stage_off, size_t nvec, float scale) {
   SymmEpoch ep(d, blockIdx.x);
   const size_t slot_bytes = nvec * 16;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(512) allreduce_oneshot_push_kernel(SymmDev d, 
 
 // ---- fused one-shot allreduce + SGD ------------------------------------------------------------------
 template <bool MC>
-__global__ void __launch_bounds__(512) allreduce_sgd_oneshot_kernel(SymmDev d, float4* grad, float4* param, float4* mom,
+__global__ void __launch_bounds__(512) allreduce_sgd_oneshot_kernel(const __grid_constant__ SymmDev d, float4* grad, float4* param, float4* mom,
                                                                     size_t stage_off, size_t nvec, float scale,
                                                                     const float* lr_dev, float lr_host, float momentum,
                                                                     float dampening, float wd, int nesterov, int first_step) {
@@ -180,7 +180,7 @@ template <> __device__ __forceinline__ uint4 nvls_ld_reduce<__half>(const void* 
 template <> __device__ __forceinline__ uint4 nvls_ld_reduce<__nv_bfloat16>(const void* p) { return multimem_ld_reduce_bf16x8(p); }
 
 template <typename T, int OP, bool NVLS>
-__global__ void __launch_bounds__(512) allreduce_twoshot_kernel(SymmDev d, size_t buf_off, size_t nvec, float scale) {
+__global__ void __launch_bounds__(512) allreduce_twoshot_kernel(const __grid_constant__ SymmDev d, size_t buf_off, size_t nvec, float scale) {
   SymmEpoch ep(d, blockIdx.x);
   const size_t per = (nvec + d.world - 1) / d.world;  // vectors per slice
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(512) allreduce_twoshot_kernel(SymmDev d, size_
 
 // ---- pull-style data movement -------------------------------------------------------------------------
 // mode 0: broadcast (root → dst), 1: allgather, 2: alltoall
-__global__ void __launch_bounds__(512) pull_kernel(SymmDev d, size_t src_off, char* dst, size_t nbytes, size_t dst_stride,
+__global__ void __launch_bounds__(512) pull_kernel(const __grid_constant__ SymmDev d, size_t src_off, char* dst, size_t nbytes, size_t dst_stride,
                                                    int root, int mode, int exit_barrier) {
   SymmEpoch ep(d, blockIdx.x);
   symm_barrier_block(d, blockIdx.x, ep.next());
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(512) pull_kernel(SymmDev d, size_t src_off, ch
   ep.commit(d, blockIdx.x);
 }
 
-__global__ void barrier_kernel(SymmDev d) {
+__global__ void barrier_kernel(const __grid_constant__ SymmDev d) {
   SymmEpoch ep(d, 0);
   symm_barrier_block(d, 0, ep.next());
   ep.commit(d, 0);

@@ -95,6 +95,29 @@ def worker(rank, world, max_mb, iters, out_path):
             comm.allreduce(buf, dist.ReduceOp.SUM, 1.0).wait()
 
         row["auto_us"] = timeit(run_auto, n_iter)
+
+        # Device-side latency without host launch/stream-hop overhead: 16 back-to-back collectives
+        # captured in one CUDA graph (how they run inside the graph-replayed training step).
+        def graphed(fn):
+            chain = 16
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                for _ in range(chain):
+                    fn()
+            return timeit(gr.replay, max(5, n_iter // chain)) / chain
+
+        if nbytes <= (4 << 20):
+            try:
+                row["graph_ours_us"] = graphed(lambda: comm.allreduce_inline(buf, dist.ReduceOp.SUM, 1.0))
+                row["graph_nccl_us"] = graphed(lambda: ref.comm.allreduce(plain, dist.ReduceOp.SUM, 1.0).wait())
+            except Exception as e:  # noqa: BLE001
+                row["graph_err"] = str(e)[:120]
         best = min((v, k) for k, v in row.items() if k.endswith("_us") and not k.startswith("nccl") and k != "auto_us")
         row["best"] = best[1][:-3]
         row["best_us"] = best[0]

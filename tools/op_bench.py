@@ -68,6 +68,10 @@ def main():
         ("conv1_fwd_simt", lambda: _C.conv5x5_fwd(x1, w1, b1, True, "simt")),
         ("bn_relu_pool1_fwd", lambda: _C.bn_relu_pool_fwd(y1, st1, g1, be1, None, None, None, 0.1, 1e-5, False)),
         ("conv2_fwd_tcgen05(+repack)", lambda: _C.conv5x5_fwd(a1, w2, b2, True, "tcgen05")),
+        ("conv2_fwd_tma_im2col(+repack)", lambda: _C.conv5x5_fwd(a1, w2, b2, True, "tma")),
+        ("conv2_dgrad_tma_im2col(+repack)", lambda: _C.conv5x5_dgrad(dy2, w2, "tma")),
+        ("conv2_wgrad_tcgen05(+fold)", lambda: _C.conv5x5_wgrad(dy2, a1, dw2, dbb2, "tcgen05")),
+        ("conv2_wgrad_simt(+fold)", lambda: _C.conv5x5_wgrad(dy2, a1, dw2, dbb2, "simt")),
         ("conv2_fwd_simt", lambda: _C.conv5x5_fwd(a1, w2, b2, True, "simt")),
         ("bn_relu_pool2_fwd", lambda: _C.bn_relu_pool_fwd(y2, st2, g2, be2, None, None, None, 0.1, 1e-5, True)),
         ("linear_fwd", lambda: _C.linear_fwd(flat, wf, bf)),
