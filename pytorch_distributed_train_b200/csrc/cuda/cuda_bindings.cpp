@@ -65,11 +65,12 @@ ReduceScratch scratch(const at::Tensor& like) {
   return r;
 }
 
-// The tensor-core weight gradient is opt-in (PDT_WGRAD_TCGEN05=1) until its GPU numerics test is green.
+// The tensor-core weight gradient is the default (exact-integer GPU test green, 31.8 µs vs 70.7 µs SIMT
+// on B200, profiles/op_bench.md); PDT_WGRAD_TCGEN05=0 falls back to the SIMT kernel.
 bool wgrad_tcgen05_default() {
   static const bool on = [] {
     const char* e = getenv("PDT_WGRAD_TCGEN05");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }();
   return on;
 }

@@ -171,6 +171,63 @@ def test_ddp_convnet_matches_torch_ddp_nccl(syncbn):
         assert r["copies"] == 0 and sum(r["buckets"]) == 116136
 
 
+def _resnet(rank, world, syncbn, port):
+    """BASELINE.json config 4 at test scale: multi-bucket reduce (11.7 M params) + generic SyncBN kernels."""
+    import torch.distributed as td
+
+    dev = torch.device("cuda", rank)
+    steps = 3
+
+    def data(s):
+        g = torch.Generator().manual_seed(77 * s + rank)
+        return torch.randn(4, 3, 64, 64, generator=g).to(dev), torch.randint(0, 10, (4,), generator=g).to(dev)
+
+    torch.manual_seed(0)
+    net = pdt.models.resnet18(num_classes=10)
+    if syncbn:
+        net = pdt.SyncBatchNorm.convert_sync_batchnorm(net)
+    net.to(dev)
+    opt = pdt.optim.SGD(net.parameters(), 0.05, momentum=0.9)
+    ddp = pdt.DistributedDataParallel(net, device_ids=[rank], bucket_cap_mb=8, first_bucket_cap_mb=1)
+    ours = []
+    for s in range(steps):
+        x, y = data(s)
+        loss = nn.functional.cross_entropy(ddp(x), y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ours.append(loss.item())
+    info = ddp._get_ddp_logging_data()
+    td.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
+    torch.manual_seed(0)
+    ref = pdt.models.resnet18(num_classes=10)
+    if syncbn:
+        ref = nn.SyncBatchNorm.convert_sync_batchnorm(ref)
+    ref.to(dev)
+    ropt = torch.optim.SGD(ref.parameters(), 0.05, momentum=0.9)
+    rddp = nn.parallel.DistributedDataParallel(ref, device_ids=[rank], bucket_cap_mb=8)
+    theirs = []
+    for s in range(steps):
+        x, y = data(s)
+        loss = nn.functional.cross_entropy(rddp(x), y)
+        ropt.zero_grad()
+        loss.backward()
+        ropt.step()
+        theirs.append(loss.item())
+    td.destroy_process_group()
+    flat = torch.cat([p.detach().reshape(-1) for p in ddp.parameters()])
+    return {"ours": ours, "theirs": theirs, "psum": flat.double().sum().item(), "buckets": info["bucket_sizes"]}
+
+
+@pytest.mark.parametrize("syncbn", [False, True])
+def test_ddp_resnet18_multibucket_matches_torch(syncbn):
+    res = run_ranks(_resnet, _world(), syncbn, free_port(), backend="nccl")
+    assert len({r["psum"] for r in res}) == 1, "parameters diverged between ranks"
+    assert len(res[0]["buckets"]) >= 3 and sum(res[0]["buckets"]) == 4 * 11181642
+    for r in res:
+        assert max(abs(a - b) for a, b in zip(r["ours"], r["theirs"])) < 5e-2, (r["ours"], r["theirs"])
+
+
 def _graphed(rank, world, syncbn):
     from pytorch_distributed_train_b200.engine import GraphedTrainStep
 
