@@ -113,7 +113,8 @@ def run_ours(args):
         launches_per_step = None
     else:
         before = _C.kernel_launch_count()
-        graphed = GraphedTrainStep(ddp, criterion, optimizer, (dev_x[0], dev_y[0]), warmup=3, zero_grad_set_to_none=True)
+        graphed = GraphedTrainStep(ddp, criterion, optimizer, (dev_x[0], dev_y[0]), warmup=3, zero_grad_set_to_none=True,
+                                   fuse_optimizer=os.environ.get("PDT_FUSE_OPT", "1") != "0")
         launches_per_step = graphed.kernels_per_replay
         step = graphed
         del before
@@ -186,7 +187,8 @@ def run_ours(args):
                        "seq_len": None, "parallelism": f"dp{world}", "optimizer": "SGD lr=1e-4", "syncbn": args.syncbn,
                        "comm": info.get("comm_kind"), "cuda_graph": not args.no_graph,
                        "inputs": f"rotating pool of {POOL_BATCHES} batches = {dev_x.numel() * 4 / 1e6:.0f} MB > 126 MB L2 (no explicit L2 flush)",
-                       "buckets": info.get("bucket_sizes"), "grad_copies_into_bucket": info.get("copies_into_bucket")},
+                       "buckets": info.get("bucket_sizes"), "grad_copies_into_bucket": info.get("copies_into_bucket"),
+                       "fused_allreduce_sgd": bool(getattr(optimizer, "_fused_active", False))},
             "gpu_launches": int(gpu_launches),
             "gpu_launches_per_step": launches_per_step if launches_per_step is not None else eager_launches / K,
             "clocks": clock_block(clocks),
@@ -238,6 +240,9 @@ def run_reference(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(local_rank)
 
+    # The reference rendezvouses over its own tcp:// endpoint (ddp_example.py:55); under torchrun the
+    # TORCHELASTIC_USE_AGENT_STORE flag would make *every* rank a client of that port (nobody serves it).
+    os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)
     # ---- (1) stack-only: the reference's model / DDP / loss / optimizer with device-resident inputs ----
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{base_port + 11}", world_size=world, rank=rank)
     torch.manual_seed(0)

@@ -183,6 +183,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("grads_are_views", &Reducer::grads_are_views)
       .def("install_grad_views", &Reducer::install_grad_views, py::arg("zero") = true)
       .def("set_postscale", &Reducer::set_postscale)
+      .def("set_defer_comm", &Reducer::set_defer_comm)
+      .def_property_readonly("defer_comm", &Reducer::defer_comm)
       .def("stats", [](Reducer& r) {
         ReducerStats s = r.stats();
         py::dict d;

@@ -105,10 +105,13 @@ void register_cuda_bindings(py::module_& m) {
            py::arg("store"), py::arg("rank"), py::arg("size"), py::arg("device"), py::arg("timeout") = 600.0,
            py::arg("heap_bytes") = int64_t(1) << 30)
       .def("allreduce_inline", &SymmComm::allreduce_inline, py::arg("tensor"), py::arg("op") = ReduceOp::SUM, py::arg("postscale") = 1.0)
+      .def("broadcast_inline", &SymmComm::broadcast_inline, py::arg("tensor"), py::arg("root") = 0)
       .def("allreduce_sgd_inline", &SymmComm::allreduce_sgd_inline, py::arg("grad"), py::arg("param"), py::arg("momentum_buf") = py::none(),
            py::arg("lr") = 0.0, py::arg("lr_tensor") = py::none(), py::arg("momentum") = 0.0, py::arg("dampening") = 0.0,
            py::arg("weight_decay") = 0.0, py::arg("nesterov") = false, py::arg("first_step") = false)
       .def_property_readonly("has_multicast", &SymmComm::has_multicast)
+      .def_property_readonly("fused_step_max_bytes",
+                             [](SymmComm& c) { return static_cast<int64_t>(c.heap().staging_half_bytes(kChanInline) / std::max(1, c.size())); })
       .def_property("algo", &SymmComm::algo, &SymmComm::set_algo)
       .def("set_oneshot_max_bytes", &SymmComm::set_oneshot_max_bytes)
       .def("set_launch", &SymmComm::set_launch, py::arg("blocks") = 0, py::arg("threads") = 0)

@@ -65,6 +65,7 @@ class SymmComm : public CudaCommBase {
   // Same collective launched directly on the caller's current stream (channel kChanInline):
   // no stream hop — used where the result is needed by the very next kernel (SyncBatchNorm).
   void allreduce_inline(at::Tensor t, ReduceOp op, double postscale);
+  void broadcast_inline(at::Tensor t, int root);
   // Fused mean-allreduce(grad) + SGD(param) in one launch on the caller's stream.
   void allreduce_sgd_inline(at::Tensor grad, at::Tensor param, c10::optional<at::Tensor> momentum_buf, double lr,
                             c10::optional<at::Tensor> lr_tensor, double momentum, double dampening, double weight_decay,
@@ -82,6 +83,7 @@ class SymmComm : public CudaCommBase {
 
  private:
   void do_allreduce(at::Tensor& t, ReduceOp op, double scale, int channel, cudaStream_t s);
+  void do_broadcast(at::Tensor& t, int root, int channel, cudaStream_t s);
   std::shared_ptr<SymmetricHeap> heap_;  // shared with every tensor carved out of it (see alloc_flat)
   std::string algo_ = "auto";   // auto | oneshot | oneshot_mc | twoshot | nvls
   size_t oneshot_max_ = 512 * 1024;

@@ -33,7 +33,7 @@ void check_launch(const char* what) {
 // TRANSPOSED=true computes the data gradient: weights are read as w[ci_k][co_k][24-tap].
 // =====================================================================================================
 template <int CIN, int COUT, int CPT, int TH, bool STATS, bool TRANSPOSED>
-__global__ void __launch_bounds__(448) conv5x5_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(TH >= 14 ? 1024 : 448) conv5x5_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y, float* stats,
                                                       ReduceScratch scr, int B, int H, int W) {
   constexpr int G = COUT / CPT;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(448) conv5x5_kernel(const float* __restrict__ 
     }
     __syncthreads();
     const float cnt = static_cast<float>(B) * H * W;
-    __shared__ float s_tmp[448];
+    __shared__ float s_tmp[1024];
     __shared__ int s_flag;
     grid_fold(blk, 2 * COUT, blockIdx.x, gridDim.x, scr, s_tmp, &s_flag, tid, blockDim.x, CtaSync{}, [&](int i, float v) {
       stats[i] = v;
@@ -211,11 +211,22 @@ __global__ void __launch_bounds__(256) conv5x5_wgrad_kernel(const float* __restr
       out[(co * CIN + ci) * 25 + tap] = s;
     }
   }
-  // bias gradient partial: Σ_pixels dy[:, co]
-  if (tid < COUT) {
+  // bias gradient partial: Σ_pixels dy[:, co] — 256/COUT pixel slices in parallel, folded in slice order
+  {
+    __shared__ float s_db[256];
+    constexpr int SL = 256 / COUT;
+    const int co = tid % COUT, sl = tid / COUT;
     float s = 0.f;
-    for (int pix = 0; pix < npix; ++pix) s += dys[pix * COUT + tid];
-    out[P * COUT + tid] = s;
+    if (tid < 256)
+      for (int pix = sl; pix < npix; pix += SL) s += dys[pix * COUT + co];
+    __syncthreads();
+    if (tid < 256) s_db[tid] = s;
+    __syncthreads();
+    if (tid < COUT) {
+      float tot = 0.f;
+      for (int k = 0; k < SL; ++k) tot += s_db[k * COUT + tid];
+      out[P * COUT + tid] = tot;
+    }
   }
 }
 
@@ -528,33 +539,46 @@ __global__ void bn_bwd_apply_nchw_kernel(const float* __restrict__ dy, const flo
 // =====================================================================================================
 // Linear + cross entropy
 // =====================================================================================================
-template <int NMAX>
+// out[row, n] = Σ_k x[row, k] w[n, k] + b[n].  A CTA owns R rows so every weight element it loads is
+// reused R times (25 CTAs re-read the 62 KB weight matrix instead of 100), threads split K.
+template <int NMAX, int R>
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ b, float* __restrict__ out, int B, int K, int N) {
-  const int row = blockIdx.x;
-  const float* xr = x + static_cast<size_t>(row) * K;
-  float acc[NMAX];
+  const int row0 = blockIdx.x * R;
+  float acc[R][NMAX];
 #pragma unroll
-  for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[r][n] = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const float xv = xr[k];
+    float wv[NMAX];
 #pragma unroll
-    for (int n = 0; n < NMAX; ++n)
-      if (n < N) acc[n] = fmaf(xv, w[static_cast<size_t>(n) * K + k], acc[n]);
+    for (int n = 0; n < NMAX; ++n) wv[n] = n < N ? w[static_cast<size_t>(n) * K + k] : 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float xv = (row0 + r < B) ? x[static_cast<size_t>(row0 + r) * K + k] : 0.f;
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n) acc[r][n] = fmaf(xv, wv[n], acc[r][n]);
+    }
   }
-  __shared__ float red[8][NMAX];
+  __shared__ float red[8][R * NMAX];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int n = 0; n < NMAX; ++n) {
-    float v = acc[n];
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) red[warp][n] = v;
-  }
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      float v = acc[r][n];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) red[warp][r * NMAX + n] = v;
+    }
   __syncthreads();
-  if (threadIdx.x < N) {
-    float s = b ? b[threadIdx.x] : 0.f;
-    for (int wi = 0; wi < (blockDim.x >> 5); ++wi) s += red[wi][threadIdx.x];
-    out[static_cast<size_t>(row) * N + threadIdx.x] = s;
+  if (threadIdx.x < R * NMAX) {
+    const int r = threadIdx.x / NMAX, n = threadIdx.x % NMAX;
+    if (n < N && row0 + r < B) {
+      float s = b ? b[n] : 0.f;
+      for (int wi = 0; wi < (blockDim.x >> 5); ++wi) s += red[wi][threadIdx.x];
+      out[static_cast<size_t>(row0 + r) * N + n] = s;
+    }
   }
 }
 
@@ -699,10 +723,18 @@ void launch_conv5x5_fwd(const float* x, const float* w, const float* bias, float
                         cudaStream_t st) {
   constexpr int TH = 7;
   if (s.H % TH != 0) throw std::invalid_argument("conv5x5_fwd: H must be a multiple of 7");
-  const int blocks = s.B * (s.H / TH);
+  // conv1 (1→16): one CTA per image when it fits (784 threads): a single wave of 100 CTAs instead of
+  // 2.7 waves of 400 quarter-image CTAs, and 100 instead of 400 partial rows in the BN-statistics fold
+  const bool whole_image = s.Cin == 1 && s.Cout == 16 && s.H == 28 && s.W * 28 <= 1024;
+  const int blocks = whole_image ? s.B : s.B * (s.H / TH);
   if (stats && (static_cast<long long>(blocks + blocks / kFoldGroup + 1) * 2 * s.Cout > scr.capacity_floats || blocks / kFoldGroup + 2 > scr.counters))
     throw std::invalid_argument("conv5x5_fwd: reduction scratch too small");
-  if (s.Cin == 1 && s.Cout == 16) {
+  if (whole_image) {
+    const int threads = (28 * s.W + 31) / 32 * 32;
+    const size_t sm = conv_smem(1, 16, 28, s.W, threads);
+    if (stats) conv5x5_kernel<1, 16, 16, 28, true, false><<<blocks, threads, sm, st>>>(x, w, bias, y, stats, scr, s.B, s.H, s.W);
+    else conv5x5_kernel<1, 16, 16, 28, false, false><<<blocks, threads, sm, st>>>(x, w, bias, y, stats, scr, s.B, s.H, s.W);
+  } else if (s.Cin == 1 && s.Cout == 16) {
     const int threads = (TH * s.W + 31) / 32 * 32;
     const size_t sm = conv_smem(1, 16, TH, s.W, threads);
     if (stats) conv5x5_kernel<1, 16, 16, TH, true, false><<<blocks, threads, sm, st>>>(x, w, bias, y, stats, scr, s.B, s.H, s.W);
@@ -735,11 +767,17 @@ void launch_conv5x5_dgrad(const float* dy, const float* w, float* dx, ConvShape 
 void launch_conv5x5_wgrad(const float* dy, const float* x, float* dw, float* db, ConvShape s, ReduceScratch scr, cudaStream_t st) {
   constexpr int TH = 7;
   if (s.H % TH != 0) throw std::invalid_argument("conv5x5_wgrad: H must be a multiple of 7");
-  const int blocks = s.B * (s.H / TH);
+  const bool whole_image = s.Cin == 1 && s.Cout == 16 && s.H == 28;  // conv1: one CTA per image, 100 partial rows
+  const int blocks = whole_image ? s.B : s.B * (s.H / TH);
   const int width = 25 * s.Cin * s.Cout + s.Cout;
   if (static_cast<long long>(blocks) * width > scr.capacity_floats) throw std::invalid_argument("conv5x5_wgrad: reduction scratch too small");
-  const size_t xs_f = static_cast<size_t>(s.Cin) * (TH + 4) * (s.W + 4);
-  if (s.Cin == 1 && s.Cout == 16) {
+  const size_t xs_f = static_cast<size_t>(s.Cin) * ((whole_image ? 28 : TH) + 4) * (s.W + 4);
+  if (whole_image) {
+    const size_t fold_f = static_cast<size_t>(8) * 25 * 16;
+    const size_t sm = (xs_f + 4 + static_cast<size_t>(28) * s.W * s.Cout + fold_f) * sizeof(float);
+    set_smem(conv5x5_wgrad_kernel<1, 16, 28>, sm);
+    conv5x5_wgrad_kernel<1, 16, 28><<<blocks, 256, sm, st>>>(dy, x, scr.partials, s.B, s.H, s.W);
+  } else if (s.Cin == 1 && s.Cout == 16) {
     const size_t fold_f = static_cast<size_t>(8) * 25 * 16;  // [warps][P*COUT] after dys
     const size_t sm = (xs_f + 4 + static_cast<size_t>(TH) * s.W * s.Cout + fold_f) * sizeof(float);
     conv5x5_wgrad_kernel<1, 16, TH><<<blocks, 256, sm, st>>>(dy, x, scr.partials, s.B, s.H, s.W);
@@ -822,7 +860,7 @@ void launch_bn_bwd_apply_nchw(const float* dy, const float* x, const float* mean
 
 void launch_linear_fwd(const float* x, const float* w, const float* b, float* out, int B, int K, int N, cudaStream_t st) {
   if (N > 16) throw std::invalid_argument("linear_fwd (fused head): N <= 16 supported; wider layers use the GEMM path");
-  linear_fwd_kernel<16><<<B, 256, 0, st>>>(x, w, b, out, B, K, N);
+  linear_fwd_kernel<16, 4><<<(B + 3) / 4, 256, 0, st>>>(x, w, b, out, B, K, N);
   check_launch("linear_fwd");
 }
 void launch_linear_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, float* db, int B, int K, int N,

@@ -205,29 +205,39 @@ void SymmComm::allreduce_sgd_inline(at::Tensor grad, at::Tensor param, c10::opti
                                first_step, heap_->has_multicast() && algo_ != "oneshot", cfg_, s);
 }
 
+void SymmComm::do_broadcast(at::Tensor& t, int root, int channel, cudaStream_t s) {
+  const size_t nbytes = t.nbytes();
+  if (nbytes == 0 || size_ == 1) return;
+  SymmDev d = heap_->dev(channel);
+  if (heap_->contains(t.data_ptr(), nbytes)) {
+    launch_broadcast_pull(d, heap_->offset_of(t.data_ptr()), t.data_ptr(), nbytes, root, /*exit_barrier=*/true, cfg_, s);
+    return;
+  }
+  const size_t half = heap_->staging_half_bytes(channel);
+  char* p = static_cast<char*>(t.data_ptr());
+  for (size_t done = 0; done < nbytes; done += half) {
+    const size_t n = std::min(half, nbytes - done);
+    const size_t stage = heap_->staging_off(channel, heap_->next_parity(channel));
+    if (rank_ == root) PDT_CUDA_CHECK(cudaMemcpyAsync(heap_->local_base() + stage, p + done, n, cudaMemcpyDeviceToDevice, s));
+    // the root's destination is its own (already correct) tensor: pull into it anyway would be a
+    // self-copy from staging — harmless and keeps every rank on the same barrier sequence
+    launch_broadcast_pull(d, stage, p + done, n, root, /*exit_barrier=*/false, cfg_, s);
+  }
+}
+
 std::shared_ptr<CommWork> SymmComm::broadcast(at::Tensor t, int root) {
   check(t, "broadcast");
   TORCH_CHECK(root >= 0 && root < size_, "broadcast: invalid root");
   record("broadcast", &t);
-  return enqueue({t}, [&](cudaStream_t s) {
-    const size_t nbytes = t.nbytes();
-    if (nbytes == 0 || size_ == 1) return;
-    SymmDev d = heap_->dev(kChanComm);
-    if (heap_->contains(t.data_ptr(), nbytes)) {
-      launch_broadcast_pull(d, heap_->offset_of(t.data_ptr()), t.data_ptr(), nbytes, root, /*exit_barrier=*/true, cfg_, s);
-      return;
-    }
-    const size_t half = heap_->staging_half_bytes(kChanComm);
-    char* p = static_cast<char*>(t.data_ptr());
-    for (size_t done = 0; done < nbytes; done += half) {
-      const size_t n = std::min(half, nbytes - done);
-      const size_t stage = heap_->staging_off(kChanComm, heap_->next_parity(kChanComm));
-      if (rank_ == root) PDT_CUDA_CHECK(cudaMemcpyAsync(heap_->local_base() + stage, p + done, n, cudaMemcpyDeviceToDevice, s));
-      // the root's destination is its own (already correct) tensor: pull into it anyway would be a
-      // self-copy from staging — harmless and keeps every rank on the same barrier sequence
-      launch_broadcast_pull(d, stage, p + done, n, root, /*exit_barrier=*/false, cfg_, s);
-    }
-  });
+  return enqueue({t}, [&](cudaStream_t s) { do_broadcast(t, root, kChanComm, s); });
+}
+
+void SymmComm::broadcast_inline(at::Tensor t, int root) {
+  check(t, "broadcast");
+  TORCH_CHECK(root >= 0 && root < size_, "broadcast: invalid root");
+  record("broadcast_inline", &t);
+  c10::cuda::CUDAGuard guard(device_);
+  do_broadcast(t, root, kChanInline, c10::cuda::getCurrentCUDAStream(device_).stream());
 }
 
 std::shared_ptr<CommWork> SymmComm::allgather(at::Tensor out, at::Tensor in) {

@@ -236,9 +236,17 @@ __global__ void __launch_bounds__(512) pull_kernel(const __grid_constant__ SymmD
     if (mode == 0 && d.rank == root && dst == d.peer[root] + src_off) break;  // in place at the root
     const char* src = d.peer[q] + src_off + (mode == 2 ? static_cast<size_t>(d.rank) * dst_stride : 0);
     char* out = dst + (mode == 0 ? 0 : static_cast<size_t>(q) * dst_stride);
-    for (size_t i = first; i < nvec; i += stride) st_vec(out + i * 16, ld_vec_nc(src + i * 16));
-    if (tail && blockIdx.x == 0 && threadIdx.x < tail)
-      out[nvec * 16 + threadIdx.x] = *reinterpret_cast<const volatile char*>(src + nvec * 16 + threadIdx.x);
+    const uintptr_t mis = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out);
+    if ((mis & 15) == 0) {
+      for (size_t i = first; i < nvec; i += stride) st_vec(out + i * 16, ld_vec_nc(src + i * 16));
+      if (tail && blockIdx.x == 0 && threadIdx.x < tail)
+        out[nvec * 16 + threadIdx.x] = *reinterpret_cast<const volatile char*>(src + nvec * 16 + threadIdx.x);
+    } else if (((mis | nbytes) & 3) == 0) {  // small / oddly-strided slices (e.g. 5 floats per rank): word copies
+      for (size_t i = first; i < nbytes / 4; i += stride)
+        reinterpret_cast<uint32_t*>(out)[i] = *reinterpret_cast<const volatile uint32_t*>(src + i * 4);
+    } else {
+      for (size_t i = first; i < nbytes; i += stride) out[i] = *reinterpret_cast<const volatile char*>(src + i);
+    }
   }
   if (exit_barrier) symm_barrier_block(d, blockIdx.x, ep.next());
   ep.commit(d, blockIdx.x);

@@ -271,7 +271,7 @@ void Reducer::launch_bucket(size_t b) {
     gb.offsets = bk.offsets;
     gb.lengths = bk.lengths;
     bk.py_future = comm_hook_(py::cast(std::move(gb)));
-  } else {
+  } else if (!defer_comm_) {
     bk.work = comm_->allreduce(bk.flat, ReduceOp::SUM, postscale_);
   }
 }

@@ -84,6 +84,10 @@ class Reducer {
   // engine so backward writes land directly in comm-visible memory.
   void install_grad_views(bool zero);
   void set_postscale(double s) { postscale_ = s; }
+  // The optimizer reduces: buckets are filled and gradients re-pointed exactly as in a synchronised
+  // backward, but no collective is launched (a fused allreduce+update kernel consumes the flat buckets).
+  void set_defer_comm(bool on) { defer_comm_ = on; }
+  bool defer_comm() const { return defer_comm_; }
 
  private:
   struct Bucket {
@@ -116,6 +120,7 @@ class Reducer {
   bool callback_queued_ = false;
   bool has_rebuilt_ = false;
   double postscale_;
+  bool defer_comm_ = false;
 
   std::vector<Bucket> buckets_;
   std::vector<Loc> locs_;

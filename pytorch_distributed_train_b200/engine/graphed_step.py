@@ -1,5 +1,7 @@
 """Whole-step CUDA graph: forward + loss + backward + bucket allreduce + optimizer update
-captured once and replayed with a single ``cudaGraphLaunch``.
+captured once and replayed with a single ``cudaGraphLaunch``.  With ``fuse_optimizer=True`` (default)
+and a single-bucket model on the NVLink backend, the bucket allreduce and the SGD update are one
+kernel (``optim.SGD.fuse_with_ddp``).
 
 Why this exists: one ConvNet step is ≈10 µs of GPU work behind 60-80 kernel launches in the
 reference stack, so the step is launch/host bound.  The reference's DDP
@@ -20,7 +22,7 @@ import torch
 
 class GraphedTrainStep:
     def __init__(self, model, criterion, optimizer, example_inputs: Sequence[torch.Tensor], warmup: int = 3,
-                 zero_grad_set_to_none: bool = False):
+                 zero_grad_set_to_none: bool = True, fuse_optimizer: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainStep needs CUDA")
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
@@ -29,7 +31,12 @@ class GraphedTrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_loss: Optional[torch.Tensor] = None
         self.replays = 0
+        self.fused_optimizer = False
+        if fuse_optimizer and hasattr(optimizer, "fuse_with_ddp") and hasattr(model, "enable_optimizer_fusion"):
+            optimizer.fuse_with_ddp(model)
+            warmup = max(warmup, 4)  # bucket rebuild after step 1, fusion switches on after step 2
         self._capture(warmup)
+        self.fused_optimizer = bool(getattr(optimizer, "_fused_active", False))
 
     def _eager_step(self):
         out = self.model(self.static_inputs[0])
@@ -66,6 +73,8 @@ class GraphedTrainStep:
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
         for dst, src in zip(self.static_inputs, inputs):
             dst.copy_(src, non_blocking=True)
+        if hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()  # scheduler changes reach the captured step through a device scalar
         self.graph.replay()
         self.replays += 1
         return self.static_loss

@@ -36,6 +36,106 @@ class SGD(torch.optim.Optimizer):
         defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay,
                         nesterov=nesterov, maximize=maximize, capturable=capturable, fused=fused)
         super().__init__(params, defaults)
+        self._ddp = None            # set by fuse_with_ddp()
+        self._fused_active = False
+        self._flat_momentum = None
+        self._lr_dev = {}           # group index -> (device scalar, last host value) when capturable
+
+    # ---- device-resident learning rate (CUDA-graph friendly schedulers) ------------------------------
+    def _lr_tensor(self, gi: int, group, device) -> Optional[torch.Tensor]:
+        if not group.get("capturable") or device.type != "cuda":
+            return None
+        ent = self._lr_dev.get(gi)
+        if ent is None:
+            ent = [torch.full((1,), float(group["lr"]), dtype=torch.float32, device=device), float(group["lr"])]
+            self._lr_dev[gi] = ent
+        elif ent[1] != float(group["lr"]) and not torch.cuda.is_current_stream_capturing():
+            ent[0].fill_(float(group["lr"]))
+            ent[1] = float(group["lr"])
+        return ent[0]
+
+    def sync_lr(self) -> None:
+        """Push ``param_groups[i]['lr']`` into the device scalars a captured step reads (call between
+        graph replays after a scheduler step; a no-op when nothing changed)."""
+        for gi, group in enumerate(self.param_groups):
+            ent = self._lr_dev.get(gi)
+            if ent is not None and ent[1] != float(group["lr"]):
+                ent[0].fill_(float(group["lr"]))
+                ent[1] = float(group["lr"])
+
+    # ---- DDP fusion: gradient mean-allreduce + update in one kernel ------------------------------------
+    def fuse_with_ddp(self, ddp) -> "SGD":
+        """Let ``step()`` perform the gradient allreduce itself, fused with the parameter update.
+
+        The reference's step is ``backward`` (→ NCCL allreduce of the bucket) followed by a foreach
+        SGD kernel (ddp_example.py:89-92).  When the wrapped model's gradients fit one bucket on the
+        NVLink backend, ours turns the pair into ONE kernel: every rank pushes its flat gradient into
+        its peers' staging slots, crosses one device-side barrier, folds the ``world`` slots in rank
+        order and applies the update to the (bucket-mirroring) flat parameter arena.  The reducer still
+        fills the bucket and re-points ``.grad`` but launches no collective of its own.
+        Activation happens on the first ``step()`` after the reducer has settled its bucket layout;
+        until then (and whenever the preconditions do not hold) the ordinary two-kernel path runs.
+        On backends without the fused kernel the same protocol runs as allreduce + update."""
+        self._ddp = ddp
+        return self
+
+    def _maybe_activate_fusion(self) -> None:
+        ddp = self._ddp
+        if self._fused_active or ddp is None or len(self.param_groups) != 1:
+            return
+        group = self.param_groups[0]
+        if group["maximize"] or ddp.process_group.size() == 1:
+            return
+        mine = [p for p in group["params"]]
+        if len(mine) != len(ddp._params) or {id(p) for p in mine} != {id(p) for p in ddp._params}:
+            return
+        if any(p.dtype != torch.float32 for p in mine):
+            return
+        if not ddp.enable_optimizer_fusion():
+            return
+        if group["momentum"] != 0:
+            flat = torch.zeros_like(ddp.param_arena)
+            for p, off in zip(ddp._params, ddp._param_offsets):
+                view = flat[off:off + p.numel()].view(p.shape)
+                st = self.state[p]
+                if st.get("momentum_buffer") is not None:
+                    view.copy_(st["momentum_buffer"])
+                    st["momentum_buffer"] = view
+            self._flat_momentum = flat
+        self._fused_active = True
+
+    def _fused_step(self) -> bool:
+        ddp = self._ddp
+        if not (self._fused_active and ddp.reducer.defer_comm and ddp.require_backward_grad_sync):
+            return False
+        group = self.param_groups[0]
+        bucket = ddp.reducer.bucket_buffers()[0]
+        arena = ddp.param_arena
+        momentum = group["momentum"]
+        first = False
+        if momentum != 0:
+            first = any(self.state[p].get("momentum_buffer") is None for p in ddp._params)
+        comm = ddp.comm
+        if hasattr(comm, "allreduce_sgd_inline") and bucket.is_cuda:
+            comm.allreduce_sgd_inline(bucket, arena, self._flat_momentum, float(group["lr"]),
+                                      self._lr_tensor(0, group, arena.device), float(momentum), float(group["dampening"]),
+                                      float(group["weight_decay"]), bool(group["nesterov"]), bool(first))
+        else:
+            from ..distributed import ReduceOp
+
+            comm.allreduce(bucket, ReduceOp.SUM, 1.0 / ddp.process_group.size()).wait()
+            g = bucket if group["weight_decay"] == 0 else bucket.add(arena, alpha=group["weight_decay"])
+            if momentum != 0:
+                if first:
+                    self._flat_momentum.copy_(g)
+                else:
+                    self._flat_momentum.mul_(momentum).add_(g, alpha=1 - group["dampening"])
+                g = g.add(self._flat_momentum, alpha=momentum) if group["nesterov"] else self._flat_momentum
+            arena.add_(g, alpha=-group["lr"])
+        if first:
+            for p, off in zip(ddp._params, ddp._param_offsets):
+                self.state[p]["momentum_buffer"] = self._flat_momentum[off:off + p.numel()].view(p.shape)
+        return True
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         if set_to_none:
@@ -52,7 +152,11 @@ class SGD(torch.optim.Optimizer):
                 loss = closure()
         from .. import ops
 
-        for group in self.param_groups:
+        if self._ddp is not None:
+            if self._fused_step():
+                return loss
+            self._maybe_activate_fusion()  # takes effect from the next backward on
+        for gi, group in enumerate(self.param_groups):
             params, grads, bufs = [], [], []
             momentum = group["momentum"]
             for p in group["params"]:
@@ -85,7 +189,8 @@ class SGD(torch.optim.Optimizer):
                     mbufs = [st["momentum_buffer"] for st in bufs]
                 ops.sgd_step(params, grads, mbufs, lr=group["lr"], momentum=momentum, dampening=group["dampening"],
                              weight_decay=group["weight_decay"], nesterov=group["nesterov"],
-                             maximize=group["maximize"], first_step=first)
+                             maximize=group["maximize"], first_step=first,
+                             lr_tensor=self._lr_tensor(gi, group, params[0].device))
                 continue
             # reference math through foreach ops (CPU / exotic dtypes)
             gs = [(-g if group["maximize"] else g) for g in grads] if group["maximize"] else list(grads)

@@ -172,6 +172,7 @@ class DistributedDataParallel(nn.Module):
             flatten_parameters = self.device.type == "cuda" and getattr(self.process_group, "comm_kind", "") == "nvlink"
         self.param_arena = None
         self.buffer_arenas = {}
+        self.buffer_arena = None
         if flatten_parameters:
             self._flatten_into_arenas()
         if init_sync:
@@ -221,24 +222,63 @@ class DistributedDataParallel(nn.Module):
                     p.data = view
             self.param_arena = arena
             self._param_offsets = offs
+        # buffers of every dtype share ONE byte arena, so the per-step buffer sync is one broadcast kernel
         bufs = {}
         for b in self._buffers_to_sync:
             bufs.setdefault(b.dtype, []).append(b)
+        regions, total_bytes = [], 0
         for dtype, bs in bufs.items():
-            a = max(1, 16 // max(1, bs[0].element_size()))
+            esize = max(1, bs[0].element_size())
+            a = max(1, 16 // esize)
             total, offs = 0, []
             for b in bs:
                 total = (total + a - 1) // a * a
                 offs.append(total)
                 total += b.numel()
             total = (total + a - 1) // a * a
-            arena = self.comm.alloc_flat(total, dtype, self.device)
+            regions.append((dtype, bs, offs, total_bytes, total))
+            total_bytes += total * esize
+        if total_bytes:
+            self.buffer_arena = self.comm.alloc_flat(total_bytes, torch.uint8, self.device)
             with torch.no_grad():
-                for b, off in zip(bs, offs):
-                    view = arena[off:off + b.numel()].view(b.shape)
-                    view.copy_(b.data)
-                    b.data = view
-            self.buffer_arenas[dtype] = arena
+                for dtype, bs, offs, start, total in regions:
+                    region = self.buffer_arena[start:start + total * bs[0].element_size()].view(dtype)
+                    for b, off in zip(bs, offs):
+                        view = region[off:off + b.numel()].view(b.shape)
+                        view.copy_(b.data)
+                        b.data = view
+                    self.buffer_arenas[dtype] = region
+
+    def enable_optimizer_fusion(self) -> bool:
+        """Prepare for a fused allreduce+update optimizer step (``optim.SGD.fuse_with_ddp``): once the
+        reducer has settled on a single bucket, re-home the parameters into an arena that mirrors
+        the bucket element for element and stop the reducer from launching its own collective.
+        Returns False (and changes nothing) when the preconditions do not hold."""
+        if getattr(self, "_defer_comm", False):
+            return True
+        st = self.reducer.stats()
+        if (not st["has_rebuilt_buckets"] or len(st["bucket_indices"]) != 1 or self._comm_hook_registered
+                or self.find_unused_parameters or not self.gradient_as_bucket_view):
+            return False
+        flat = self.reducer.bucket_buffers()[0]
+        views = self.reducer.grad_views()
+        if flat.dtype != torch.float32 or any(not v.is_contiguous() for v in views):
+            return False
+        limit = getattr(self.comm, "fused_step_max_bytes", None)
+        if limit is not None and flat.numel() * 4 > limit:
+            return False
+        offs = [(v.data_ptr() - flat.data_ptr()) // 4 for v in views]
+        arena = self.comm.alloc_flat(flat.numel(), torch.float32, self.device)
+        with torch.no_grad():
+            arena.zero_()
+            for p, off in zip(self._params, offs):
+                view = arena[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        self.param_arena, self._param_offsets = arena, offs
+        self._defer_comm = True
+        self.reducer.set_defer_comm(True)
+        return True
 
     def _sync_module_states(self):
         if self.process_group.size() == 1:
@@ -255,9 +295,11 @@ class DistributedDataParallel(nn.Module):
     def _sync_buffers(self):
         if not self._buffers_to_sync or self.process_group.size() == 1:
             return
-        if self.buffer_arenas:
-            for arena in self.buffer_arenas.values():
-                self.comm.broadcast(arena, 0).wait()
+        if self.buffer_arena is not None:
+            if hasattr(self.comm, "broadcast_inline"):
+                self.comm.broadcast_inline(self.buffer_arena, 0)  # our kernel, on the compute stream
+            else:
+                self.comm.broadcast(self.buffer_arena, 0).wait()
         else:
             broadcast_coalesced(self.comm, self._buffers_to_sync, 0)
 
@@ -299,6 +341,8 @@ class DistributedDataParallel(nn.Module):
         if rebuilt:
             self.reducer.apply_rebuild(layout)
             self._rebuild_checked = True
+        if getattr(self, "_defer_comm", False):
+            self.reducer.set_defer_comm(True)
         self._publish_grad_views()
 
     def _publish_grad_views(self):

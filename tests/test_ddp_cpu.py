@@ -373,3 +373,38 @@ def test_state_dict_roundtrip_and_pickle_keys():
 def test_requires_process_group():
     with pytest.raises(RuntimeError):
         pdt.DistributedDataParallel(pdt.models.ConvNet())
+
+
+def _fused_opt(rank, world, momentum):
+    """optim.SGD.fuse_with_ddp: the optimizer owns the gradient allreduce; results must equal the
+    reducer-driven path step for step (protocol test on the CPU backend; the one-kernel version is
+    tests/test_gpu_comm.py::test_fused_allreduce_sgd)."""
+    out = []
+    for fuse in (False, True):
+        torch.manual_seed(0)
+        model = pdt.models.ConvNet()
+        opt = pdt.optim.SGD(model.parameters(), 0.05, momentum=momentum, weight_decay=1e-3 if momentum else 0.0)
+        ddp = pdt.DistributedDataParallel(model)
+        if fuse:
+            opt.fuse_with_ddp(ddp)
+        crit = pdt.nn.CrossEntropyLoss()
+        for s in range(6):
+            x, y = _data(rank, s)
+            loss = crit(ddp(x), y)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        assert bool(opt._fused_active) == fuse
+        if fuse:
+            assert ddp.reducer.defer_comm and ddp._get_ddp_logging_data()["params_flattened"]
+            # gradients still read as the averaged gradient after step()
+            g = [p.grad.clone() for p in ddp.parameters()]
+            assert all(torch.isfinite(t).all() for t in g)
+        out.append(torch.cat([p.detach().flatten() for p in ddp.parameters()]))
+    return out
+
+
+@pytest.mark.parametrize("momentum", [0.0, 0.9])
+def test_optimizer_fused_allreduce_matches_reducer_path(momentum):
+    for plain, fused in run_ranks(_fused_opt, 2, momentum):
+        assert torch.allclose(plain, fused, rtol=1e-5, atol=1e-6)

@@ -256,3 +256,48 @@ def test_graph_captured_step_keeps_ranks_in_lockstep(syncbn):
     assert len({r[2] for r in res}) == 1
     assert all(r[1] < r[0] for r in res), res
     print("kernels per replay:", res[0][3])
+
+
+def _fused_sgd(rank, world, momentum):
+    """One-kernel allreduce+SGD (optim.SGD.fuse_with_ddp) vs the reducer-driven two-kernel path, eager
+    and graph-captured: same parameters after the same steps."""
+    from pytorch_distributed_train_b200.engine import GraphedTrainStep
+
+    dev = torch.device("cuda", rank)
+    outs = []
+    for mode in ("plain", "fused", "fused_graph"):
+        torch.manual_seed(0)
+        model = pdt.models.ConvNet().to(dev)
+        opt = pdt.optim.SGD(model.parameters(), 0.05, momentum=momentum, weight_decay=1e-3 if momentum else 0.0)
+        ddp = pdt.DistributedDataParallel(model, device_ids=[rank])
+        crit = pdt.nn.CrossEntropyLoss()
+        if mode == "fused_graph":
+            x, y = _data(rank, 0)
+            step = GraphedTrainStep(ddp, crit, opt, (x.to(dev), y.to(dev)), warmup=0)
+            assert step.fused_optimizer
+            # the capture ran max(warmup, 4) eager steps on batch 0: redo the same on the other arms
+            for s in range(8):
+                x, y = _data(rank, s)
+                step(x.pin_memory(), y.pin_memory())
+        else:
+            if mode == "fused":
+                opt.fuse_with_ddp(ddp)
+            for s in [0, 0, 0, 0] + list(range(8)):
+                x, y = _data(rank, s)
+                loss = crit(ddp(x.to(dev)), y.to(dev))
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+            assert bool(opt._fused_active) == (mode == "fused")
+        torch.cuda.synchronize()
+        outs.append(torch.cat([p.detach().reshape(-1) for p in ddp.parameters()]).cpu())
+    return outs
+
+
+@pytest.mark.parametrize("momentum", [0.0, 0.9])
+def test_fused_allreduce_sgd(momentum):
+    res = run_ranks(_fused_sgd, _world(), momentum, backend="nccl")
+    for plain, fused, graphed in res:
+        assert torch.allclose(plain, fused, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(plain, graphed, rtol=1e-4, atol=1e-6)
+    assert torch.equal(res[0][1], res[-1][1]) and torch.equal(res[0][2], res[-1][2])  # ranks bit-identical

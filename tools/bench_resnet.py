@@ -50,6 +50,7 @@ def main():
         import torch.distributed as dist
 
         port = int(os.environ.get("MASTER_PORT", "29500")) + 21
+        os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)  # else every rank would be a client of our tcp:// port
         dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
         if a.syncbn:
             model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
