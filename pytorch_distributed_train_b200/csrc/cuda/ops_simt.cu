@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -723,9 +724,10 @@ void launch_conv5x5_fwd(const float* x, const float* w, const float* bias, float
                         cudaStream_t st) {
   constexpr int TH = 7;
   if (s.H % TH != 0) throw std::invalid_argument("conv5x5_fwd: H must be a multiple of 7");
-  // conv1 (1→16): one CTA per image when it fits (784 threads): a single wave of 100 CTAs instead of
-  // 2.7 waves of 400 quarter-image CTAs, and 100 instead of 400 partial rows in the BN-statistics fold
-  const bool whole_image = s.Cin == 1 && s.Cout == 16 && s.H == 28 && s.W * 28 <= 1024;
+  // conv1 (1→16) one-CTA-per-image variant (784 threads, 100 CTAs): measured 23.5 µs vs 20.5 µs for the
+  // 400 quarter-image CTAs on B200 (profiles/op_bench_v1.md, v3) — kept for experiments, off by default
+  static const bool whole_env = [] { const char* e = getenv("PDT_CONV1_WHOLE_IMAGE"); return e && e[0] == '1'; }();
+  const bool whole_image = whole_env && s.Cin == 1 && s.Cout == 16 && s.H == 28 && s.W * 28 <= 1024;
   const int blocks = whole_image ? s.B : s.B * (s.H / TH);
   if (stats && (static_cast<long long>(blocks + blocks / kFoldGroup + 1) * 2 * s.Cout > scr.capacity_floats || blocks / kFoldGroup + 2 > scr.counters))
     throw std::invalid_argument("conv5x5_fwd: reduction scratch too small");
@@ -767,7 +769,8 @@ void launch_conv5x5_dgrad(const float* dy, const float* w, float* dx, ConvShape 
 void launch_conv5x5_wgrad(const float* dy, const float* x, float* dw, float* db, ConvShape s, ReduceScratch scr, cudaStream_t st) {
   constexpr int TH = 7;
   if (s.H % TH != 0) throw std::invalid_argument("conv5x5_wgrad: H must be a multiple of 7");
-  const bool whole_image = s.Cin == 1 && s.Cout == 16 && s.H == 28;  // conv1: one CTA per image, 100 partial rows
+  static const bool whole_env = [] { const char* e = getenv("PDT_CONV1_WHOLE_IMAGE"); return e && e[0] == '1'; }();
+  const bool whole_image = whole_env && s.Cin == 1 && s.Cout == 16 && s.H == 28;  // one CTA per image: slower (29.7 vs 25.5 µs)
   const int blocks = whole_image ? s.B : s.B * (s.H / TH);
   const int width = 25 * s.Cin * s.Cout + s.Cout;
   if (static_cast<long long>(blocks) * width > scr.capacity_floats) throw std::invalid_argument("conv5x5_wgrad: reduction scratch too small");

@@ -274,6 +274,52 @@ def new_group(ranks: Optional[Sequence[int]] = None, backend: Optional[str] = No
 
 
 # ---- collectives ---------------------------------------------------------------------------
+def _debug_level() -> str:
+    return (os.environ.get("PDT_DISTRIBUTED_DEBUG") or os.environ.get("TORCH_DISTRIBUTED_DEBUG") or "OFF").upper()
+
+
+def _precheck(g: ProcessGroup, op: str, tensors: Sequence[torch.Tensor], extra: str = "") -> None:
+    """Debug layer (the reference stack's counterpart is ProcessGroupWrapper under
+    TORCH_DISTRIBUTED_DEBUG=DETAIL, torch distributed_c10d.py:5121-5137, and TORCH_NCCL_NAN_CHECK).
+
+    ``PDT_DISTRIBUTED_DEBUG=DETAIL``: before a collective runs, every rank publishes a fingerprint
+    (sequence number, op, shapes, dtypes, root/op argument) through the group's store and compares it
+    with every peer's, so "rank 3 called broadcast while the rest called all_reduce" is an exception
+    naming the ranks instead of a hang or silent corruption.  ``PDT_NAN_CHECK=1``: refuse to
+    communicate non-finite floating-point payloads."""
+    nan_check = os.environ.get("PDT_NAN_CHECK", "0") == "1"
+    detail = _debug_level() == "DETAIL"
+    if not (nan_check or detail):
+        return
+    if nan_check:
+        for t in tensors:
+            if t.is_floating_point() and t.numel() and not bool(torch.isfinite(t).all()):
+                raise RuntimeError(f"[rank{g.rank()}] {op}: non-finite values in a tensor handed to a collective "
+                                   f"(shape {tuple(t.shape)}, dtype {t.dtype}) — PDT_NAN_CHECK=1")
+    if detail and g.size() > 1:
+        g._dbg_seq = getattr(g, "_dbg_seq", 0) + 1
+        seq = g._dbg_seq
+        fp = f"{op}|{extra}|" + ";".join(f"{tuple(t.shape)}:{t.dtype}" for t in tensors)
+        base = f"dbg/{g.name}/{seq}"
+        g.store.set(f"{base}/{g.rank()}", fp.encode())
+        bad = []
+        for r in range(g.size()):
+            if r == g.rank():
+                continue
+            other = bytes(g.store.get(f"{base}/{r}")).decode()
+            if other != fp:
+                bad.append((r, other))
+        if seq > 2:
+            try:
+                g.store.delete_key(f"dbg/{g.name}/{seq - 2}/{g.rank()}")
+            except Exception:
+                pass
+        if bad:
+            lines = "\n".join(f"  rank {r}: {o}" for r, o in bad)
+            raise RuntimeError(f"[rank{g.rank()}] collective mismatch at sequence number {seq} in group {g.name!r}:\n"
+                               f"  rank {g.rank()}: {fp}\n{lines}")
+
+
 def _finish(work, async_op: bool):
     if async_op:
         return work
@@ -289,6 +335,7 @@ def _contig(t: torch.Tensor, what: str) -> torch.Tensor:
 
 def all_reduce(tensor: torch.Tensor, op=ReduceOp.SUM, group: Optional[ProcessGroup] = None, async_op: bool = False):
     g = _group(group)
+    _precheck(g, "all_reduce", [tensor], str(op))
     if op == ReduceOp.AVG and g.is_cuda:
         return _finish(g.comm.allreduce(_contig(tensor, "all_reduce"), ReduceOp.SUM, 1.0 / g.size()), async_op)
     return _finish(g.comm.allreduce(_contig(tensor, "all_reduce"), op, 1.0), async_op)
@@ -297,12 +344,14 @@ def all_reduce(tensor: torch.Tensor, op=ReduceOp.SUM, group: Optional[ProcessGro
 def broadcast(tensor: torch.Tensor, src: int, group: Optional[ProcessGroup] = None, async_op: bool = False):
     g = _group(group)
     root = g.ranks.index(src) if group is not None and src in g.ranks else src
+    _precheck(g, "broadcast", [tensor], f"root={root}")
     return _finish(g.comm.broadcast(_contig(tensor, "broadcast"), root), async_op)
 
 
 def all_gather_into_tensor(output_tensor: torch.Tensor, input_tensor: torch.Tensor,
                            group: Optional[ProcessGroup] = None, async_op: bool = False):
     g = _group(group)
+    _precheck(g, "all_gather_into_tensor", [input_tensor])
     return _finish(g.comm.allgather(_contig(output_tensor, "all_gather output"), _contig(input_tensor, "all_gather input")), async_op)
 
 
@@ -333,12 +382,14 @@ def all_gather(tensor_list: List[torch.Tensor], tensor: torch.Tensor, group: Opt
 
 def reduce(tensor: torch.Tensor, dst: int, op=ReduceOp.SUM, group: Optional[ProcessGroup] = None, async_op: bool = False):
     g = _group(group)
+    _precheck(g, "reduce", [tensor], f"{op},dst={dst}")
     return _finish(g.comm.reduce(_contig(tensor, "reduce"), op, dst), async_op)
 
 
 def reduce_scatter_tensor(output: torch.Tensor, input: torch.Tensor, op=ReduceOp.SUM,
                           group: Optional[ProcessGroup] = None, async_op: bool = False):
     g = _group(group)
+    _precheck(g, "reduce_scatter_tensor", [input], str(op))
     return _finish(g.comm.reduce_scatter(_contig(output, "reduce_scatter output"), _contig(input, "reduce_scatter input"), op), async_op)
 
 
@@ -361,6 +412,7 @@ def scatter(tensor: torch.Tensor, scatter_list: Optional[List[torch.Tensor]] = N
 
 def all_to_all_single(output: torch.Tensor, input: torch.Tensor, group: Optional[ProcessGroup] = None, async_op: bool = False):
     g = _group(group)
+    _precheck(g, "all_to_all_single", [input])
     return _finish(g.comm.alltoall(_contig(output, "all_to_all output").view(-1), _contig(input, "all_to_all input").view(-1)), async_op)
 
 

@@ -157,3 +157,38 @@ def test_single_process_env_rendezvous(monkeypatch):
 def test_file_rendezvous(tmp_path):
     pdt.init_process_group("gloo", init_method=f"file://{tmp_path}/rdzv", world_size=1, rank=0)
     pdt.destroy_process_group()
+
+
+def _debug_detail(rank, world):
+    import os
+
+    os.environ["PDT_DISTRIBUTED_DEBUG"] = "DETAIL"
+    t = torch.ones(4)
+    dist.all_reduce(t)  # matching call passes the fingerprint check
+    assert t[0].item() == world
+    try:
+        if rank == 0:
+            dist.all_reduce(torch.ones(4))
+        else:
+            dist.broadcast(torch.ones(5), 0)  # wrong collective, wrong shape
+    except RuntimeError as e:
+        msg = str(e)
+    else:
+        msg = ""
+    os.environ["PDT_DISTRIBUTED_DEBUG"] = "OFF"
+    os.environ["PDT_NAN_CHECK"] = "1"
+    try:
+        dist.all_reduce(torch.tensor([1.0, float("nan")]))
+    except RuntimeError as e:
+        nan_msg = str(e)
+    else:
+        nan_msg = ""
+    os.environ["PDT_NAN_CHECK"] = "0"
+    return msg, nan_msg
+
+
+def test_debug_detail_names_mismatched_collectives_and_nan_check():
+    """collective fingerprint check + NaN check instead of a hang / silent corruption."""
+    for msg, nan_msg in run_ranks(_debug_detail, 2):
+        assert "collective mismatch at sequence number 2" in msg and "all_reduce" in msg and "broadcast" in msg
+        assert "non-finite" in nan_msg

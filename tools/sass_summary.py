@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """Summarise the SASS of our kernels: per kernel, a histogram of the mnemonics that prove the
-Blackwell-native path (UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA,
+Blackwell-native path (UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA, LDGMC = multimem.ld_reduce,
 LDGSTS = cp.async, multimem = NVLS).  Usage: tools/sass_summary.py <file.sass> > profiles/sass/x.md"""
 import collections
 import re
 import sys
 
-KEY = re.compile(r"\b(UTC[A-Z]*MMA|UTCBAR|UTCATOMSWS|LDTM|STTM|UTMALDG|UTMASTG|UTMAPF|UBLKCP|LDGSTS|SYNCS|HMMA|FFMA|FMUL|FADD|LDG|STG|LDS|STS|BAR|ATOM|RED|MEMBAR|FENCE|ERRBAR|CCTL|MULTIMEM|LD\.E|ST\.E|SHFL|MUFU|ELECT|R2UR|NANOSLEEP)\b")
+KEY = re.compile(r"\b(LDGMC|REDGMC|UTC[A-Z]*MMA|UTCBAR|UTCATOMSWS|LDTM|STTM|UTMALDG|UTMASTG|UTMAPF|UBLKCP|LDGSTS|SYNCS|HMMA|FFMA|FMUL|FADD|LDG|STG|LDS|STS|BAR|ATOM|RED|MEMBAR|FENCE|ERRBAR|CCTL|MULTIMEM|LD\.E|ST\.E|SHFL|MUFU|ELECT|R2UR|NANOSLEEP)\b")
 fn = None
 hist = collections.OrderedDict()
 for line in open(sys.argv[1]):
@@ -29,5 +29,12 @@ print("| kernel | instructions | notable mnemonics |\n|---|---|---|")
 for fn, h in hist.items():
     tot = sum(h.values())
     keys = {k: v for k, v in h.items() if KEY.search(k) or k.startswith("UT") or k.startswith("LDTM") or k == "<multimem>"}
-    short = re.sub(r"^_ZN?\d*", "", fn)[:90]
+    try:
+        import subprocess
+
+        short = subprocess.run(["c++filt", fn], capture_output=True, text=True).stdout.strip() or fn
+    except OSError:
+        short = fn
+    short = re.sub(r"\(anonymous namespace\)::", "", short)
+    short = re.sub(r"\(.*$", "", short)[:150]   # drop the argument list
     print(f"| `{short}` | {tot} | " + ", ".join(f"{k}×{v}" for k, v in sorted(keys.items(), key=lambda kv: -kv[1])[:14]) + " |")
