@@ -117,6 +117,7 @@ void register_cuda_bindings(py::module_& m) {
       .def("set_launch", &SymmComm::set_launch, py::arg("blocks") = 0, py::arg("threads") = 0)
       .def("describe", &SymmComm::describe)
       .def("status", &SymmComm::status)
+      .def("status_string", &SymmComm::status_string)
       .def("heap_bytes_in_use", [](SymmComm& c) { return c.heap().user_bytes_in_use(); })
       .def("is_symmetric", [](SymmComm& c, const at::Tensor& t) { return c.heap().contains(t.data_ptr(), t.nbytes()); });
 

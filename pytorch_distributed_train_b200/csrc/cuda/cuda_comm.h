@@ -80,6 +80,15 @@ class SymmComm : public CudaCommBase {
   void set_launch(int blocks, int threads) { cfg_.blocks = blocks; cfg_.threads = threads; }
   std::string describe() const;
   int status() const { return heap_->status(); }
+  // Human-readable form of the device-written status word (see symm_trap_timeout in symm_device.h).
+  std::string status_string() const {
+    const int s = heap_->status();
+    if (s == 0) return "ok";
+    if ((static_cast<unsigned>(s) & 0xFF000000u) == 0x7D000000u)
+      return "device-side barrier timeout on rank " + std::to_string(rank_) + ": channel " + std::to_string((s >> 20) & 0xF) +
+             " never heard from rank " + std::to_string((s >> 16) & 0xF) + " (waiting for epoch …" + std::to_string(s & 0xFFFF) + ")";
+    return "unknown status " + std::to_string(s);
+  }
 
  private:
   void do_allreduce(at::Tensor& t, ReduceOp op, double scale, int channel, cudaStream_t s);
