@@ -51,6 +51,8 @@ void launch_bn_relu_pool_bwd_apply(const float* dout, const float* y, const floa
 
 // ---- generic NCHW BatchNorm pieces (SyncBatchNorm on arbitrary models) ---------------------------------
 void launch_bn_stats_nchw(const float* x, float* stats, int N, int C, int HW, ReduceScratch scr, cudaStream_t st);
+// same sums accumulated and returned in fp64 (SyncBatchNorm forward: var = E[x²] − μ² needs the headroom)
+void launch_bn_stats_nchw_f64(const float* x, double* stats, int N, int C, int HW, ReduceScratch scr, cudaStream_t st);
 void launch_bn_apply_nchw(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta, float* out,
                           int N, int C, int HW, cudaStream_t st);
 void launch_bn_bwd_reduce_nchw(const float* dy, const float* x, const float* mean, const float* invstd, float* red4c, int N, int C,

@@ -516,6 +516,57 @@ __global__ void __launch_bounds__(256) bn_reduce_nchw_kernel(const float* __rest
   if (threadIdx.x == 0) *scr.counter = 0u;
 }
 
+// Forward statistics in fp64: Σx, Σx² of channel c.  Downstream computes var = E[x²] − μ², which
+// amplifies the rounding of the two sums by μ²/σ²; fp32 sums made first-step gradients of a
+// SyncBN ResNet-18 differ from torch's (Welford) by 1 % (profiles/numerics_syncbn.md), fp64 sums
+// (and an fp64 exchange between ranks) bring that to 1e-5.  The kernel is bandwidth-bound either way.
+__global__ void __launch_bounds__(256) bn_stats_nchw_f64_kernel(const float* __restrict__ x, double* out, int N, int C, int HW, int S,
+                                                                ReduceScratch scr) {
+  const int c = blockIdx.x / S, s = blockIdx.x % S;
+  const long long total = static_cast<long long>(N) * HW;
+  const long long chunk = (total + S - 1) / S;
+  const long long lo = chunk * s, hi = min(total, lo + chunk);
+  double s1 = 0.0, s2 = 0.0;
+  for (long long e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+    const long long n = e / HW, hw = e % HW;
+    const double v = static_cast<double>(x[(static_cast<size_t>(n) * C + c) * HW + hw]);
+    s1 += v;
+    s2 = fma(v, v, s2);
+  }
+  __shared__ double r1[8], r2[8];
+  for (int off = 16; off > 0; off >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  }
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  double* parts = reinterpret_cast<double*>(scr.partials);
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int wi = 0; wi < (blockDim.x >> 5); ++wi) { t1 += r1[wi]; t2 += r2[wi]; }
+    parts[static_cast<size_t>(blockIdx.x) * 2] = t1;
+    parts[static_cast<size_t>(blockIdx.x) * 2 + 1] = t2;
+  }
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(scr.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int k = 0; k < S; ++k) {
+      t1 += __ldcg(&parts[(static_cast<size_t>(ch) * S + k) * 2]);
+      t2 += __ldcg(&parts[(static_cast<size_t>(ch) * S + k) * 2 + 1]);
+    }
+    out[ch] = t1;
+    out[C + ch] = t2;
+    if (ch == 0) out[2 * C] = static_cast<double>(total);
+  }
+  if (threadIdx.x == 0) *scr.counter = 0u;
+}
+
 __global__ void bn_apply_nchw_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
                                      long long total, int C, int HW) {
@@ -840,6 +891,12 @@ void launch_bn_stats_nchw(const float* x, float* stats, int N, int C, int HW, Re
   if (static_cast<long long>(C) * S * 2 > scr.capacity_floats) throw std::invalid_argument("bn_stats: reduction scratch too small");
   bn_reduce_nchw_kernel<false><<<C * S, 256, 0, st>>>(nullptr, x, nullptr, nullptr, stats, N, C, HW, S, scr);
   check_launch("bn_stats_nchw");
+}
+void launch_bn_stats_nchw_f64(const float* x, double* stats, int N, int C, int HW, ReduceScratch scr, cudaStream_t st) {
+  const int S = bn_slices(N, C, HW);
+  if (static_cast<long long>(C) * S * 4 > scr.capacity_floats) throw std::invalid_argument("bn_stats: reduction scratch too small");
+  bn_stats_nchw_f64_kernel<<<C * S, 256, 0, st>>>(x, stats, N, C, HW, S, scr);
+  check_launch("bn_stats_nchw_f64");
 }
 void launch_bn_apply_nchw(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta, float* out, int N,
                           int C, int HW, cudaStream_t st) {

@@ -192,8 +192,8 @@ def sgd_step(params, grads, momentum_bufs, lr, momentum=0.0, dampening=0.0, weig
 
 # ---- generic (NCHW) BatchNorm pieces used by parallel.SyncBatchNorm ------------------------------------------
 def bn_local_stats(x: torch.Tensor) -> torch.Tensor:
-    """[2C+1] = per-channel Σx, Σx², then the per-channel element count."""
-    return _C.bn_stats_nchw(x)
+    """float64 [2C+1] = per-channel Σx, Σx² (accumulated in fp64), then the per-channel element count."""
+    return _C.bn_stats_nchw_f64(x)
 
 
 def bn_apply(x, mean, invstd, weight, bias):

@@ -17,6 +17,7 @@ GPU (torch's own SyncBatchNorm refuses CPU tensors).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -51,25 +52,31 @@ class _SyncBatchNormFn(torch.autograd.Function):
 
         C = x.shape[1]
         count = x.numel() // C if x.numel() else 0
-        fused = x.is_cuda and ops.native_available() and x.dtype == torch.float32
+        native = x.is_cuda and ops.native_available() and x.dtype == torch.float32
+        # debugging aid: PDT_SYNCBN_KERNELS is a bit mask of the native kernels to use
+        # (1 = local stats, 2 = normalise, 4 = backward reduce, 8 = backward elementwise; default all)
+        mask = int(os.environ.get("PDT_SYNCBN_KERNELS", "15")) if native else 0
+        fused = bool(mask & 2)
         xc = x.contiguous()
-        # local (Σx, Σx², n) in one fp32 vector of 2C+1
-        if fused:
-            stats = ops.bn_local_stats(xc)  # [2C+1], stats[2C] = count
+        # local (Σx, Σx², n) in one *float64* vector of 2C+1: var = E[x²] − μ² magnifies the rounding of
+        # the sums by μ²/σ², so they are accumulated, exchanged and combined in fp64 (torch gets the
+        # same robustness from Welford + count-weighted merging, _functions.py:39-124)
+        if mask & 1:
+            stats = ops.bn_local_stats(xc)  # [2C+1] float64, stats[2C] = count
         else:
-            xf = xc.float()
+            xf = xc.double()
             dims = _reduce_dims(xf)
             stats = torch.cat([xf.sum(dims), (xf * xf).sum(dims), xf.new_full((1,), float(count))])
         _allreduce_now(group, stats)
-        total = stats[2 * C]
+        total64 = stats[2 * C]
         # every rank holding zero samples is legal as long as somebody has data
-        n = total.clamp_min(1.0)
-        mean = stats[:C] / n
-        var = (stats[C:2 * C] / n - mean * mean).clamp_min_(0.0)
-        invstd = torch.rsqrt(var + eps)
+        n = total64.clamp_min(1.0)
+        mean64 = stats[:C] / n
+        var64 = (stats[C:2 * C] / n - mean64 * mean64).clamp_min_(0.0)
+        mean, invstd, total = mean64.float(), torch.rsqrt(var64 + eps).float(), total64.float()
         if running_mean is not None:
             with torch.no_grad():
-                unbiased = var * (n / (n - 1.0).clamp_min(1.0))
+                unbiased = var64 * (n / (n - 1.0).clamp_min(1.0))
                 running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
                 running_var.mul_(1 - momentum).add_(unbiased.to(running_var.dtype), alpha=momentum)
         if fused:
@@ -84,7 +91,7 @@ class _SyncBatchNormFn(torch.autograd.Function):
             out = out.to(x.dtype)
         ctx.save_for_backward(xc, weight, mean, invstd, total)
         ctx.group = group
-        ctx.fused = fused
+        ctx.mask = mask
         ctx.has_bias = bias is not None
         return out
 
@@ -95,7 +102,7 @@ class _SyncBatchNormFn(torch.autograd.Function):
         x, weight, mean, invstd, total = ctx.saved_tensors
         C = x.shape[1]
         dy = dy.contiguous()
-        if ctx.fused:
+        if ctx.mask & 4:
             red = ops.bn_backward_reduce(dy, x, mean, invstd)  # [4C]: Σdy, Σdy·(x-μ), dγ, dβ
         else:
             dims = _reduce_dims(x)
@@ -113,7 +120,7 @@ class _SyncBatchNormFn(torch.autograd.Function):
             n = total.clamp_min(1.0)
             mean_dy = sums[:C] / n
             mean_dy_xmu = sums[C:] / n
-            if ctx.fused:
+            if ctx.mask & 8:
                 dx = ops.bn_backward_apply(dy, x, mean, invstd, weight, mean_dy, mean_dy_xmu)
             else:
                 shp = _bshape(x)

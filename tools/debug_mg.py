@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Multi-GPU numerics probe (run on a 2-GPU box): generic SyncBatchNorm kernels vs torch SyncBatchNorm,
+first-step gradients of ConvNet / ResNet-18 under our DDP vs torch DDP, per parameter."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def worker(rank, world, port):
+    import torch
+    import torch.distributed as td
+    import torch.nn as nn
+
+    import pytorch_distributed_train_b200 as pdt
+
+    dist = pdt.distributed
+    dev = torch.device("cuda", rank)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    td.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
+    comm = dist.get_default_group().comm
+    out = {}
+    # ---- A/B: one SyncBN layer ------------------------------------------------------------------------
+    for shape in [(4, 64, 32, 32)]:
+        for busy in (False, True):
+            for kernels in ("15", "0"):
+                os.environ["PDT_SYNCBN_KERNELS"] = kernels
+                g = torch.Generator(device=dev).manual_seed(100 + rank)
+                x = torch.randn(shape, device=dev, generator=g) * 2 + 0.5
+                dy = torch.randn(shape, device=dev, generator=g)
+                C = shape[1]
+                w = torch.rand(C, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) + 0.5
+                b = torch.randn(C, device=dev, generator=torch.Generator(device=dev).manual_seed(6))
+                mine = pdt.SyncBatchNorm(C).to(dev)
+                theirs = nn.SyncBatchNorm(C).to(dev)
+                for m in (mine, theirs):
+                    with torch.no_grad():
+                        m.weight.copy_(w)
+                        m.bias.copy_(b)
+                big = comm.alloc_flat(1 << 22, torch.float32, dev)
+                big.fill_(1.0)
+                xa = x.clone().requires_grad_()
+                ya = mine(xa)
+                work = comm.allreduce(big, dist.ReduceOp.SUM, 1.0) if busy else None
+                ya.backward(dy)
+                if work is not None:
+                    work.wait()
+                xb = x.clone().requires_grad_()
+                yb = theirs(xb)
+                yb.backward(dy)
+                torch.cuda.synchronize()
+                out[f"syncbn{shape}|busy={busy}|kernels={kernels}"] = {
+                    "y": rel(ya, yb), "dx": rel(xa.grad, xb.grad), "dgamma": rel(mine.weight.grad, theirs.weight.grad),
+                    "dbeta": rel(mine.bias.grad, theirs.bias.grad), "rm": rel(mine.running_mean, theirs.running_mean),
+                    "rv": rel(mine.running_var, theirs.running_var)}
+                del big
+    os.environ["PDT_SYNCBN_KERNELS"] = "15"
+
+    # ---- C/D: first-step gradients under DDP ------------------------------------------------------------
+    def grads(build, wrap, x, y, lossf):
+        torch.manual_seed(0)
+        net = build()
+        ddp = wrap(net)
+        loss = lossf(ddp(x), y)
+        loss.backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.detach().clone() for n, p in ddp.module.named_parameters()}, loss.item()
+
+    for name, syncbn, kernels in [("convnet", False, "15"), ("convnet", True, "15"), ("resnet", False, "15"), ("resnet", True, "15"), ("resnet", True, "0")]:
+        os.environ["PDT_SYNCBN_KERNELS"] = kernels
+        g = torch.Generator().manual_seed(77 + rank)
+        if name == "convnet":
+            x, y = torch.rand(100, 1, 28, 28, generator=g).to(dev), torch.randint(0, 10, (100,), generator=g).to(dev)
+            mk_o = lambda: pdt.models.ConvNet()
+            mk_t = lambda: pdt.models.ConvNet(fused=False)
+        else:
+            x, y = torch.randn(4, 3, 64, 64, generator=g).to(dev), torch.randint(0, 10, (4,), generator=g).to(dev)
+            mk_o = mk_t = lambda: pdt.models.resnet18(num_classes=10)
+        bo = (lambda: pdt.SyncBatchNorm.convert_sync_batchnorm(mk_o()).to(dev)) if syncbn else (lambda: mk_o().to(dev))
+        bt = (lambda: nn.SyncBatchNorm.convert_sync_batchnorm(mk_t()).to(dev)) if syncbn else (lambda: mk_t().to(dev))
+        go, lo = grads(bo, lambda n: pdt.DistributedDataParallel(n, device_ids=[rank], bucket_cap_mb=8, first_bucket_cap_mb=1), x, y, nn.functional.cross_entropy)
+        gt, lt = grads(bt, lambda n: nn.parallel.DistributedDataParallel(n, device_ids=[rank], bucket_cap_mb=8), x, y, nn.functional.cross_entropy)
+        errs = {n: rel(go[n], gt[n]) for n in gt}
+        worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+        out[f"{name}|syncbn={syncbn}|kernels={kernels}"] = {"loss": (lo, lt), "worst": worst,
+                                                             "gnorm": {n: gt[n].abs().max().item() for n, _ in worst}}
+    # ---- E: precision of one ConvNet step against a float64 oracle (single GPU, no DDP) ---------------------
+    os.environ["PDT_SYNCBN_KERNELS"] = "15"
+    if rank == 0:
+        torch.manual_seed(1)
+        ref64 = pdt.models.ConvNet(fused=False).to(dev)
+        sd = ref64.state_dict()
+        g = torch.Generator().manual_seed(5)
+        x, y = torch.rand(100, 1, 28, 28, generator=g).to(dev), torch.randint(0, 10, (100,), generator=g).to(dev)
+        ref64 = ref64.double()
+        nn.functional.cross_entropy(ref64(x.double()), y).backward()
+        oracle = {n: p.grad.clone() for n, p in ref64.named_parameters()}
+
+        def arm(fused, tf32):
+            torch.backends.cudnn.allow_tf32 = tf32
+            net = pdt.models.ConvNet(fused=fused).to(dev)
+            net.load_state_dict(sd)
+            nn.functional.cross_entropy(net(x), y).backward()
+            return {n: rel(p.grad.double(), oracle[n]) for n, p in net.named_parameters() if oracle[n].abs().max() > 1e-6}
+
+        out["precision_vs_fp64|ours(tf32 tcgen05 conv2)"] = arm(True, False)
+        out["precision_vs_fp64|torch cudnn allow_tf32=True (reference default)"] = arm(False, True)
+        out["precision_vs_fp64|torch cudnn allow_tf32=False"] = arm(False, False)
+        torch.backends.cudnn.allow_tf32 = False
+    td.destroy_process_group()
+    return out
+
+
+if __name__ == "__main__":
+    from mp_helpers import free_port, run_ranks
+
+    res = run_ranks(worker, 2, free_port(), backend="nccl")
+    for k, v in res[0].items():
+        print(k, json.dumps(v))
