@@ -118,6 +118,13 @@ void register_cuda_bindings(py::module_& m) {
       .def("describe", &SymmComm::describe)
       .def("status", &SymmComm::status)
       .def("status_string", &SymmComm::status_string)
+      .def("parity_state", [](SymmComm& c) {
+        // which half of each channel's double-buffered staging the NEXT collective will use; a CUDA graph bakes
+        // these in, so a captured step with an odd number of staged collectives must alternate between two captures
+        std::vector<int> v;
+        for (int ch = 0; ch < kSymmChannels; ++ch) v.push_back(c.heap().peek_parity(ch));
+        return v;
+      })
       .def("heap_bytes_in_use", [](SymmComm& c) { return c.heap().user_bytes_in_use(); })
       .def("is_symmetric", [](SymmComm& c, const at::Tensor& t) { return c.heap().contains(t.data_ptr(), t.nbytes()); });
 

@@ -50,6 +50,7 @@ class SymmetricHeap {
   // Host-side parity flip, one per collective issued on the channel (all ranks issue the same
   // sequence, so parities agree).
   int next_parity(int channel) { return parity_[channel]++ & 1; }
+  int peek_parity(int channel) const { return parity_[channel] & 1; }
 
   // User area. Offsets are identical across ranks as long as every rank performs the same
   // sequence of alloc/free calls (DDP construction is deterministic).

@@ -11,7 +11,15 @@ the per-step buffer sync and the fused optimizer all land inside the graph.
 
 Cross-GPU safety of replay: the reduce kernels use monotonically increasing epoch counters kept
 in *device* memory (not kernel arguments), so replaying the same graph on every rank advances all
-ranks in lockstep.
+ranks in lockstep.  The staged collectives double-buffer their peer-visible staging area and the
+half they use is a *launch argument* (baked into the graph): if a step issues an odd number of
+them, replaying one graph would use the same half twice in a row across the step boundary and a
+fast rank could overwrite a slot a slow rank is still reading.  Two things prevent that: (a) a step
+that also contains an independent barrier-synchronised collective (DDP's per-forward buffer
+broadcast: every rank must have finished step k before anyone leaves the broadcast of step k+1) is
+safe as is — this is the ConvNet/ResNet case; (b) otherwise the step is captured twice (the second
+capture starts on the other half) and replays alternate between the two graphs, which reproduces
+exactly the eager alternation.
 """
 from __future__ import annotations
 
@@ -62,19 +70,32 @@ class GraphedTrainStep:
                 self._eager_step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        before = _C.kernel_launch_count()
-        with torch.cuda.graph(self.graph, stream=side):
-            self.static_loss = self._eager_step()
-        # how many of *our* kernels one replay runs (ATen glue kernels are not counted)
-        self.kernels_per_replay = int(_C.kernel_launch_count() - before)
-        torch.cuda.synchronize(dev)
+        comm = getattr(self.model, "comm", None)
+        parity = (lambda: list(comm.parity_state())) if hasattr(comm, "parity_state") else (lambda: [])
+        self.graphs, self.losses = [], []
+        p0 = parity()
+        for _ in range(2):
+            g = torch.cuda.CUDAGraph()
+            before = _C.kernel_launch_count()
+            with torch.cuda.graph(g, stream=side):
+                loss = self._eager_step()
+            # how many of *our* kernels one replay runs (ATen glue kernels are not counted)
+            self.kernels_per_replay = int(_C.kernel_launch_count() - before)
+            self.graphs.append(g)
+            self.losses.append(loss)
+            torch.cuda.synchronize(dev)
+            ordered = getattr(self.model, "syncs_buffers_every_step", None)
+            if parity() == p0 or (ordered is not None and ordered()):
+                break  # even number of staged collectives per step, or case (a): one graph replays safely
+        self.graph, self.static_loss = self.graphs[0], self.losses[0]
 
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
         for dst, src in zip(self.static_inputs, inputs):
             dst.copy_(src, non_blocking=True)
         if hasattr(self.optimizer, "sync_lr"):
             self.optimizer.sync_lr()  # scheduler changes reach the captured step through a device scalar
-        self.graph.replay()
+        i = self.replays % len(self.graphs)
+        self.graphs[i].replay()
         self.replays += 1
+        self.static_loss = self.losses[i]
         return self.static_loss

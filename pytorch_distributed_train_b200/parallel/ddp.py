@@ -292,6 +292,11 @@ class DistributedDataParallel(nn.Module):
             broadcast_coalesced(self.comm, [p for p in self.module.parameters()], 0)
         self._sync_buffers()
 
+    def syncs_buffers_every_step(self) -> bool:
+        """True when every training forward runs a barrier-synchronised buffer broadcast (C4) — which
+        also orders consecutive steps across ranks (engine.GraphedTrainStep relies on it)."""
+        return bool(self.broadcast_buffers and self._buffers_to_sync and self.process_group.size() > 1)
+
     def _sync_buffers(self):
         if not self._buffers_to_sync or self.process_group.size() == 1:
             return

@@ -354,3 +354,35 @@ def test_absent_rank_trips_the_device_side_timeout(tmp_path):
         assert res[r]["status"] != 0 and f"never heard from rank {w - 1}" in res[r]["text"], res[r]
         assert res[r]["msg"] != "none" and res[r]["seconds"] < 30
     assert res[w - 1]["status"] == 0
+
+
+def _stress(rank, world):
+    """SURVEY §4.3 stress: 10k back-to-back collectives with randomised per-rank stream delays — the
+    flag/epoch protocol must neither deadlock nor let a fast rank overwrite a slot a slow rank is reading."""
+    import random
+
+    dev = torch.device("cuda", rank)
+    comm = dist.get_default_group().comm
+    rng = random.Random(1234 + rank)
+    small = torch.zeros(257, device=dev)          # odd length: vector body + tail
+    heap = comm.alloc_flat(4096, torch.float32, dev)
+    expect_small = expect_heap = 0.0
+    total = sum(range(1, world + 1))
+    for i in range(10000):
+        if rng.random() < 0.02:
+            torch.cuda._sleep(rng.randrange(20000, 400000))   # 10–200 µs of stall on this rank only
+        small.fill_(float(rank + 1))
+        comm.allreduce_inline(small, dist.ReduceOp.SUM, 1.0)
+        if i % 7 == 0:
+            heap.fill_(float(rank + 1) * (i % 5))
+            comm.allreduce(heap, dist.ReduceOp.SUM, 1.0).wait()   # comm-stream channel interleaved with the inline one
+            expect_heap = float(total * (i % 5))
+        if i % 1000 == 999:
+            assert small.eq(float(total)).all().item(), i
+            assert heap.eq(expect_heap).all().item(), i
+    torch.cuda.synchronize()
+    return comm.status()
+
+
+def test_ten_thousand_back_to_back_collectives():
+    assert run_ranks(_stress, _world(), backend="nccl") == [0] * _world()

@@ -2,6 +2,13 @@
 N=${1:-8}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_$N.txt 2>&1
+# preflight: bring the heap + multicast up at this world size with a short leash; fall back to P2P-only if it fails
+if ! timeout -s KILL 150 python tools/allreduce_sweep.py --gpus $N --max-mb 1 --iters 20 > gpurun_out/preflight_$N.log 2>&1; then
+  echo "PREFLIGHT FAILED with multicast; retrying without"; tail -n 5 gpurun_out/preflight_$N.log | cut -c1-300
+  export PDT_SYMM_NO_MULTICAST=1
+  timeout -s KILL 150 python tools/allreduce_sweep.py --gpus $N --max-mb 1 --iters 20 > gpurun_out/preflight_nomc_$N.log 2>&1 || { echo "PREFLIGHT FAILED again"; tail -n 5 gpurun_out/preflight_nomc_$N.log | cut -c1-300; exit 1; }
+fi
+tail -n 2 gpurun_out/preflight_$N.log | cut -c1-300
 P=$((29500 + RANDOM % 1000))
 run() { name=$1; shift; P=$((P + 50))
   timeout -s KILL 300 env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N $ARGS > gpurun_out/bench_${name}_$N.json 2> gpurun_out/bench_${name}_$N.err
