@@ -910,6 +910,73 @@ __global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict
   }
 }
 
+// =====================================================================================================
+// Hardware probe for the next conv design (profiles/conv_tma_ncu.md §3): can a K-major swizzled A operand
+// start at an arbitrary ROW of a larger smem buffer?  A [256][ROWB/4] tile is loaded once by TMA; the MMA
+// reads rows [shift, shift+128) through a descriptor whose start address is base + shift·ROWB, with the
+// descriptor's base-offset field either 0 (mode 0) or (start >> 7) & 7 (mode 1, the documented rule for
+// starts that are not aligned to the swizzle repeat).  D[128][32] = A[shift:shift+128] · Bᵀ.
+// Not used by any product path; run by tools/exp_rowshift.py.
+// =====================================================================================================
+template <int ROWB>
+__global__ void __launch_bounds__(128, 1) umma_rowshift_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                                                                     float* __restrict__ d, int shift, int mode) {
+  constexpr int kRows = 256, kN = 32, kK = ROWB / 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                         // [256][ROWB]
+  uint8_t* sb = smem + kRows * ROWB;          // [32][ROWB]   (1024-aligned: 256·ROWB is a multiple of 1024)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 4096);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<32>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0 && elect_one()) {
+    mbar_arrive_expect_tx(&bars[0], kRows * ROWB + kN * ROWB);
+    tma_load_2d(sa, &tm_a, &bars[0], 0, 0);
+    tma_load_2d(sb, &tm_b, &bars[0], 0, 0);
+  }
+  if (warp == 1) {
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kTileM, kN);
+      const uint32_t a0 = smem_u32(sa) + static_cast<uint32_t>(shift) * ROWB, b0 = smem_u32(sb);
+#pragma unroll
+      for (int k = 0; k < kK / 8; ++k) {
+        const uint32_t astart = a0 + k * 32;
+        uint64_t ad = umma_desc_kmajor<ROWB>(astart);
+        if (mode == 1) ad |= static_cast<uint64_t>((astart >> 7) & 7) << 49;
+        umma_tf32(tmem_base, ad, umma_desc_kmajor<ROWB>(b0 + k * 32), idesc, k != 0);
+      }
+      umma_commit(&bars[1]);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bars[1], 0);
+  __syncwarp();
+  tc_fence_after();
+  const int row = warp * 32 + (threadIdx.x & 31);
+#pragma unroll
+  for (int c0 = 0; c0 < kN; c0 += 16) {
+    float v[16];
+    tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) d[row * kN + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<32>(tmem_base);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -1113,6 +1180,24 @@ void launch_gemm_tf32_tcgen05(const float* a, const float* b, float* d, int M, i
   PDT_GEMM_CASE(128)
   PDT_GEMM_CASE(256)
 #undef PDT_GEMM_CASE
+}
+
+void launch_umma_rowshift_probe(const float* a, const float* b, float* d, int rowb, int shift, int mode, cudaStream_t st) {
+  if (rowb != 64 && rowb != 128) throw std::invalid_argument("umma_rowshift_probe: row bytes must be 64 or 128");
+  if (shift < 0 || shift > 128) throw std::invalid_argument("umma_rowshift_probe: shift must be in [0, 128]");
+  const int kf = rowb / 4;
+  const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tm_a = make_tmap_2d(a, kf, 256, kf, 256, sw);
+  CUtensorMap tm_b = make_tmap_2d(b, kf, 32, kf, 32, sw);
+  const size_t smem = 1024 + 256 * static_cast<size_t>(rowb) + 4096 + 256;
+  if (rowb == 128) {
+    opt_in_smem(umma_rowshift_probe_kernel<128>, smem);
+    umma_rowshift_probe_kernel<128><<<1, 128, smem, st>>>(tm_a, tm_b, d, shift, mode);
+  } else {
+    opt_in_smem(umma_rowshift_probe_kernel<64>, smem);
+    umma_rowshift_probe_kernel<64><<<1, 128, smem, st>>>(tm_a, tm_b, d, shift, mode);
+  }
+  check_launch("umma_rowshift_probe");
 }
 
 }  // namespace pdt

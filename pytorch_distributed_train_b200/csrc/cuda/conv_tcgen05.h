@@ -28,4 +28,8 @@ void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, fl
 // D[M,N] = A[M,K] · B[N,K]^T, fp32 in/out, TF32 tensor-core math (K % 4 == 0, N % 16 == 0, N <= 256).
 void launch_gemm_tf32_tcgen05(const float* a, const float* b, float* d, int M, int N, int K, cudaStream_t st);
 
+// Hardware probe (tools/exp_rowshift.py): D[128,32] = A[shift:shift+128, :] · B[32, :]^T with A [256][rowb/4] loaded
+// once into swizzled smem and the UMMA descriptor started `shift` rows in; mode 1 sets the descriptor base offset.
+void launch_umma_rowshift_probe(const float* a, const float* b, float* d, int rowb, int shift, int mode, cudaStream_t st);
+
 }  // namespace pdt

@@ -346,6 +346,16 @@ void register_cuda_bindings(py::module_& m) {
   });
 
   // ---- tcgen05 GEMM self-test (D[M,N] = A[M,K]·B[N,K]^T in TF32) — validates descriptors/TMEM/TMA ---------
+  m.def("umma_rowshift_probe", [](const at::Tensor& a, const at::Tensor& b, int64_t shift, int64_t mode) {
+    chk(a, "a"); chk(b, "b");
+    TORCH_CHECK(a.dim() == 2 && a.size(0) == 256 && (a.size(1) == 16 || a.size(1) == 32) && b.dim() == 2 && b.size(0) == 32 &&
+                    b.size(1) == a.size(1), "umma_rowshift_probe: a [256, 16|32], b [32, same]");
+    c10::cuda::CUDAGuard g(a.device());
+    at::Tensor d = at::empty({128, 32}, a.options());
+    launch_umma_rowshift_probe(a.data_ptr<float>(), b.data_ptr<float>(), d.data_ptr<float>(), static_cast<int>(a.size(1)) * 4,
+                               static_cast<int>(shift), static_cast<int>(mode), cur_stream(a));
+    return d;
+  });
   m.def("gemm_tf32_tcgen05", [](const at::Tensor& a, const at::Tensor& b) {
     chk(a, "a"); chk(b, "b");
     c10::cuda::CUDAGuard g(a.device());
