@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -682,6 +683,202 @@ __global__ void __launch_bounds__(192, 1) conv5x5_umma_tma_kernel(const __grid_c
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
+// =====================================================================================================
+// EXPERIMENTAL (not validated on hardware yet, not reachable unless impl == "win" is requested):
+// "window" implicit-GEMM 5x5 convolution — every input pixel is loaded ONCE.
+//
+// ncu showed the im2col kernels above bound by the TMA gather's row rate (128 pixels × 25 taps = 3,200
+// rows per tile at ≈3.8 cycles/row, profiles/conv_tma_ncu.md).  Here a tile is R output rows of one image
+// in *padded-width* coordinates (PW = W + 4 positions per row, M = R·PW ≤ 128 MMA rows of which R·W are real
+// outputs): ONE tiled TMA box {32 ch, PW, R + 4 rows} brings the zero-haloed patch (hardware OOB fill
+// provides the halo and, for C = 16, the upper half of the 128-byte row), and tap (kh, kw) is the same
+// buffer read through a K-major SWIZZLE_128B descriptor that starts (kh·PW + kw) rows in — the base-offset
+// field carries the swizzle phase of that start row.  Index math proven on the CPU by
+// tools/emulate_window_conv.py; descriptor addressing to be confirmed by tools/exp_rowshift.py.
+// Weights: Bm[NOUT][25·32] (K index = tap·32 + c, zero padded for C = 16), resident in smem.
+// =====================================================================================================
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+template <int NOUT>
+struct ConvWinCfg {
+  static constexpr int kRowB = 128;                          // bytes per padded position (32 floats, upper half zero for C=16)
+  static constexpr int kPatchRowsMax = 256;                  // PW·(R+4) positions per tile, box limit
+  static constexpr int kAStageBytes = kPatchRowsMax * kRowB + 1024;   // + slack: the last taps of padding rows read past the box
+  static constexpr int kStages = 3;
+  static constexpr int kBTapBytes = NOUT * kRowB;            // 4 KB / 2 KB
+  static constexpr int kSyBytes = kTileM * 128;              // row staging for the BN statistics
+  static constexpr int kTmemCols = 64;
+  static constexpr int kThreads = 192;
+  static constexpr size_t kSmem = 2048 + kStages * kAStageBytes + 25 * kBTapBytes + kSyBytes + 2048;
+};
+
+template <int CK, int NOUT, bool FWD>
+__global__ void __launch_bounds__(192, 1) conv5x5_umma_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_b,
+                                                                  const float* __restrict__ bias, float* __restrict__ y, float* stats,
+                                                                  ReduceScratch scr, int B, int H, int W, int R, int num_tiles, int bo_mode) {
+  using Cfg = ConvWinCfg<NOUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                                        // stages start 1024-aligned (kAStageBytes % 1024 == 0)
+  uint8_t* sb = sa + Cfg::kStages * Cfg::kAStageBytes;
+  uint8_t* sy = sb + 25 * Cfg::kBTapBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sy + Cfg::kSyBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* b_full = empty + Cfg::kStages;
+  uint64_t* acc_full = b_full + 1;      // [2]
+  uint64_t* acc_empty = acc_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_part = reinterpret_cast<float*>(tmem_slot + 2);   // [4][2*NOUT] + [2*NOUT]
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int PW = W + 4, tiles_per_img = H / R, Mrows = R * PW;
+  const int M = B * H * W;
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(b_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_full, 25 * Cfg::kBTapBytes);
+      for (int t = 0; t < 25; ++t) tma_load_2d(sb + t * Cfg::kBTapBytes, &tm_b, b_full, t * 32, 0);
+      const uint32_t patch_bytes = static_cast<uint32_t>(Cfg::kRowB) * PW * (R + 4);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int n = tile / tiles_per_img, oh0 = (tile % tiles_per_img) * R;
+        const int s = it % Cfg::kStages;
+        mbar_wait(&empty[s], ((it / Cfg::kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], patch_bytes);
+        tma_load_4d(sa + s * Cfg::kAStageBytes, &tm_x, &full[s], 0, -2, oh0 - 2, n);   // halo and channel pad: OOB zero fill
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_tf32(kTileM, NOUT);
+    mbar_wait(b_full, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1, s = it % Cfg::kStages;
+      mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&full[s], (it / Cfg::kStages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a0 = smem_u32(sa + s * Cfg::kAStageBytes), b0 = smem_u32(sb);
+        for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+          for (int kw = 0; kw < 5; ++kw) {
+            const uint32_t arow = a0 + static_cast<uint32_t>(kh * PW + kw) * Cfg::kRowB;
+#pragma unroll
+            for (int k = 0; k < CK / 8; ++k) {   // C = 16: the zero upper half of the row is simply not multiplied
+              const uint32_t astart = arow + k * 32;
+              uint64_t ad = umma_desc_kmajor<128>(astart);
+              if (bo_mode) ad |= static_cast<uint64_t>((astart >> 7) & 7) << 49;
+              umma_tf32(tmem_base + as * 32, ad, umma_desc_kmajor<128>(b0 + (kh * 5 + kw) * Cfg::kBTapBytes + k * 32), idesc,
+                        (kh | kw | k) != 0);
+            }
+          }
+        }
+        umma_commit(&empty[s]);
+        umma_commit(&acc_full[as]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM lane quadrant = warp % 4; lane = padded position of the tile -------------
+    const int et = tid - 64;                  // 0..127
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;           // tile row = TMEM lane = padded position
+    const int rr = r / PW, owp = r - rr * PW;
+    const bool real = r < Mrows && owp < W;   // 4 of every PW positions (and rows ≥ R·PW) are padding
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int n = tile / tiles_per_img, oh0 = (tile % tiles_per_img) * R;
+      mbar_wait(&acc_full[as], (it >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      float v[NOUT];
+#pragma unroll
+      for (int c0 = 0; c0 < NOUT; c0 += 16) {
+        float t16[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 32 + c0, t16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c0 + j] = t16[j];
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) v[j] += bias[j];
+      }
+      if (real) {
+        float* o = y + (static_cast<size_t>(n * H + oh0 + rr) * W + owp) * NOUT;
+#pragma unroll
+        for (int q = 0; q < NOUT / 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      if constexpr (FWD) {
+        if (stats) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // the previous tile's statistics pass has finished reading sy
+#pragma unroll
+          for (int q = 0; q < NOUT / 4; ++q) {
+            float4 o4 = real ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(sy + r * 128 + ((q ^ (r & 7)) << 4)) = o4;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float s1 = 0.f, s2 = 0.f;
+          const int q = lane >> 2, e = lane & 3;
+          const int w4 = et >> 5;
+          for (int r2 = w4 * 32; r2 < w4 * 32 + 32; ++r2) {
+            const float val = reinterpret_cast<const float*>(sy + r2 * 128 + ((q ^ (r2 & 7)) << 4))[e];
+            s1 += val;
+            s2 += val * val;
+          }
+          s_part[w4 * 2 * NOUT + lane] = s1;
+          s_part[w4 * 2 * NOUT + NOUT + lane] = s2;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float* tile_sums = s_part + 8 * NOUT;
+          if (et < 2 * NOUT) tile_sums[et] = s_part[et] + s_part[2 * NOUT + et] + s_part[4 * NOUT + et] + s_part[6 * NOUT + et];
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          grid_fold(tile_sums, 2 * NOUT, tile, num_tiles, scr, s_part, &s_last, et, 128, NamedSync<1, 128>{}, [&](int i, float tot) {
+            stats[i] = tot;
+            if (i == 0) stats[2 * NOUT] = static_cast<float>(M);
+          });
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// Bm[NOUT][25·32]: K index = tap·32 + c, channels ≥ CK zero (window kernel: 128-byte rows for every C)
+template <bool FWD>
+__global__ void repack_weights_pad32_kernel(const float* __restrict__ w, float* __restrict__ bm, int Cout, int Cin) {
+  const int CK = FWD ? Cin : Cout, NOUT = FWD ? Cout : Cin;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NOUT * 800) return;
+  const int n = i / 800, k = i % 800, tap = k / 32, c = k % 32;
+  float v = 0.f;
+  if (c < CK) v = FWD ? w[(n * Cin + c) * 25 + tap] : w[(c * Cin + n) * 25 + (24 - tap)];
+  bm[i] = v;
+}
+
 // Bm[NOUT][25*CK] without K padding (the TMA-fed kernel loads one [NOUT][CK] box per tap)
 template <bool FWD>
 __global__ void repack_weights_dense_kernel(const float* __restrict__ w, float* __restrict__ bm, int Cout, int Cin) {
@@ -996,6 +1193,21 @@ CUtensorMap make_tmap_2d(const float* base, uint64_t inner, uint64_t outer, uint
 
 // NHWC activation [N,H,W,C] as a rank-4 im2col tensor map for a 5x5 / pad 2 / stride 1 window:
 // bounding box lower corner = -pad, upper corner = pad - (filter - 1); 128 pixels × C channels per load.
+// NHWC activation as a 4-D tiled map {C, W, H, N} with a box of {32 channels, box_w, box_h, 1}: coordinates may start
+// outside the tensor (negative w/h, channels ≥ C) — the hardware zero-fills, which is the conv halo and the channel pad.
+CUtensorMap make_tmap_nhwc_patch(const float* base, int C, int W, int H, int N, int box_w, int box_h) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4, static_cast<cuuint64_t>(H) * W * C * 4};
+  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = driver().cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(nhwc patch) failed: " + cu_error(r));
+  return m;
+}
+
 CUtensorMap make_tmap_im2col(const float* base, int C, int W, int H, int N, CUtensorMapSwizzle swizzle) {
   const DriverApi& d = driver();
   if (!d.cuTensorMapEncodeIm2col) throw std::runtime_error("cuTensorMapEncodeIm2col is not available in this driver");
@@ -1128,6 +1340,58 @@ void launch_conv5x5_dgrad_tma(const float* dy, const float* w, float* dx, ConvSh
   const int grid = std::min(tiles, sm_count());
   kern<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tm_x, tm_b, tm_b, nullptr, dx, nullptr, ReduceScratch{}, s.B, s.H, s.W, tiles);
   check_launch("conv5x5_umma_tma(dgrad)");
+}
+
+// ---- experimental window kernels (see conv5x5_umma_win_kernel) -----------------------------------------------
+static int win_rows_per_tile(const ConvShape& s) {
+  const int PW = s.W + 4;
+  int R = 0;
+  for (int r = 1; r <= s.H; ++r)
+    if (s.H % r == 0 && r * PW <= kTileM && (r + 4) * PW <= 256 && r + 4 <= 256) R = r;
+  return R;
+}
+static int win_base_offset_mode() {
+  static const int m = [] { const char* e = getenv("PDT_WIN_BASE_OFFSET"); return e ? atoi(e) : 1; }();
+  return m;
+}
+
+void launch_conv5x5_fwd_win(const float* x, const float* w, const float* bias, float* y, float* stats, ConvShape s, ReduceScratch scr,
+                            cudaStream_t st) {
+  if (!conv_tcgen05_supported(s)) throw std::invalid_argument("conv5x5 win: only 16→32 channels are implemented");
+  using Cfg = ConvWinCfg<32>;
+  const int R = win_rows_per_tile(s);
+  if (R == 0) throw std::invalid_argument("conv5x5 win: no row tiling fits 128 MMA rows for this image size");
+  const int tiles = s.B * (s.H / R);
+  if (stats && (static_cast<long long>(tiles + tiles / kFoldGroup + 1) * 64 > scr.capacity_floats || tiles / kFoldGroup + 2 > scr.counters))
+    throw std::invalid_argument("conv5x5 win: scratch too small");
+  float* bm = repack_buffer(5, static_cast<size_t>(32) * 800);
+  repack_weights_pad32_kernel<true><<<(32 * 800 + 255) / 256, 256, 0, st>>>(w, bm, 32, 16);
+  check_launch("repack_weights_pad32(fwd)");
+  CUtensorMap tm_x = make_tmap_nhwc_patch(x, 16, s.W, s.H, s.B, s.W + 4, R + 4);
+  CUtensorMap tm_b = make_tmap_2d(bm, 800, 32, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  auto kern = conv5x5_umma_win_kernel<16, 32, true>;
+  opt_in_smem(kern, Cfg::kSmem);
+  const int grid = std::min(tiles, sm_count());
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tm_x, tm_b, bias, y, stats, scr, s.B, s.H, s.W, R, tiles, win_base_offset_mode());
+  check_launch("conv5x5_umma_win(fwd)");
+}
+
+void launch_conv5x5_dgrad_win(const float* dy, const float* w, float* dx, ConvShape s, cudaStream_t st) {
+  if (!conv_tcgen05_supported(s)) throw std::invalid_argument("conv5x5 win dgrad: only 16→32 channels are implemented");
+  using Cfg = ConvWinCfg<16>;
+  const int R = win_rows_per_tile(s);
+  if (R == 0) throw std::invalid_argument("conv5x5 win dgrad: no row tiling fits 128 MMA rows for this image size");
+  const int tiles = s.B * (s.H / R);
+  float* bm = repack_buffer(6, static_cast<size_t>(16) * 800);
+  repack_weights_pad32_kernel<false><<<(16 * 800 + 255) / 256, 256, 0, st>>>(w, bm, 32, 16);
+  check_launch("repack_weights_pad32(dgrad)");
+  CUtensorMap tm_x = make_tmap_nhwc_patch(dy, 32, s.W, s.H, s.B, s.W + 4, R + 4);
+  CUtensorMap tm_b = make_tmap_2d(bm, 800, 16, 32, 16, CU_TENSOR_MAP_SWIZZLE_128B);
+  auto kern = conv5x5_umma_win_kernel<32, 16, false>;
+  opt_in_smem(kern, Cfg::kSmem);
+  const int grid = std::min(tiles, sm_count());
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tm_x, tm_b, nullptr, dx, nullptr, ReduceScratch{}, s.B, s.H, s.W, R, tiles, win_base_offset_mode());
+  check_launch("conv5x5_umma_win(dgrad)");
 }
 
 void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, float* db, ConvShape s, ReduceScratch scr, cudaStream_t st) {

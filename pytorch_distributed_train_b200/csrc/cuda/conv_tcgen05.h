@@ -21,6 +21,12 @@ void launch_conv5x5_fwd_tma(const float* x, const float* w, const float* bias, f
                             cudaStream_t st);
 void launch_conv5x5_dgrad_tma(const float* dy, const float* w, float* dx, ConvShape s, cudaStream_t st);
 
+// EXPERIMENTAL, not validated on hardware (impl == "win"): one tiled TMA load of the haloed patch per tile, the 25 taps
+// as row-shifted UMMA descriptors into that single buffer (NOTES_NEXT.md §1, tools/emulate_window_conv.py).
+void launch_conv5x5_fwd_win(const float* x, const float* w, const float* bias, float* y, float* stats, ConvShape s, ReduceScratch scr,
+                            cudaStream_t st);
+void launch_conv5x5_dgrad_win(const float* dy, const float* w, float* dx, ConvShape s, cudaStream_t st);
+
 // dw [32,16,5,5], db [32] (nullable) from dy NHWC [B,H,W,32] and x NHWC [B,H,W,16]: persistent split-K over
 // pixel tiles with MN-major operands, four TMEM accumulators, deterministic fold of the per-CTA partials.
 void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, float* db, ConvShape s, ReduceScratch scr, cudaStream_t st);

@@ -147,7 +147,10 @@ void register_cuda_bindings(py::module_& m) {
     // Shapes the tensor-core kernels do not cover (conv1: K = 25) always take the SIMT kernel.
     const bool sup = conv_tcgen05_supported(s);
     const bool tc = sup && impl == "tcgen05";
-    if (sup && (impl == "tma" || impl == "auto")) launch_conv5x5_fwd_tma(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
+    if (sup && impl == "win")  // experimental window kernel: explicit opt-in only
+      launch_conv5x5_fwd_win(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
+                             want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
+    else if (sup && (impl == "tma" || impl == "auto")) launch_conv5x5_fwd_tma(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
                                               want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
     else if (tc) launch_conv5x5_fwd_tcgen05(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
                                        want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
@@ -165,7 +168,8 @@ void register_cuda_bindings(py::module_& m) {
     at::Tensor dx = at::empty({s.B, s.H, s.W, s.Cin}, dy.options());
     const bool sup = conv_tcgen05_supported(s);
     const bool tc = sup && impl == "tcgen05";
-    if (sup && (impl == "tma" || impl == "auto")) launch_conv5x5_dgrad_tma(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
+    if (sup && impl == "win") launch_conv5x5_dgrad_win(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
+    else if (sup && (impl == "tma" || impl == "auto")) launch_conv5x5_dgrad_tma(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
     else if (tc) launch_conv5x5_dgrad_tcgen05(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
     else launch_conv5x5_dgrad(dy.data_ptr<float>(), w.data_ptr<float>(), dx.data_ptr<float>(), s, cur_stream(dy));
     return dx;
@@ -176,7 +180,7 @@ void register_cuda_bindings(py::module_& m) {
     c10::cuda::CUDAGuard g(dy.device());
     ConvShape s = conv_shape(x, dw);
     const bool sup = conv_tcgen05_supported(s);
-    const bool tc = sup && (impl == "tcgen05" || ((impl == "auto" || impl == "tma") && wgrad_tcgen05_default()));
+    const bool tc = sup && (impl == "tcgen05" || ((impl == "auto" || impl == "tma" || impl == "win") && wgrad_tcgen05_default()));
     if (tc) launch_conv5x5_wgrad_tcgen05(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
     else launch_conv5x5_wgrad(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
   }, py::arg("dy"), py::arg("x"), py::arg("dw"), py::arg("db") = py::none(), py::arg("impl") = "auto");
