@@ -136,13 +136,18 @@ void register_cuda_bindings(py::module_& m) {
            py::arg("store"), py::arg("rank"), py::arg("size"), py::arg("device"), py::arg("timeout") = 600.0);
 
   // ---- convolution ---------------------------------------------------------------------------------
-  m.def("conv5x5_fwd", [](const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, bool want_stats, const std::string& impl) {
+  m.def("conv5x5_fwd", [](const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, bool want_stats, const std::string& impl,
+                          bool zero_pad) {
     chk(x, "x"); chk(w, "w");
     c10::cuda::CUDAGuard g(x.device());
     ConvShape s = conv_shape(x, w);
     TORCH_CHECK(x.size(3) == s.Cin, "conv5x5_fwd: x channels ", x.size(3), " != weight Cin ", s.Cin);
     at::Tensor y = at::empty({s.B, s.H, s.W, s.Cout}, x.options());
-    at::Tensor stats = want_stats ? at::empty({2 * s.Cout + 1}, x.options()) : at::Tensor();
+    // [2C+1] statistics live in a [2C+4] vector: a 16-byte multiple goes through the vectorised one-shot allreduce
+    // directly (SyncBatchNorm asks for the three pad entries to be zeroed), an odd length would bounce through a
+    // padded temporary (3 extra kernels)
+    at::Tensor stats_full = !want_stats ? at::Tensor() : (zero_pad ? at::zeros({2 * s.Cout + 4}, x.options()) : at::empty({2 * s.Cout + 4}, x.options()));
+    at::Tensor stats = want_stats ? stats_full.narrow(0, 0, 2 * s.Cout + 1) : at::Tensor();
     // auto / tma → fully TMA-fed tcgen05 kernel; tcgen05 → cp.async-gather tcgen05 kernel; simt → CUDA cores.
     // Shapes the tensor-core kernels do not cover (conv1: K = 25) always take the SIMT kernel.
     const bool sup = conv_tcgen05_supported(s);
@@ -156,8 +161,9 @@ void register_cuda_bindings(py::module_& m) {
                                        want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
     else launch_conv5x5_fwd(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), y.data_ptr<float>(),
                             want_stats ? stats.data_ptr<float>() : nullptr, s, scratch(x), cur_stream(x));
-    return py::make_tuple(y, stats);
-  }, py::arg("x"), py::arg("w"), py::arg("bias") = py::none(), py::arg("want_stats") = true, py::arg("impl") = "auto");
+    return py::make_tuple(y, stats);  // stats is a view of the first 2C+1 entries of the zero-padded vector
+  }, py::arg("x"), py::arg("w"), py::arg("bias") = py::none(), py::arg("want_stats") = true, py::arg("impl") = "auto",
+     py::arg("zero_pad") = false);
 
   m.def("conv5x5_dgrad", [](const at::Tensor& dy, const at::Tensor& w, const std::string& impl) {
     chk(dy, "dy"); chk(w, "w");
@@ -248,7 +254,7 @@ void register_cuda_bindings(py::module_& m) {
     c10::cuda::CUDAGuard g(x.device());
     const int N = x.size(0), C = x.size(1);
     const int HW = static_cast<int>(x.numel() / std::max<int64_t>(1, static_cast<int64_t>(N) * C));
-    at::Tensor stats = at::zeros({2 * C + 1}, x.options().dtype(at::kDouble));
+    at::Tensor stats = at::zeros({2 * C + 2}, x.options().dtype(at::kDouble));  // [2C+1] + one pad: 16-byte multiple for the allreduce
     if (x.numel() > 0) launch_bn_stats_nchw_f64(x.data_ptr<float>(), stats.data_ptr<double>(), N, C, HW, scratch(x), cur_stream(x));
     return stats;
   });

@@ -37,6 +37,15 @@ def _inline_allreduce(group, t: torch.Tensor) -> None:
         comm.allreduce(t, dist.ReduceOp.SUM, 1.0).wait()   # NCCL baseline: stream hop + wait
 
 
+def _padded_stats(stats: torch.Tensor) -> torch.Tensor:
+    """conv5x5_fwd hands back the first 2C+1 entries of a zeroed [2C+4] vector; all-reduce the whole padded
+    vector (a 16-byte multiple takes the vectorised kernel, an odd length would bounce through a temporary)."""
+    n = (stats.numel() + 3) // 4 * 4
+    if stats.dim() == 1 and stats.is_contiguous() and stats.untyped_storage().nbytes() >= (stats.storage_offset() + n) * stats.element_size():
+        return stats.as_strided((n,), (1,), stats.storage_offset())
+    return stats
+
+
 def _to_nhwc(x: torch.Tensor) -> torch.Tensor:
     """[B,C,H,W] (any strides) → contiguous [B,H,W,C] without a copy when already channels_last."""
     if x.shape[1] == 1:
@@ -50,9 +59,9 @@ class _ConvBnReluPool(torch.autograd.Function):
         xh = _to_nhwc(x)
         C = w.shape[0]
         if training:
-            y, stats = _C.conv5x5_fwd(xh, w, b, True, impl)
+            y, stats = _C.conv5x5_fwd(xh, w, b, True, impl, group is not None)
             if group is not None:
-                _inline_allreduce(group, stats)   # Σy, Σy², n across the group: SyncBatchNorm
+                _inline_allreduce(group, _padded_stats(stats))   # Σy, Σy², n across the group: SyncBatchNorm
             out, saved = _C.bn_relu_pool_fwd(y, stats, gamma, beta, running_mean, running_var, nbt, momentum, eps, out_nchw)
             count = stats[2 * C:2 * C + 1]
         else:
@@ -192,7 +201,7 @@ def sgd_step(params, grads, momentum_bufs, lr, momentum=0.0, dampening=0.0, weig
 
 # ---- generic (NCHW) BatchNorm pieces used by parallel.SyncBatchNorm ------------------------------------------
 def bn_local_stats(x: torch.Tensor) -> torch.Tensor:
-    """float64 [2C+1] = per-channel Σx, Σx² (accumulated in fp64), then the per-channel element count."""
+    """float64 [2C+2] = per-channel Σx, Σx² (accumulated in fp64), the per-channel element count, one zero pad."""
     return _C.bn_stats_nchw_f64(x)
 
 

@@ -62,11 +62,11 @@ class _SyncBatchNormFn(torch.autograd.Function):
         # the sums by μ²/σ², so they are accumulated, exchanged and combined in fp64 (torch gets the
         # same robustness from Welford + count-weighted merging, _functions.py:39-124)
         if mask & 1:
-            stats = ops.bn_local_stats(xc)  # [2C+1] float64, stats[2C] = count
+            stats = ops.bn_local_stats(xc)  # [2C+2] float64: Σx, Σx², count, one zero pad (16-byte multiple)
         else:
             xf = xc.double()
             dims = _reduce_dims(xf)
-            stats = torch.cat([xf.sum(dims), (xf * xf).sum(dims), xf.new_full((1,), float(count))])
+            stats = torch.cat([xf.sum(dims), (xf * xf).sum(dims), xf.new_full((1,), float(count)), xf.new_zeros(1)])
         _allreduce_now(group, stats)
         total64 = stats[2 * C]
         # every rank holding zero samples is legal as long as somebody has data

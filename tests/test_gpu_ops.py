@@ -229,7 +229,7 @@ def test_convnet_fused_matches_unfused(syncbn_module):
 def test_generic_bn_kernels_match_torch():
     x = torch.randn(8, 12, 9, 7, device=dev()) * 3 + 1
     st = ops.bn_local_stats(x)
-    assert st.dtype == torch.float64 and st[24].item() == 8 * 63
+    assert st.dtype == torch.float64 and st.numel() == 26 and st[24].item() == 8 * 63 and st[25].item() == 0
     assert torch.allclose(st[:12], x.double().sum((0, 2, 3)), rtol=1e-9) and torch.allclose(st[12:24], (x.double() ** 2).sum((0, 2, 3)), rtol=1e-9)
     mean = x.mean((0, 2, 3))
     invstd = (x.var((0, 2, 3), unbiased=False) + 1e-5).rsqrt()
