@@ -54,6 +54,10 @@ SymmComm::SymmComm(std::shared_ptr<Store> store, int rank, int size, int device,
   c10::cuda::CUDAGuard guard(device);
   heap_ = std::make_shared<SymmetricHeap>(std::move(store), rank, size, device, heap_bytes, timeout);
   if (const char* a = getenv("PDT_AR_ALGO")) algo_ = a;
+  // Measured one-shot / two-shot crossover (profiles/allreduce_sweep_{2,8}gpu.json): at N = 2 a one-shot push moves the
+  // same bytes as a two-shot and wins up to 4 MiB (20.8 vs 25.4 µs); at N = 8 it sends 7× the data and loses above
+  // 256 KiB (1 MiB: 24.9 vs 16.2 µs NVLS).  N = 4 is interpolated until it is measured.
+  oneshot_max_ = size <= 2 ? (size_t(4) << 20) : size <= 4 ? (size_t(1) << 20) : (size_t(512) << 10);
   if (const char* m = getenv("PDT_AR_ONESHOT_MAX")) oneshot_max_ = static_cast<size_t>(atoll(m));
   if (const char* b = getenv("PDT_AR_BLOCKS")) cfg_.blocks = atoi(b);
   if (const char* t = getenv("PDT_AR_THREADS")) cfg_.threads = atoi(t);
@@ -105,7 +109,8 @@ void SymmComm::do_allreduce(at::Tensor& t, ReduceOp op, double scale, int channe
   std::string algo = algo_;
   if (algo == "auto") {
     if (slot_bytes * size_ <= half && nbytes <= oneshot_max_) algo = heap_->has_multicast() ? "oneshot_mc" : "oneshot";
-    else algo = nvls_ok ? "nvls" : "twoshot";
+    // with two ranks the switch adds a hop and reduces nothing: peer loads beat NVLS (64 MiB: 137 vs 183 µs)
+    else algo = (nvls_ok && size_ > 2) ? "nvls" : "twoshot";
   }
   if ((algo == "oneshot" || algo == "oneshot_mc") && slot_bytes * size_ > half) algo = nvls_ok ? "nvls" : "twoshot";
   if (algo == "oneshot_mc" && !heap_->has_multicast()) algo = "oneshot";
