@@ -8,7 +8,7 @@ GPU → init_process_group over TCP → seed → model → optional SyncBN → D
 Extra flags cover what the reference hard-codes: ``--init-method`` (its LAN address
 ``tcp://10.9.1.2:34567`` only works on the author's network, ref: ddp_example.py:110; we default
 to loopback with a free port), ``--data synthetic|mnist``, ``--model``, ``--comm fused|nccl``,
-``--steps``, ``--graph`` (whole-step CUDA graph), ``--batch-size``, ``--lr``.
+``--steps``, ``--graph`` (whole-step CUDA graph), ``--batch-size``, ``--lr``, ``--checkpoint`` / ``--resume``.
 """
 from __future__ import annotations
 
@@ -45,6 +45,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--samples", default=60000, type=int, help="synthetic dataset size")
     p.add_argument("--graph", default=False, action="store_true", help="capture the whole training step in a CUDA graph")
     p.add_argument("--log-interval", default=10, type=int)
+    p.add_argument("--checkpoint", default=None, type=str, help="write a checkpoint here at the end of every epoch (rank 0, atomic)")
+    p.add_argument("--resume", default=None, type=str, help="restore model/optimizer/epoch from this checkpoint before training")
     p.add_argument("--set-epoch", default=False, action="store_true",
                    help="call sampler.set_epoch(e) each epoch (the reference does not)")
     return p
@@ -96,9 +98,16 @@ def dist_train(gpu: int, args) -> None:
         step_fn = GraphedTrainStep(model, criterion, optimizer, example_inputs=(
             torch.zeros((batch_size,) + shape, device=device), torch.zeros(batch_size, dtype=torch.int64, device=device)))
 
+    first_epoch = 0
+    if args.resume:
+        info = pdt.utils.load_checkpoint(args.resume, model, optimizer, sampler=train_sampler)
+        first_epoch = info["epoch"]
+        if gpu == 0:
+            print(f"Resumed from {args.resume} at epoch {first_epoch}")
+
     start = datetime.now()
     total_step = len(train_loader)
-    for epoch in range(args.epochs):
+    for epoch in range(first_epoch, args.epochs):
         if args.set_epoch:
             train_sampler.set_epoch(epoch)
         for i, (images, labels) in enumerate(train_loader):
@@ -116,6 +125,8 @@ def dist_train(gpu: int, args) -> None:
                 optimizer.step()
             if (i + 1) % args.log_interval == 0 and gpu == 0:
                 print("Epoch [{}/{}], Step [{}/{}], Loss: {:.4f}".format(epoch + 1, args.epochs, i + 1, total_step, loss.item()))
+        if args.checkpoint:
+            pdt.utils.save_checkpoint(args.checkpoint, model, optimizer, epoch=epoch + 1, sampler=train_sampler)
     if use_cuda:
         torch.cuda.synchronize()
     if gpu == 0:

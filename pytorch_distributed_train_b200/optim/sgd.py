@@ -137,6 +137,20 @@ class SGD(torch.optim.Optimizer):
                 self.state[p]["momentum_buffer"] = self._flat_momentum[off:off + p.numel()].view(p.shape)
         return True
 
+    def load_state_dict(self, state_dict) -> None:
+        """Standard behaviour, plus: when the step is fused with DDP the momentum lives in ONE flat buffer that
+        mirrors the bucket — restored values are copied into it instead of replacing its views."""
+        super().load_state_dict(state_dict)
+        if self._flat_momentum is not None and self._ddp is not None:
+            for p, off in zip(self._ddp._params, self._ddp._param_offsets):
+                st = self.state.get(p)
+                if st is None or st.get("momentum_buffer") is None:
+                    continue
+                view = self._flat_momentum[off:off + p.numel()].view(p.shape)
+                if st["momentum_buffer"].data_ptr() != view.data_ptr():
+                    view.copy_(st["momentum_buffer"])
+                    st["momentum_buffer"] = view
+
     def zero_grad(self, set_to_none: bool = True) -> None:
         if set_to_none:
             return super().zero_grad(set_to_none=True)

@@ -86,3 +86,14 @@ def test_train_script_two_cpu_ranks():
     assert "Use SyncBN in training" in so                      # ref: ddp_example.py:56
     assert "Epoch [1/1], Step [10/20], Loss:" in so and "Epoch [1/1], Step [20/20], Loss:" in so  # ref: :94
     assert "Training complete in: " in so                      # ref: ddp_example.py:97
+
+
+def test_train_script_checkpoint_and_resume(tmp_path):
+    ck = str(tmp_path / "run.pt")
+    base = [sys.executable, os.path.join(ROOT, "train_mnist.py"), "-g", "2", "--backend", "gloo", "--steps", "5", "--samples", "2000",
+            "--log-interval", "5"]
+    a = subprocess.run(base + ["--epochs", "1", "--checkpoint", ck], capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert a.returncode == 0 and os.path.exists(ck), a.stderr[-2000:]
+    b = subprocess.run(base + ["--epochs", "2", "--resume", ck], capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert b.returncode == 0, b.stderr[-2000:]
+    assert "Resumed from" in b.stdout and "Epoch [2/2], Step [5/10]" in b.stdout and "Epoch [1/2]" not in b.stdout

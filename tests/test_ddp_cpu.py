@@ -408,3 +408,51 @@ def _fused_opt(rank, world, momentum):
 def test_optimizer_fused_allreduce_matches_reducer_path(momentum):
     for plain, fused in run_ranks(_fused_opt, 2, momentum):
         assert torch.allclose(plain, fused, rtol=1e-5, atol=1e-6)
+
+
+def _ckpt(rank, world, path, fuse):
+    """Train 2 steps, checkpoint, train 2 more — versus a fresh process state restored from the checkpoint and
+    trained for the same 2 steps: identical parameters and momentum."""
+    def fresh():
+        torch.manual_seed(0)
+        model = pdt.models.ConvNet()
+        opt = pdt.optim.SGD(model.parameters(), 0.05, momentum=0.9)
+        ddp = pdt.DistributedDataParallel(model)
+        if fuse:
+            opt.fuse_with_ddp(ddp)
+        return ddp, opt
+
+    def train(ddp, opt, steps):
+        crit = pdt.nn.CrossEntropyLoss()
+        for s in steps:
+            x, y = _data(rank, s)
+            loss = crit(ddp(x), y)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+    ddp, opt = fresh()
+    train(ddp, opt, [0, 1, 2])
+    pdt.utils.save_checkpoint(path, ddp, opt, epoch=3, extra={"note": "mid"})
+    train(ddp, opt, [3, 4])
+    want = torch.cat([p.detach().flatten() for p in ddp.parameters()])
+    want_buf = ddp.module.layer1[1].running_mean.clone()
+
+    ddp2, opt2 = fresh()
+    if fuse:
+        train(ddp2, opt2, [7, 8, 9])       # get the fused layout (flat momentum arena) in place before restoring into it
+        assert opt2._fused_active
+    info = pdt.utils.load_checkpoint(path, ddp2, opt2)
+    assert info["epoch"] == 3 and info["extra"] == {"note": "mid"}
+    train(ddp2, opt2, [3, 4])
+    got = torch.cat([p.detach().flatten() for p in ddp2.parameters()])
+    bare = pdt.models.ConvNet()
+    pdt.utils.load_checkpoint(path, bare)  # module.-prefixed file into an unwrapped model
+    same_buf = bool(torch.allclose(want_buf, ddp2.module.layer1[1].running_mean))
+    return bool(torch.allclose(want, got, rtol=1e-6, atol=1e-7)), same_buf, os.path.exists(path)
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_checkpoint_resume_is_exact(tmp_path, fuse):
+    res = run_ranks(_ckpt, 2, str(tmp_path / "ck.pt"), fuse)
+    assert all(all(r) for r in res), res
