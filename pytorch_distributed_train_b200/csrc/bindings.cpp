@@ -199,6 +199,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         d["backward_comm_us"] = s.backward_comm_us;
         d["backward_comm_exposed_us"] = s.backward_comm_exposed_us;
         d["backward_total_us"] = s.backward_total_us;
+        d["timed_iterations"] = s.timed_iterations;
+        d["avg_forward_compute_time_us"] = s.avg_forward_us;
+        d["avg_backward_compute_time_us"] = s.avg_backward_compute_us;
+        d["avg_backward_comm_time_us"] = s.avg_backward_comm_us;
+        d["avg_backward_comm_exposed_time_us"] = s.avg_backward_comm_exposed_us;
         d["has_rebuilt_buckets"] = s.has_rebuilt;
         d["gradient_as_bucket_view"] = s.gradient_as_bucket_view;
         d["find_unused_parameters"] = s.find_unused_parameters;

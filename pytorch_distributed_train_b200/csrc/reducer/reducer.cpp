@@ -334,6 +334,14 @@ void Reducer::finalize_backward() {
     stats_.backward_compute_us = us_between(t_backward_start_, t_last_launch_);
     stats_.backward_comm_us = us_between(t_first_launch_, t1);
     stats_.backward_comm_exposed_us = us_between(t0, t1);
+    constexpr int64_t kStatsWarmup = 10;
+    if (stats_.num_iterations > kStatsWarmup) {
+      const double n = static_cast<double>(++stats_.timed_iterations);
+      stats_.avg_forward_us += (stats_.forward_us - stats_.avg_forward_us) / n;
+      stats_.avg_backward_compute_us += (stats_.backward_compute_us - stats_.avg_backward_compute_us) / n;
+      stats_.avg_backward_comm_us += (stats_.backward_comm_us - stats_.avg_backward_comm_us) / n;
+      stats_.avg_backward_comm_exposed_us += (stats_.backward_comm_exposed_us - stats_.avg_backward_comm_exposed_us) / n;
+    }
   }
   stats_.grad_ready_order = ready_order_;
 }

@@ -48,6 +48,10 @@ struct ReducerStats {
   // host-side wall times of the last sampled iteration, microseconds
   double forward_us = 0, backward_compute_us = 0, backward_comm_us = 0, backward_total_us = 0;
   double backward_comm_exposed_us = 0;    // time finalize spent waiting on collectives
+  // running means over the synchronised iterations after the first kStatsWarmup (the reference's logger samples
+  // the same quantities every 100 iterations after the first 10, hdr:reducer.hpp:33,166-170)
+  int64_t timed_iterations = 0;
+  double avg_forward_us = 0, avg_backward_compute_us = 0, avg_backward_comm_us = 0, avg_backward_comm_exposed_us = 0;
   bool has_rebuilt = false;
   bool gradient_as_bucket_view = true;
   bool find_unused_parameters = false;

@@ -456,3 +456,17 @@ def _ckpt(rank, world, path, fuse):
 def test_checkpoint_resume_is_exact(tmp_path, fuse):
     res = run_ranks(_ckpt, 2, str(tmp_path / "ck.pt"), fuse)
     assert all(all(r) for r in res), res
+
+
+def _logger(rank, world):
+    ddp, _ = _train_ours(rank, world, 14)
+    return ddp._get_ddp_logging_data()
+
+
+def test_ddp_logging_data_running_averages():
+    """B11: construction-time facts + runtime averages sampled after the first 10 iterations."""
+    for d in run_ranks(_logger, 2):
+        assert d["world_size"] == 2 and d["backend_name"] in ("gloo", "cpu") and d["num_parameter_tensors"] == 10
+        assert d["bucket_sizes"] == [116136] and d["has_rebuilt_buckets"] and sorted(d["grad_ready_order"]) == list(range(10))
+        assert d["num_iterations"] == 14 and d["timed_iterations"] == 4
+        assert d["avg_forward_compute_time_us"] > 0 and d["avg_backward_compute_time_us"] > 0 and d["avg_backward_comm_time_us"] >= 0
