@@ -118,3 +118,97 @@ def post_localSGD_hook(state: PostLocalSGDState, bucket) -> Future:
         fut = noop_hook(None, bucket)
     state.maybe_increase_iter(bucket)
     return fut
+
+
+class PowerSGDState:
+    """State for :func:`powerSGD_hook` (rank-r gradient compression with error feedback; the substrate ships the
+    same algorithm in ddp_comm_hooks/powerSGD_hook.py — optional surface, unused by the reference).
+
+    For every ≥2-D gradient M (viewed as n×m) the hook communicates P = M·Q (n×r) and Q = Mᵀ·P̂ (m×r) instead of
+    M: two small allreduces per bucket.  The compression error is kept per parameter and added back next step.
+    1-D tensors, and matrices where r·(n+m) would not save at least ``min_compression_rate``×, travel uncompressed
+    in one flat allreduce."""
+
+    def __init__(self, process_group=None, matrix_approximation_rank: int = 1, start_powerSGD_iter: int = 2,
+                 min_compression_rate: float = 2.0, use_error_feedback: bool = True, warm_start: bool = True, random_seed: int = 0):
+        self.process_group = process_group
+        self.rank = int(matrix_approximation_rank)
+        self.start_powerSGD_iter = int(start_powerSGD_iter)
+        self.min_compression_rate = float(min_compression_rate)
+        self.use_error_feedback = use_error_feedback
+        self.warm_start = warm_start
+        self.rng = torch.Generator().manual_seed(random_seed)   # identical Q on every rank
+        self.iter = 0
+        self.errors = {}   # (bucket index, slot) -> residual tensor
+        self.qs = {}       # (bucket index, slot) -> Q reused across steps (warm start)
+
+
+def _orthogonalize(p: torch.Tensor) -> torch.Tensor:
+    q, _ = torch.linalg.qr(p.float(), mode="reduced")
+    return q.to(p.dtype)
+
+
+def powerSGD_hook(state: PowerSGDState, bucket) -> Future:
+    g = _group(state.process_group)
+    world = g.size()
+    if state.iter < state.start_powerSGD_iter:
+        fut = allreduce_hook(g, bucket)
+        if bucket.is_last():
+            state.iter += 1
+        return fut
+    buf = bucket.buffer()
+    grads = bucket.gradients()
+    bidx = bucket.index()
+    plain, low = [], []
+    for slot, t in enumerate(grads):
+        n = t.shape[0] if t.dim() >= 2 else 0
+        m = t.numel() // n if n else 0
+        r = min(state.rank, n, m) if n else 0
+        if n and r * (n + m) * state.min_compression_rate <= n * m:
+            low.append((slot, t, n, m, r))
+        else:
+            plain.append(t)
+    # uncompressed part: one flat allreduce (mean)
+    if plain:
+        flat = torch.cat([t.reshape(-1) for t in plain])
+        g.comm.allreduce(flat, dist.ReduceOp.SUM, 1.0 / world).wait()
+        off = 0
+        for t in plain:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+    if low:
+        mats, ps = [], []
+        for slot, t, n, m, r in low:
+            M = t.reshape(n, m)
+            key = (bidx, slot)
+            if state.use_error_feedback and key in state.errors:
+                M.add_(state.errors[key])
+            q = state.qs.get(key) if state.warm_start else None
+            if q is None or q.shape != (m, r):
+                q = torch.randn(m, r, generator=state.rng).to(device=M.device, dtype=M.dtype)
+                q = _orthogonalize(q)
+            mats.append((key, M, q, r))
+            ps.append(M @ q)
+        flat_p = torch.cat([p.reshape(-1) for p in ps])
+        g.comm.allreduce(flat_p, dist.ReduceOp.SUM, 1.0 / world).wait()
+        qs, off = [], 0
+        for (key, M, q, r), p in zip(mats, ps):
+            p_hat = _orthogonalize(flat_p[off:off + p.numel()].view_as(p))
+            off += p.numel()
+            ps[len(qs)] = p_hat
+            qs.append(M.t() @ p_hat)
+        flat_q = torch.cat([q.reshape(-1) for q in qs])
+        g.comm.allreduce(flat_q, dist.ReduceOp.SUM, 1.0 / world).wait()
+        off = 0
+        for (key, M, _, r), p_hat, q in zip(mats, ps, qs):
+            q_avg = flat_q[off:off + q.numel()].view_as(q)
+            off += q.numel()
+            approx = p_hat @ q_avg.t()
+            if state.use_error_feedback:
+                state.errors[key] = M - approx
+            if state.warm_start:
+                state.qs[key] = q_avg.clone()
+            M.copy_(approx)
+    if bucket.is_last():
+        state.iter += 1
+    return Future(None, buf)

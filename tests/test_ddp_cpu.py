@@ -470,3 +470,35 @@ def test_ddp_logging_data_running_averages():
         assert d["bucket_sizes"] == [116136] and d["has_rebuilt_buckets"] and sorted(d["grad_ready_order"]) == list(range(10))
         assert d["num_iterations"] == 14 and d["timed_iterations"] == 4
         assert d["avg_forward_compute_time_us"] > 0 and d["avg_backward_compute_time_us"] > 0 and d["avg_backward_comm_time_us"] >= 0
+
+
+def _powersgd(rank, world, rank_r):
+    from pytorch_distributed_train_b200.parallel import comm_hooks
+
+    torch.manual_seed(0)
+    ddp = pdt.DistributedDataParallel(pdt.models.ConvNet())
+    state = comm_hooks.PowerSGDState(matrix_approximation_rank=rank_r, start_powerSGD_iter=1, min_compression_rate=1.0)
+    ddp.register_comm_hook(state, comm_hooks.powerSGD_hook)
+    torch.manual_seed(0)
+    plain = pdt.DistributedDataParallel(pdt.models.ConvNet())
+    crit = nn.CrossEntropyLoss()
+    errs = []
+    for s in range(3):
+        x, y = _data(rank, s)
+        for m in (ddp, plain):
+            m.zero_grad()
+            crit(m(x), y).backward()
+        a, b = ddp.module.fc.weight.grad, plain.module.fc.weight.grad
+        errs.append(((a - b).norm() / b.norm()).item())
+    return errs, ddp.module.fc.weight.grad.clone(), ddp.module.fc.bias.grad.clone(), plain.module.fc.bias.grad.clone(), len(state.errors)
+
+
+def test_powersgd_hook_full_rank_is_exact_and_low_rank_agrees_across_ranks():
+    full = run_ranks(_powersgd, 2, 10)   # fc.weight is 10×1568: rank 10 spans it
+    for errs, _, bias, bias_ref, _ in full:
+        assert errs[0] < 1e-5                       # first step uses the plain allreduce (start_powerSGD_iter=1)
+        assert max(errs[1:]) < 1e-3, errs           # full-rank projection reproduces the averaged gradient
+        assert torch.allclose(bias, bias_ref, atol=1e-6)  # 1-D tensors are never compressed
+    low = run_ranks(_powersgd, 2, 1)
+    assert torch.allclose(low[0][1], low[1][1], atol=1e-6), "every rank decompresses to the same gradient"
+    assert 0.0 < max(low[0][0][1:]) < 1.0 and low[0][4] > 0   # lossy, with residuals kept for error feedback
