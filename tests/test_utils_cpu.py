@@ -1,0 +1,53 @@
+"""Auxiliary subsystems on the CPU box: watchdog, rank-aware logging (§5.5), NVTX no-op (§5.1),
+clock sampler fallback, device-timer helpers that must degrade gracefully without a GPU."""
+import json
+import os
+import time
+
+import torch
+
+import pytorch_distributed_train_b200 as pdt
+from mp_helpers import free_port
+
+
+def _watchdog_entry(rank, world, init, outdir):
+    pdt.init_process_group("gloo", init_method=init, world_size=world, rank=rank, timeout=30.0)
+    wd = pdt.utils.Watchdog(interval=0.2, timeout=1.0, abort=False).start()
+    if rank == 1:
+        time.sleep(1.0)      # a few heartbeats, then die without saying goodbye
+        os._exit(0)
+    t0 = time.time()
+    while not wd.dead_peers and time.time() - t0 < 15:
+        time.sleep(0.1)
+    with open(os.path.join(outdir, "r0.json"), "w") as f:
+        json.dump({"dead": wd.dead_peers, "seconds": time.time() - t0}, f)
+        f.flush()
+    os._exit(0)              # peers are gone: skip the orderly teardown
+
+
+def test_watchdog_notices_a_silent_peer(tmp_path):
+    pdt.spawn(_watchdog_entry, args=(2, f"tcp://127.0.0.1:{free_port()}", str(tmp_path)), nprocs=2, grace_period=5.0)
+    res = json.load(open(tmp_path / "r0.json"))
+    assert res["dead"] == [1] and res["seconds"] < 10, res
+
+
+def test_rank_zero_print_and_logger(capsys):
+    pdt.utils.rank_zero_print("hello", 3)       # no process group: behaves like print
+    assert capsys.readouterr().out == "hello 3\n"
+    log = pdt.utils.get_logger("pdt.test")
+    log.setLevel("INFO")
+    log.info("message %d", 7)
+    err = capsys.readouterr().err
+    assert "[pdt][rank" in err and "INFO message 7" in err
+
+
+def test_nvtx_and_clock_sampler_degrade_without_a_gpu():
+    with pdt.utils.nvtx_range("phase"):
+        x = torch.ones(3).sum().item()
+    assert x == 3
+    with pdt.utils.ClockSampler(0) as c:
+        time.sleep(0.02)
+    s = c.summary()
+    assert set(s) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
+    if not torch.cuda.is_available():
+        assert s["samples"] == 0 and s["sm_mhz"] is None
