@@ -182,3 +182,73 @@ def spawn(fn: Callable, args: Sequence = (), nprocs: int = 1, join: bool = True,
         raise ValueError("spawn() only supports start_method='spawn' (CUDA contexts do not survive fork); "
                          "use start_processes() for other start methods")
     return start_processes(fn, args, nprocs, join, daemon, start_method="spawn", **kw)
+
+
+# ---- script launcher: `python -m pytorch_distributed_train_b200.launcher --nproc-per-node N script.py args…` -------------
+def _run_script(local_rank: int, script: str, script_args: Tuple[str, ...], as_module: bool) -> None:
+    import runpy
+
+    sys.argv = [script] + list(script_args)
+    try:
+        if as_module:
+            runpy.run_module(script, run_name="__main__", alter_sys=True)
+        else:
+            runpy.run_path(script, run_name="__main__")
+    except SystemExit as e:  # a script that ends with sys.exit(0) succeeded
+        if e.code not in (None, 0):
+            raise
+
+
+def run(argv: Optional[Sequence[str]] = None) -> None:
+    """Single-node equivalent of ``torchrun --standalone``: starts ``--nproc-per-node`` copies of a script with
+    RANK / LOCAL_RANK / WORLD_SIZE / LOCAL_WORLD_SIZE / MASTER_ADDR / MASTER_PORT exported, so a script that calls
+    ``init_process_group(init_method="env://")`` (ours or torch's) works unchanged; the same failure contract as
+    ``spawn`` (first failing rank kills its siblings, its traceback is re-raised, exit status is non-zero)."""
+    import argparse
+    import socket
+
+    p = argparse.ArgumentParser(prog="python -m pytorch_distributed_train_b200.launcher",
+                                description="one process per GPU on this node, env:// rendezvous")
+    p.add_argument("--nproc-per-node", "--nproc_per_node", type=int, default=1)
+    p.add_argument("--master-addr", "--master_addr", default="127.0.0.1")
+    p.add_argument("--master-port", "--master_port", type=int, default=0, help="0 = pick a free port")
+    p.add_argument("-m", "--module", action="store_true", help="treat SCRIPT as a module name (python -m)")
+    p.add_argument("script")
+    p.add_argument("script_args", nargs=argparse.REMAINDER)
+    a = p.parse_args(argv)
+    port = a.master_port
+    if port == 0:
+        with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+            s.bind((a.master_addr, 0))
+            port = s.getsockname()[1]
+    n = a.nproc_per_node
+    ctx = mp.get_context("spawn")
+    tmpdir = tempfile.mkdtemp(prefix="pdt_run_")
+    launch_id = uuid.uuid4().hex[:12]
+    procs, errs = [], []
+    for i in range(n):
+        env = {"RANK": str(i), "LOCAL_RANK": str(i), "WORLD_SIZE": str(n), "LOCAL_WORLD_SIZE": str(n), "MASTER_ADDR": a.master_addr,
+               "MASTER_PORT": str(port), "PDT_LAUNCH_ID": launch_id, "PDT_LOCAL_RANK": str(i), "PDT_LOCAL_WORLD_SIZE": str(n)}
+        err = os.path.join(tmpdir, f"rank{i}.err")
+        pr = ctx.Process(target=_child_main, args=(_run_script, i, (a.script, tuple(a.script_args), a.module), err, env))
+        pr.start()
+        procs.append(pr)
+        errs.append(err)
+    context = ProcessContext(procs, errs, grace_period=30.0)
+    try:
+        while not context.join():
+            pass
+    finally:
+        context.cleanup()
+        try:
+            os.rmdir(tmpdir)
+        except OSError:
+            pass
+
+
+if __name__ == "__main__":
+    try:
+        run(sys.argv[1:])
+    except ProcessException as e:
+        sys.stderr.write(str(e) + "\n")
+        sys.exit(1)

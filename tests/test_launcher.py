@@ -69,3 +69,31 @@ def test_nonblocking_join_context(tmp_path):
 def test_only_spawn_start_method():
     with pytest.raises(ValueError):
         launcher.spawn(_ok, nprocs=1, start_method="fork")
+
+
+def test_script_launcher_env_rendezvous(tmp_path):
+    """`python -m pytorch_distributed_train_b200.launcher --nproc-per-node 2 script.py` — the torchrun-style entry."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "job.py"
+    script.write_text(
+        "import os, sys, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import pytorch_distributed_train_b200 as pdt\n"
+        "pdt.init_process_group('gloo', init_method='env://')\n"
+        "t = torch.tensor([float(pdt.get_rank() + 1)])\n"
+        "pdt.distributed.all_reduce(t)\n"
+        "print(f\"rank {os.environ['RANK']}/{os.environ['WORLD_SIZE']} local {os.environ['LOCAL_RANK']} sum {t.item()} arg {sys.argv[1]}\", flush=True)\n"
+        "pdt.destroy_process_group()\n"
+        "sys.exit(0)\n")
+    out = subprocess.run([sys.executable, "-m", "pytorch_distributed_train_b200.launcher", "--nproc-per-node", "2", str(script), "hello"],
+                         capture_output=True, text=True, timeout=120, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "rank 0/2 local 0 sum 3.0 arg hello" in out.stdout and "rank 1/2 local 1 sum 3.0 arg hello" in out.stdout
+    bad = tmp_path / "bad.py"
+    bad.write_text("import os\nif os.environ['RANK'] == '1':\n    raise ValueError('boom on rank 1')\nimport time; time.sleep(30)\n")
+    out = subprocess.run([sys.executable, "-m", "pytorch_distributed_train_b200.launcher", "--nproc-per-node", "2", str(bad)],
+                         capture_output=True, text=True, timeout=120, cwd=root)
+    assert out.returncode == 1 and "boom on rank 1" in out.stderr   # sibling killed, traceback surfaced, bounded time
