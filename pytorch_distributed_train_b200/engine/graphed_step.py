@@ -39,6 +39,7 @@ class GraphedTrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_loss: Optional[torch.Tensor] = None
         self.replays = 0
+        self._seed: Optional[torch.Tensor] = None   # d(loss)/d(loss) = 1, allocated once (autograd would fill a new one per step)
         self.fused_optimizer = False
         if fuse_optimizer and hasattr(optimizer, "fuse_with_ddp") and hasattr(model, "enable_optimizer_fusion"):
             optimizer.fuse_with_ddp(model)
@@ -50,7 +51,9 @@ class GraphedTrainStep:
         out = self.model(self.static_inputs[0])
         loss = self.criterion(out, *self.static_inputs[1:])
         self.optimizer.zero_grad(set_to_none=self.set_to_none)
-        loss.backward()
+        if self._seed is None or self._seed.shape != loss.shape or self._seed.dtype != loss.dtype:
+            self._seed = torch.ones_like(loss)
+        loss.backward(self._seed)
         self.optimizer.step()
         return loss
 
