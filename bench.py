@@ -114,7 +114,8 @@ def run_ours(args):
     else:
         before = _C.kernel_launch_count()
         graphed = GraphedTrainStep(ddp, criterion, optimizer, (dev_x[0], dev_y[0]), warmup=3, zero_grad_set_to_none=True,
-                                   fuse_optimizer=os.environ.get("PDT_FUSE_OPT", "1") != "0")
+                                   fuse_optimizer=os.environ.get("PDT_FUSE_OPT", "1") != "0",
+                                   double_buffer_inputs=os.environ.get("PDT_E2E_DOUBLE_BUFFER", "0") == "1")
         launches_per_step = graphed.kernels_per_replay
         step = graphed
         del before

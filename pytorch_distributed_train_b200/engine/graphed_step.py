@@ -30,11 +30,15 @@ import torch
 
 class GraphedTrainStep:
     def __init__(self, model, criterion, optimizer, example_inputs: Sequence[torch.Tensor], warmup: int = 3,
-                 zero_grad_set_to_none: bool = True, fuse_optimizer: bool = True):
+                 zero_grad_set_to_none: bool = True, fuse_optimizer: bool = True, double_buffer_inputs: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainStep needs CUDA")
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.static_inputs = [t.clone() for t in example_inputs]
+        # EXPERIMENTAL (off by default, not yet validated on hardware): two input buffers, one captured graph each; the
+        # next batch's host→device copy runs on a copy stream while the current replay computes (NOTES_NEXT.md §2)
+        self.double_buffer = bool(double_buffer_inputs)
+        self.input_sets = [self.static_inputs] + ([[t.clone() for t in example_inputs]] if self.double_buffer else [])
         self.set_to_none = zero_grad_set_to_none
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_loss: Optional[torch.Tensor] = None
@@ -47,9 +51,10 @@ class GraphedTrainStep:
         self._capture(warmup)
         self.fused_optimizer = bool(getattr(optimizer, "_fused_active", False))
 
-    def _eager_step(self):
-        out = self.model(self.static_inputs[0])
-        loss = self.criterion(out, *self.static_inputs[1:])
+    def _eager_step(self, inputs=None):
+        inputs = self.static_inputs if inputs is None else inputs
+        out = self.model(inputs[0])
+        loss = self.criterion(out, *inputs[1:])
         self.optimizer.zero_grad(set_to_none=self.set_to_none)
         if self._seed is None or self._seed.shape != loss.shape or self._seed.dtype != loss.dtype:
             self._seed = torch.ones_like(loss)
@@ -77,28 +82,47 @@ class GraphedTrainStep:
         parity = (lambda: list(comm.parity_state())) if hasattr(comm, "parity_state") else (lambda: [])
         self.graphs, self.losses = [], []
         p0 = parity()
-        for _ in range(2):
+        for k in range(2):
             g = torch.cuda.CUDAGraph()
             before = _C.kernel_launch_count()
             with torch.cuda.graph(g, stream=side):
-                loss = self._eager_step()
+                loss = self._eager_step(self.input_sets[k % len(self.input_sets)])
             # how many of *our* kernels one replay runs (ATen glue kernels are not counted)
             self.kernels_per_replay = int(_C.kernel_launch_count() - before)
             self.graphs.append(g)
             self.losses.append(loss)
             torch.cuda.synchronize(dev)
             ordered = getattr(self.model, "syncs_buffers_every_step", None)
-            if parity() == p0 or (ordered is not None and ordered()):
+            if not self.double_buffer and (parity() == p0 or (ordered is not None and ordered())):
                 break  # even number of staged collectives per step, or case (a): one graph replays safely
         self.graph, self.static_loss = self.graphs[0], self.losses[0]
+        if self.double_buffer:
+            self.copy_stream = torch.cuda.Stream(device=dev)
+            self._ready = [torch.cuda.Event() for _ in self.graphs]
+            self._done = [torch.cuda.Event() for _ in self.graphs]
+            for e in self._done:
+                e.record(torch.cuda.current_stream(dev))
 
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
-        for dst, src in zip(self.static_inputs, inputs):
-            dst.copy_(src, non_blocking=True)
+        i = self.replays % len(self.graphs)
+        if self.double_buffer:
+            cur = torch.cuda.current_stream(self.static_inputs[0].device)
+            self.copy_stream.wait_event(self._done[i])       # the replay that last read this buffer has finished
+            if any(t.is_cuda for t in inputs):
+                self.copy_stream.wait_stream(cur)            # device-resident sources may still be in flight on the caller's stream
+            with torch.cuda.stream(self.copy_stream):
+                for dst, src in zip(self.input_sets[i], inputs):
+                    dst.copy_(src, non_blocking=True)
+                self._ready[i].record(self.copy_stream)
+            cur.wait_event(self._ready[i])
+        else:
+            for dst, src in zip(self.static_inputs, inputs):
+                dst.copy_(src, non_blocking=True)
         if hasattr(self.optimizer, "sync_lr"):
             self.optimizer.sync_lr()  # scheduler changes reach the captured step through a device scalar
-        i = self.replays % len(self.graphs)
         self.graphs[i].replay()
+        if self.double_buffer:
+            self._done[i].record(torch.cuda.current_stream(self.static_inputs[0].device))
         self.replays += 1
         self.static_loss = self.losses[i]
         return self.static_loss
