@@ -378,7 +378,7 @@ def test_requires_process_group():
 def _fused_opt(rank, world, momentum):
     """optim.SGD.fuse_with_ddp: the optimizer owns the gradient allreduce; results must equal the
     reducer-driven path step for step (protocol test on the CPU backend; the one-kernel version is
-    tests/test_gpu_comm.py::test_fused_allreduce_sgd)."""
+    tests/test_gpu_multigpu.py::test_fused_allreduce_sgd)."""
     out = []
     for fuse in (False, True):
         torch.manual_seed(0)

@@ -3,7 +3,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_$N.txt 2>&1
 export PDT_TEST_WORLD=$N
-timeout -s KILL 900 python -m pytest tests/test_gpu_comm.py -q -m gpu --timeout 300 -p no:cacheprovider > gpurun_out/comm_tests_$N.log 2>&1
+timeout -s KILL 900 python -m pytest tests/test_gpu_multigpu.py -q -m gpu --timeout 300 -p no:cacheprovider > gpurun_out/comm_tests_$N.log 2>&1
 tail -n 15 gpurun_out/comm_tests_$N.log | cut -c1-300
 timeout -s KILL 400 python tools/allreduce_sweep.py --gpus $N --max-mb 64 --out gpurun_out/sweep_$N.json > gpurun_out/sweep_$N.log 2>&1
 tail -n 12 gpurun_out/sweep_$N.log | cut -c1-400

@@ -26,6 +26,6 @@ for impl in ours reference; do
 done
 cat gpurun_out/resnet_*_$N.json | cut -c1-600; tail -n 3 gpurun_out/resnet_*_$N.err | cut -c1-300
 export PDT_TEST_WORLD=$N
-timeout -s KILL 600 python -m pytest tests/test_gpu_comm.py -q -m gpu --timeout 200 -p no:cacheprovider -k "collectives or nccl or fused or lockstep or absent" > gpurun_out/comm_tests_$N.log 2>&1
+timeout -s KILL 600 python -m pytest tests/test_gpu_multigpu.py -q -m gpu --timeout 200 -p no:cacheprovider -k "collectives or nccl or fused or lockstep or absent" > gpurun_out/comm_tests_$N.log 2>&1
 grep -n "^E  \|passed\|failed" gpurun_out/comm_tests_$N.log | cut -c1-300 | tail -n 30
 tail -n 3 gpurun_out/bench_*_$N.err | cut -c1-300

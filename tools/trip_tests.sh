@@ -2,5 +2,5 @@
 N=${1:-2}
 mkdir -p gpurun_out
 export PDT_TEST_WORLD=$N
-timeout -s KILL 900 python -m pytest tests/test_gpu_comm.py -q -m gpu --timeout 240 -p no:cacheprovider ${2:+-k "$2"} > gpurun_out/comm_tests_$N.log 2>&1
+timeout -s KILL 900 python -m pytest tests/test_gpu_multigpu.py -q -m gpu --timeout 240 -p no:cacheprovider ${2:+-k "$2"} > gpurun_out/comm_tests_$N.log 2>&1
 grep -n "^E  \|passed\|failed" gpurun_out/comm_tests_$N.log | cut -c1-400 | tail -n 40
