@@ -433,6 +433,10 @@ class DistributedDataParallel(nn.Module):
         distributed.py:1798).  Gradients are divided by the full world size."""
         if not divide_by_initial_world_size:
             raise NotImplementedError("join(divide_by_initial_world_size=False) is not supported")
+        if getattr(self, "_defer_comm", False):
+            # a joined rank shadows the reducer's per-bucket allreduce; with the fused step the collective lives in
+            # optimizer.step(), which a rank without data never calls
+            raise RuntimeError("join() cannot be combined with the fused allreduce+optimizer step (optim.SGD.fuse_with_ddp)")
         self._join_active = True
         self._join_iters = 0
         try:
