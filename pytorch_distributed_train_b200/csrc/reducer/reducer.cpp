@@ -141,6 +141,22 @@ void Reducer::build_buckets(const std::vector<std::vector<int64_t>>& bucket_indi
 
 void Reducer::prepare_for_forward() {
   std::lock_guard<std::mutex> g(mu_);
+  // A synchronised backward that started (some hook fired) but never reached its last bucket means some parameter
+  // produced no gradient: the collective was not launched and ranks would silently diverge.  Same diagnosis and
+  // advice as the reference's substrate (reducer "Expected to have finished reduction in the prior iteration…").
+  if (expect_hooks_ && saw_first_hook_ && next_bucket_ < buckets_.size()) {
+    std::string missing;
+    int shown = 0;
+    for (size_t i = 0; i < params_.size() && shown < 8; ++i)
+      if (!ready_[i]) { missing += (shown++ ? ", " : "") + std::to_string(i); }
+    expect_hooks_ = false;
+    TORCH_CHECK(false,
+                "Expected to have finished reduction in the prior iteration before starting a new one. This error indicates that "
+                "your module has parameters that were not used in producing loss (parameter indices without a gradient: ",
+                missing, shown == 8 ? ", …" : "",
+                "). Enable unused parameter detection by passing `find_unused_parameters=True` to DistributedDataParallel, and make "
+                "sure all `forward` outputs participate in calculating loss.");
+  }
   ++stats_.num_iterations;
   t_forward_start_ = HClock::now();
 }

@@ -502,3 +502,20 @@ def test_powersgd_hook_full_rank_is_exact_and_low_rank_agrees_across_ranks():
     low = run_ranks(_powersgd, 2, 1)
     assert torch.allclose(low[0][1], low[1][1], atol=1e-6), "every rank decompresses to the same gradient"
     assert 0.0 < max(low[0][0][1:]) < 1.0 and low[0][4] > 0   # lossy, with residuals kept for error feedback
+
+
+def _unused_without_flag(rank, world):
+    torch.manual_seed(0)
+    ddp = pdt.DistributedDataParallel(_Branchy())       # find_unused_parameters=False (default)
+    x = torch.randn(4, 4)
+    ddp(x, False).sum().backward()                      # b and never produce no gradient: the bucket cannot complete
+    try:
+        ddp(x, False)
+    except RuntimeError as e:
+        return str(e)
+    return ""
+
+
+def test_unused_parameter_without_detection_is_diagnosed_not_silent():
+    for msg in run_ranks(_unused_without_flag, 2):
+        assert "Expected to have finished reduction in the prior iteration" in msg and "find_unused_parameters=True" in msg
