@@ -258,6 +258,19 @@ void register_cuda_bindings(py::module_& m) {
     if (x.numel() > 0) launch_bn_stats_nchw_f64(x.data_ptr<float>(), stats.data_ptr<double>(), N, C, HW, scratch(x), cur_stream(x));
     return stats;
   });
+  m.def("bn_finalize", [](const at::Tensor& stats, int64_t C, double eps, double momentum, c10::optional<at::Tensor> running_mean,
+                          c10::optional<at::Tensor> running_var) {
+    chk(stats, "stats", at::kDouble);
+    TORCH_CHECK(stats.numel() >= 2 * C + 1, "bn_finalize: stats must hold 2C+1 entries");
+    TORCH_CHECK(running_mean.has_value() == running_var.has_value(), "bn_finalize: running_mean and running_var go together");
+    c10::cuda::CUDAGuard g(stats.device());
+    auto opt = stats.options().dtype(at::kFloat);
+    at::Tensor mean = at::empty({C}, opt), invstd = at::empty({C}, opt), count = at::empty({1}, opt);
+    launch_bn_finalize(stats.data_ptr<double>(), static_cast<int>(C), eps, static_cast<float>(momentum), mean.data_ptr<float>(),
+                       invstd.data_ptr<float>(), count.data_ptr<float>(), opt_mut(running_mean, "running_mean"),
+                       opt_mut(running_var, "running_var"), cur_stream(stats));
+    return py::make_tuple(mean, invstd, count);
+  });
   m.def("bn_apply_nchw", [](const at::Tensor& x, const at::Tensor& mean, const at::Tensor& invstd, c10::optional<at::Tensor> gamma,
                             c10::optional<at::Tensor> beta) {
     chk(x, "x"); chk(mean, "mean"); chk(invstd, "invstd");

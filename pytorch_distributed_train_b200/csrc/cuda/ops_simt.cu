@@ -567,6 +567,25 @@ __global__ void __launch_bounds__(256) bn_stats_nchw_f64_kernel(const float* __r
   if (threadIdx.x == 0) *scr.counter = 0u;
 }
 
+// All-reduced fp64 statistics → mean, invstd (fp32) and the running-statistics update, in one launch instead of the
+// ≈15 elementwise ATen kernels the same arithmetic costs in Python (generic SyncBatchNorm forward; opt-in for now).
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, double eps, float momentum, float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* __restrict__ count_out, float* running_mean, float* running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = fmax(stats[2 * C], 1.0);
+  const double m = stats[c] / n;
+  const double var = fmax(stats[C + c] / n - m * m, 0.0);
+  mean[c] = static_cast<float>(m);
+  invstd[c] = static_cast<float>(rsqrt(var + eps));
+  if (c == 0) count_out[0] = static_cast<float>(stats[2 * C]);
+  if (running_mean) {
+    const double unbiased = var * (n / fmax(n - 1.0, 1.0));
+    running_mean[c] = running_mean[c] * (1.f - momentum) + static_cast<float>(m) * momentum;
+    running_var[c] = running_var[c] * (1.f - momentum) + static_cast<float>(unbiased) * momentum;
+  }
+}
+
 __global__ void bn_apply_nchw_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
                                      long long total, int C, int HW) {
@@ -897,6 +916,11 @@ void launch_bn_stats_nchw_f64(const float* x, double* stats, int N, int C, int H
   if (static_cast<long long>(C) * S * 4 > scr.capacity_floats) throw std::invalid_argument("bn_stats: reduction scratch too small");
   bn_stats_nchw_f64_kernel<<<C * S, 256, 0, st>>>(x, stats, N, C, HW, S, scr);
   check_launch("bn_stats_nchw_f64");
+}
+void launch_bn_finalize(const double* stats, int C, double eps, float momentum, float* mean, float* invstd, float* count_out,
+                        float* running_mean, float* running_var, cudaStream_t st) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, C, eps, momentum, mean, invstd, count_out, running_mean, running_var);
+  check_launch("bn_finalize");
 }
 void launch_bn_apply_nchw(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta, float* out, int N,
                           int C, int HW, cudaStream_t st) {

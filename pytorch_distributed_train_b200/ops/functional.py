@@ -205,6 +205,11 @@ def bn_local_stats(x: torch.Tensor) -> torch.Tensor:
     return _C.bn_stats_nchw_f64(x)
 
 
+def bn_finalize(stats, C, eps, momentum, running_mean, running_var):
+    """All-reduced float64 statistics → (mean, invstd, count) in fp32, running statistics updated in place: one kernel."""
+    return _C.bn_finalize(stats, int(C), float(eps), float(momentum), running_mean, running_var)
+
+
 def bn_apply(x, mean, invstd, weight, bias):
     return _C.bn_apply_nchw(x, mean.contiguous(), invstd.contiguous(), weight, bias)
 

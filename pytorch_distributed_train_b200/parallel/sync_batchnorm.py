@@ -54,7 +54,8 @@ class _SyncBatchNormFn(torch.autograd.Function):
         count = x.numel() // C if x.numel() else 0
         native = x.is_cuda and ops.native_available() and x.dtype == torch.float32
         # debugging aid: PDT_SYNCBN_KERNELS is a bit mask of the native kernels to use
-        # (1 = local stats, 2 = normalise, 4 = backward reduce, 8 = backward elementwise; default all)
+        # (1 = local stats, 2 = normalise, 4 = backward reduce, 8 = backward elementwise — default 15 = all four;
+        #  16 = fused statistics finalisation, experimental)
         mask = int(os.environ.get("PDT_SYNCBN_KERNELS", "15")) if native else 0
         fused = bool(mask & 2)
         xc = x.contiguous()
@@ -68,17 +69,22 @@ class _SyncBatchNormFn(torch.autograd.Function):
             dims = _reduce_dims(xf)
             stats = torch.cat([xf.sum(dims), (xf * xf).sum(dims), xf.new_full((1,), float(count)), xf.new_zeros(1)])
         _allreduce_now(group, stats)
-        total64 = stats[2 * C]
-        # every rank holding zero samples is legal as long as somebody has data
-        n = total64.clamp_min(1.0)
-        mean64 = stats[:C] / n
-        var64 = (stats[C:2 * C] / n - mean64 * mean64).clamp_min_(0.0)
-        mean, invstd, total = mean64.float(), torch.rsqrt(var64 + eps).float(), total64.float()
-        if running_mean is not None:
-            with torch.no_grad():
-                unbiased = var64 * (n / (n - 1.0).clamp_min(1.0))
-                running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
-                running_var.mul_(1 - momentum).add_(unbiased.to(running_var.dtype), alpha=momentum)
+        if mask & 16 and stats.is_cuda:
+            # one kernel: mean, invstd, count and the running-statistics update (experimental: bit 16 is not in the default mask)
+            mean, invstd, total = ops.bn_finalize(stats, C, eps, momentum, running_mean, running_var)
+            total = total[0]
+        else:
+            total64 = stats[2 * C]
+            # every rank holding zero samples is legal as long as somebody has data
+            n = total64.clamp_min(1.0)
+            mean64 = stats[:C] / n
+            var64 = (stats[C:2 * C] / n - mean64 * mean64).clamp_min_(0.0)
+            mean, invstd, total = mean64.float(), torch.rsqrt(var64 + eps).float(), total64.float()
+            if running_mean is not None:
+                with torch.no_grad():
+                    unbiased = var64 * (n / (n - 1.0).clamp_min(1.0))
+                    running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+                    running_var.mul_(1 - momentum).add_(unbiased.to(running_var.dtype), alpha=momentum)
         if fused:
             out = ops.bn_apply(xc, mean, invstd, weight, bias)
         else:

@@ -31,7 +31,7 @@ def worker(rank, world, port):
     # ---- A/B: one SyncBN layer ------------------------------------------------------------------------
     for shape in [(4, 64, 32, 32)]:
         for busy in (False, True):
-            for kernels in ("15", "0"):
+            for kernels in ("15", "31", "0"):
                 os.environ["PDT_SYNCBN_KERNELS"] = kernels
                 g = torch.Generator(device=dev).manual_seed(100 + rank)
                 x = torch.randn(shape, device=dev, generator=g) * 2 + 0.5
@@ -74,7 +74,7 @@ def worker(rank, world, port):
         torch.cuda.synchronize()
         return {n: p.grad.detach().clone() for n, p in ddp.module.named_parameters()}, loss.item()
 
-    for name, syncbn, kernels in [("convnet", False, "15"), ("convnet", True, "15"), ("resnet", False, "15"), ("resnet", True, "15"), ("resnet", True, "0")]:
+    for name, syncbn, kernels in [("convnet", False, "15"), ("convnet", True, "15"), ("resnet", False, "15"), ("resnet", True, "15"), ("resnet", True, "31"), ("resnet", True, "0")]:
         os.environ["PDT_SYNCBN_KERNELS"] = kernels
         g = torch.Generator().manual_seed(77 + rank)
         if name == "convnet":
