@@ -477,16 +477,68 @@ def all_gather_object(obj, group: Optional[ProcessGroup] = None) -> list:
     return out
 
 
+def _object_key(g: ProcessGroup, tag: str) -> str:
+    g._seq += 1
+    return f"{tag}/{g._seq}"
+
+
+def _last_one_cleans(g: ProcessGroup, key: str, keys) -> None:
+    """Every participant checks out; the last one deletes the exchange's keys so the store does not grow."""
+    if g.store.add(f"{key}/done", 1) == g.size():
+        for k in keys:
+            g.store.delete_key(k)
+        g.store.delete_key(f"{key}/done")
+
+
 def broadcast_object(obj, src: int = 0, group: Optional[ProcessGroup] = None):
+    """Returns ``src``'s object on every rank (control-plane traffic through the store, like the substrate's
+    object collectives which pickle into byte tensors)."""
     import pickle
 
     g = _group(group)
-    g._seq += 1
-    key = f"bco/{g._seq}"
+    key = _object_key(g, "bco")
     if g.rank() == src:
         g.store.set(key, pickle.dumps(obj))
-        return obj
-    return pickle.loads(g.store.get(key))
+        out = obj
+    else:
+        out = pickle.loads(g.store.get(key))
+    _last_one_cleans(g, key, [key])
+    return out
+
+
+def broadcast_object_list(object_list: list, src: int = 0, group: Optional[ProcessGroup] = None) -> None:
+    """torch signature: ``object_list`` is overwritten in place with ``src``'s list (same length on every rank)."""
+    got = broadcast_object(list(object_list) if _group(group).rank() == src else None, src, group)
+    if len(got) != len(object_list):
+        raise ValueError(f"broadcast_object_list: rank {_group(group).rank()} passed {len(object_list)} slots, src sent {len(got)}")
+    object_list[:] = got
+
+
+def gather_object(obj, object_gather_list: Optional[list] = None, dst: int = 0, group: Optional[ProcessGroup] = None) -> None:
+    g = _group(group)
+    if g.rank() == dst and (object_gather_list is None or len(object_gather_list) != g.size()):
+        raise ValueError("gather_object: the destination rank must pass a list with world_size slots")
+    allobjs = all_gather_object(obj, g)
+    if g.rank() == dst:
+        object_gather_list[:] = allobjs
+
+
+def scatter_object_list(scatter_object_output_list: list, scatter_object_input_list: Optional[list] = None, src: int = 0,
+                        group: Optional[ProcessGroup] = None) -> None:
+    """Rank r receives ``scatter_object_input_list[r]`` of ``src`` into ``scatter_object_output_list[0]``."""
+    import pickle
+
+    g = _group(group)
+    if not scatter_object_output_list:
+        raise ValueError("scatter_object_list: the output list needs at least one slot")
+    key = _object_key(g, "sco")
+    keys = [f"{key}/{r}" for r in range(g.size())]
+    if g.rank() == src:
+        if scatter_object_input_list is None or len(scatter_object_input_list) != g.size():
+            raise ValueError("scatter_object_list: src must pass world_size objects")
+        g.store.multi_set(keys, [pickle.dumps(o) for o in scatter_object_input_list])
+    scatter_object_output_list[0] = pickle.loads(g.store.get(keys[g.rank()]))
+    _last_one_cleans(g, key, keys)
 
 
 __all__ = [
@@ -496,4 +548,5 @@ __all__ = [
     "get_default_group", "get_store", "new_group", "all_reduce", "broadcast", "all_gather",
     "all_gather_into_tensor", "reduce", "reduce_scatter_tensor", "gather", "scatter", "all_to_all_single",
     "send", "recv", "isend", "irecv", "barrier", "monitored_barrier", "all_gather_object", "broadcast_object",
+    "broadcast_object_list", "gather_object", "scatter_object_list",
 ]

@@ -192,3 +192,25 @@ def test_debug_detail_names_mismatched_collectives_and_nan_check():
     for msg, nan_msg in run_ranks(_debug_detail, 2):
         assert "collective mismatch at sequence number 2" in msg and "all_reduce" in msg and "broadcast" in msg
         assert "non-finite" in nan_msg
+
+
+def _object_collectives(rank, world):
+    store = dist.get_store()
+    before = store.num_keys()
+    objs = [{"a": 1}, "x", 3.5] if rank == 1 else [None, None, None]
+    dist.broadcast_object_list(objs, src=1)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(("r", rank), gathered, dst=0)
+    out = [None]
+    dist.scatter_object_list(out, [f"for-{r}" for r in range(world)] if rank == 0 else None, src=0)
+    b = dist.broadcast_object({"k": [1, 2]} if rank == 0 else None, 0)
+    dist.barrier()
+    return objs, gathered, out[0], b, store.num_keys() - before
+
+
+def test_object_collectives_and_store_hygiene():
+    res = run_ranks(_object_collectives, 2)
+    for rank, (objs, gathered, got, b, grown) in enumerate(res):
+        assert objs == [{"a": 1}, "x", 3.5] and got == f"for-{rank}" and b == {"k": [1, 2]}
+        assert gathered == ([("r", 0), ("r", 1)] if rank == 0 else None)
+        assert grown <= 2, "object exchanges must clean their keys out of the store"
