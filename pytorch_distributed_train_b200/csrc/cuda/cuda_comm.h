@@ -59,6 +59,12 @@ class SymmComm : public CudaCommBase {
   std::shared_ptr<CommWork> gather(at::Tensor out, at::Tensor in, int root) override;
   std::shared_ptr<CommWork> scatter(at::Tensor out, at::Tensor in, int root) override;
   std::shared_ptr<CommWork> alltoall(at::Tensor out, at::Tensor in) override;
+  // Point-to-point over the symmetric heap (API parity; the training path never uses it): the sender parks the
+  // message in its own staging area (channel 3), posts a store key, and the receiver copies it out of the sender's
+  // mapped heap.  Eager for messages up to one staging half (16 MB); larger ones advance chunk by chunk as the
+  // receiver acknowledges.  Host-synchronous on both sides.
+  std::shared_ptr<CommWork> send(at::Tensor t, int dst) override;
+  std::shared_ptr<CommWork> recv(at::Tensor t, int src) override;
   std::shared_ptr<CommWork> barrier() override;
   void shutdown() override;
 
@@ -94,6 +100,9 @@ class SymmComm : public CudaCommBase {
   void do_allreduce(at::Tensor& t, ReduceOp op, double scale, int channel, cudaStream_t s);
   void do_broadcast(at::Tensor& t, int root, int channel, cudaStream_t s);
   std::shared_ptr<SymmetricHeap> heap_;  // shared with every tensor carved out of it (see alloc_flat)
+  std::shared_ptr<Store> store_;         // control plane of send/recv
+  uint64_t send_seq_[kSymmMaxWorld] = {}, recv_seq_[kSymmMaxWorld] = {};
+  std::string pending_ack_;              // ack key of the message still parked in our staging area ("" = none)
   std::string algo_ = "auto";   // auto | oneshot | oneshot_mc | twoshot | nvls
   size_t oneshot_max_ = 512 * 1024;
   SymmLaunchCfg cfg_;

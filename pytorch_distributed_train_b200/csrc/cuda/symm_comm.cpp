@@ -52,6 +52,7 @@ std::shared_ptr<CommWork> CudaCommBase::enqueue(const std::vector<at::Tensor>& t
 SymmComm::SymmComm(std::shared_ptr<Store> store, int rank, int size, int device, Millis timeout, size_t heap_bytes)
     : CudaCommBase(rank, size, device) {
   c10::cuda::CUDAGuard guard(device);
+  store_ = store;
   heap_ = std::make_shared<SymmetricHeap>(std::move(store), rank, size, device, heap_bytes, timeout);
   if (const char* a = getenv("PDT_AR_ALGO")) algo_ = a;
   // Measured one-shot / two-shot crossover (profiles/allreduce_sweep_{2,8}gpu.json): at N = 2 a one-shot push moves the
@@ -243,6 +244,62 @@ void SymmComm::broadcast_inline(at::Tensor t, int root) {
   record("broadcast_inline", &t);
   c10::cuda::CUDAGuard guard(device_);
   do_broadcast(t, root, kChanInline, c10::cuda::getCurrentCUDAStream(device_).stream());
+}
+
+// ---- point-to-point ------------------------------------------------------------------------------------
+namespace {
+constexpr int kChanP2P = 3;
+std::string p2p_key(int src, int dst, uint64_t seq) { return "p2p/" + std::to_string(src) + ">" + std::to_string(dst) + "/" + std::to_string(seq); }
+}  // namespace
+
+std::shared_ptr<CommWork> SymmComm::send(at::Tensor t, int dst) {
+  check(t, "send");
+  TORCH_CHECK(dst >= 0 && dst < size_ && dst != rank_, "send: invalid destination rank ", dst);
+  record("send", &t);
+  c10::cuda::CUDAGuard guard(device_);
+  cudaStream_t s = c10::cuda::getCurrentCUDAStream(device_).stream();
+  const size_t half = heap_->staging_half_bytes(kChanP2P), nbytes = t.nbytes();
+  char* stage = heap_->local_base() + heap_->staging_off(kChanP2P, 0);
+  const char* p = static_cast<const char*>(t.data_ptr());
+  for (size_t done = 0; done < nbytes || (nbytes == 0 && done == 0); done += half) {
+    const size_t n = std::min(half, nbytes - done);
+    if (!pending_ack_.empty()) {  // the previous message must have left the staging area before it is overwritten
+      store_->get(pending_ack_);
+      store_->delete_key(pending_ack_);
+      pending_ack_.clear();
+    }
+    if (n) PDT_CUDA_CHECK(cudaMemcpyAsync(stage, p + done, n, cudaMemcpyDeviceToDevice, s));
+    PDT_CUDA_CHECK(cudaStreamSynchronize(s));
+    const std::string key = p2p_key(rank_, dst, send_seq_[dst]++);
+    store_->set(key + "/d", std::to_string(n));
+    pending_ack_ = key + "/a";
+    if (nbytes == 0) break;
+  }
+  return std::make_shared<CudaWork>(device_, std::vector<at::Tensor>{});
+}
+
+std::shared_ptr<CommWork> SymmComm::recv(at::Tensor t, int src) {
+  check(t, "recv");
+  TORCH_CHECK(src >= 0 && src < size_ && src != rank_, "recv: invalid source rank ", src);
+  record("recv", &t);
+  c10::cuda::CUDAGuard guard(device_);
+  cudaStream_t s = c10::cuda::getCurrentCUDAStream(device_).stream();
+  const size_t half = heap_->staging_half_bytes(kChanP2P), nbytes = t.nbytes();
+  const char* stage = heap_->base(src) + heap_->staging_off(kChanP2P, 0);   // the sender's staging area, mapped here
+  char* p = static_cast<char*>(t.data_ptr());
+  for (size_t done = 0; done < nbytes || (nbytes == 0 && done == 0); done += half) {
+    const size_t n = std::min(half, nbytes - done);
+    const std::string key = p2p_key(src, rank_, recv_seq_[src]++);
+    const std::string posted = store_->get(key + "/d");  // blocks until the sender has parked this chunk
+    TORCH_CHECK(static_cast<size_t>(std::stoull(posted)) == n, "recv: rank ", src, " sent ", posted, " bytes where ", n,
+                " were expected (mismatched send/recv sizes)");
+    if (n) PDT_CUDA_CHECK(cudaMemcpyAsync(p + done, stage, n, cudaMemcpyDeviceToDevice, s));
+    PDT_CUDA_CHECK(cudaStreamSynchronize(s));
+    store_->delete_key(key + "/d");
+    store_->set(key + "/a", "1");
+    if (nbytes == 0) break;
+  }
+  return std::make_shared<CudaWork>(device_, std::vector<at::Tensor>{});
 }
 
 std::shared_ptr<CommWork> SymmComm::allgather(at::Tensor out, at::Tensor in) {

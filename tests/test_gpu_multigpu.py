@@ -386,3 +386,30 @@ def _stress(rank, world):
 
 def test_ten_thousand_back_to_back_collectives():
     assert run_ranks(_stress, _world(), backend="nccl") == [0] * _world()
+
+
+def _p2p(rank, world):
+    """send / recv over the symmetric heap: ring exchange (eager, so send-then-recv does not deadlock), a message larger
+    than one staging half (chunked, needs the matching recv posted), an empty tensor."""
+    dev = torch.device("cuda", rank)
+    nxt, prv = (rank + 1) % world, (rank - 1) % world
+    out = torch.full((1000,), float(rank), device=dev)
+    inp = torch.empty(1000, device=dev)
+    dist.send(out, nxt)
+    dist.recv(inp, prv)
+    ok = bool(inp.eq(float(prv)).all())
+    big = 5 * (1 << 20) + 3                                   # 20 MB + 12 B of fp32: two chunks
+    if rank == 0:
+        dist.send(torch.arange(big, device=dev, dtype=torch.float32), 1)
+        dist.send(torch.empty(0, device=dev), 1)
+    elif rank == 1:
+        got = torch.empty(big, device=dev)
+        dist.recv(got, 0)
+        ok = ok and bool(torch.equal(got, torch.arange(big, device=dev, dtype=torch.float32)))
+        dist.recv(torch.empty(0, device=dev), 0)
+    dist.barrier()
+    return ok
+
+
+def test_send_recv_over_the_symmetric_heap():
+    assert all(run_ranks(_p2p, _world(), backend="nccl"))
