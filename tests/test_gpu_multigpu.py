@@ -12,6 +12,11 @@ from mp_helpers import free_port, run_ranks
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 dist = pdt.distributed
 
+# Tests written after the round's GPU budget was spent have never executed on hardware; they stay out of the default
+# `-m gpu` run until they have passed once (tools/trip_first_2gpu.sh sets PDT_TEST_EXPERIMENTAL=1).
+not_yet_run_on_hardware = pytest.mark.skipif(os.environ.get("PDT_TEST_EXPERIMENTAL") != "1",
+                                             reason="written without GPU access; set PDT_TEST_EXPERIMENTAL=1 to run")
+
 
 def _world():
     return min(torch.cuda.device_count(), int(os.environ.get("PDT_TEST_WORLD", "8")))
@@ -384,6 +389,7 @@ def _stress(rank, world):
     return comm.status()
 
 
+@not_yet_run_on_hardware
 def test_ten_thousand_back_to_back_collectives():
     assert run_ranks(_stress, _world(), backend="nccl") == [0] * _world()
 
@@ -411,5 +417,6 @@ def _p2p(rank, world):
     return ok
 
 
+@not_yet_run_on_hardware
 def test_send_recv_over_the_symmetric_heap():
     assert all(run_ranks(_p2p, _world(), backend="nccl"))
