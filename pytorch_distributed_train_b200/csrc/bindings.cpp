@@ -185,6 +185,21 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("set_postscale", &Reducer::set_postscale)
       .def("set_defer_comm", &Reducer::set_defer_comm)
       .def_property_readonly("defer_comm", &Reducer::defer_comm)
+      .def("set_chunking", &Reducer::set_chunking, py::arg("min_chunk_bytes"), py::arg("max_chunks"))
+      .def("set_fused_sgd",
+           [](Reducer& r, c10::optional<at::Tensor> param_flat, c10::optional<at::Tensor> momentum_flat, double lr,
+              c10::optional<at::Tensor> lr_tensor, double momentum, double dampening, double weight_decay, bool nesterov, bool first_step,
+              c10::optional<at::Tensor> bcast, int64_t bcast_root) {
+             FusedSgd h;
+             h.lr = lr; h.momentum = momentum; h.dampening = dampening; h.weight_decay = weight_decay;
+             h.nesterov = nesterov; h.first_step = first_step;
+             if (lr_tensor.has_value()) h.lr_tensor = *lr_tensor;
+             r.set_fused_sgd(param_flat.value_or(at::Tensor()), momentum_flat.value_or(at::Tensor()), h, bcast.value_or(at::Tensor()), bcast_root);
+           },
+           py::arg("param_flat"), py::arg("momentum_flat") = py::none(), py::arg("lr") = 0.0, py::arg("lr_tensor") = py::none(),
+           py::arg("momentum") = 0.0, py::arg("dampening") = 0.0, py::arg("weight_decay") = 0.0, py::arg("nesterov") = false,
+           py::arg("first_step") = false, py::arg("bcast") = py::none(), py::arg("bcast_root") = 0)
+      .def_property_readonly("fused_sgd", &Reducer::fused_sgd)
       .def("stats", [](Reducer& r) {
         ReducerStats s = r.stats();
         py::dict d;
@@ -199,6 +214,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         d["backward_comm_us"] = s.backward_comm_us;
         d["backward_comm_exposed_us"] = s.backward_comm_exposed_us;
         d["backward_total_us"] = s.backward_total_us;
+        d["reduce_chunks"] = s.reduce_chunks;
         d["timed_iterations"] = s.timed_iterations;
         d["avg_forward_compute_time_us"] = s.avg_forward_us;
         d["avg_backward_compute_time_us"] = s.avg_backward_compute_us;

@@ -1,5 +1,6 @@
 #include "comm.h"
 
+#include <c10/core/GradMode.h>
 #include <c10/util/Exception.h>
 
 #include <chrono>
@@ -30,6 +31,47 @@ std::shared_ptr<CommWork> Comm::scatter(at::Tensor, at::Tensor, int) { TORCH_CHE
 std::shared_ptr<CommWork> Comm::alltoall(at::Tensor, at::Tensor) { TORCH_CHECK(false, "alltoall", kUnsupported); }
 std::shared_ptr<CommWork> Comm::send(at::Tensor, int) { TORCH_CHECK(false, "send", kUnsupported); }
 std::shared_ptr<CommWork> Comm::recv(at::Tensor, int) { TORCH_CHECK(false, "recv", kUnsupported); }
+
+namespace {
+class HostStamp : public DeviceStamp {
+ public:
+  HostStamp() : t_(std::chrono::steady_clock::now()) {}
+  bool ready() override { return true; }
+  double us_since(DeviceStamp& earlier) override {
+    return std::chrono::duration<double, std::micro>(t_ - static_cast<HostStamp&>(earlier).t_).count();
+  }
+
+ private:
+  std::chrono::steady_clock::time_point t_;
+};
+
+class DoneWork : public CommWork {
+ public:
+  void wait() override {}
+  void synchronize() override {}
+  bool is_completed() override { return true; }
+};
+}  // namespace
+
+std::shared_ptr<DeviceStamp> Comm::stamp(bool) { return std::make_shared<HostStamp>(); }
+
+std::shared_ptr<CommWork> Comm::allreduce_sgd(at::Tensor grad, at::Tensor param, at::Tensor momentum_buf, const FusedSgd& h,
+                                              at::Tensor bcast, int bcast_root) {
+  // reference composition (CPU backend, NCCL baseline): three steps where SymmComm needs one kernel
+  allreduce(grad, ReduceOp::SUM, 1.0 / static_cast<double>(size()))->wait();
+  c10::NoGradGuard ng;
+  at::Tensor g = h.weight_decay != 0 ? grad.add(param, h.weight_decay) : grad;
+  if (h.momentum != 0) {
+    TORCH_CHECK(momentum_buf.defined() && momentum_buf.numel() == grad.numel(), "allreduce_sgd: momentum buffer required");
+    if (h.first_step) momentum_buf.copy_(g);
+    else momentum_buf.mul_(h.momentum).add_(g, 1.0 - h.dampening);
+    g = h.nesterov ? g.add(momentum_buf, h.momentum) : momentum_buf;
+  }
+  if (h.lr_tensor.defined()) param.sub_(g * h.lr_tensor);
+  else param.add_(g, -h.lr);
+  if (bcast.defined() && bcast.numel() > 0 && size() > 1) broadcast(bcast, bcast_root)->wait();
+  return std::make_shared<DoneWork>();
+}
 
 void Comm::record(const char* op, const at::Tensor* t) {
   std::lock_guard<std::mutex> g(rec_mu_);

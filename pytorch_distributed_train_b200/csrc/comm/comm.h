@@ -30,6 +30,23 @@ class CommWork {
   virtual bool is_completed() = 0;
 };
 
+// A point in device time: an event on the compute (or comm) stream for CUDA backends, the host clock otherwise.
+// The reducer's logger is built on these so that its numbers are *device* times ("CUDA-event
+// timers for fwd / bwd-compute / bwd-comm"), not host enqueue times.
+class DeviceStamp {
+ public:
+  virtual ~DeviceStamp() = default;
+  virtual bool ready() = 0;                                   // has the device passed this point?
+  virtual double us_since(DeviceStamp& earlier) = 0;          // both must be ready()
+};
+
+// Hyper-parameters of the SGD update fused into a gradient reduction (Comm::allreduce_sgd).
+struct FusedSgd {
+  double lr = 0, momentum = 0, dampening = 0, weight_decay = 0;
+  bool nesterov = false, first_step = false;
+  at::Tensor lr_tensor;      // optional device scalar (CUDA-graph friendly schedules); overrides lr
+};
+
 class Comm {
  public:
   virtual ~Comm() = default;
@@ -57,6 +74,17 @@ class Comm {
   virtual std::shared_ptr<CommWork> recv(at::Tensor t, int src);
   virtual std::shared_ptr<CommWork> barrier() = 0;
   virtual void shutdown() {}
+
+  // grad <- mean_r(grad_r);  param <- SGD(param, grad)  on flat fp32 vectors of equal layout — the DDP reducer's
+  // per-chunk launch when the optimizer is fused into the reduction.  `bcast` (optional): afterwards every rank's
+  // `bcast` tensor holds `bcast_root`'s contents (DDP's BatchNorm-buffer sync riding on the last chunk).
+  // Default: allreduce + ATen ops + broadcast; SymmComm runs ONE kernel with one cross-GPU barrier.
+  virtual std::shared_ptr<CommWork> allreduce_sgd(at::Tensor grad, at::Tensor param, at::Tensor momentum_buf, const FusedSgd& h,
+                                                  at::Tensor bcast, int bcast_root);
+  // Device-time marks for the reducer's logger.  on_comm_stream: mark the backend's collective stream instead of
+  // the caller's.  capturing(): a CUDA graph is being recorded (no timing marks, no host-visible state).
+  virtual std::shared_ptr<DeviceStamp> stamp(bool on_comm_stream = false);
+  virtual bool capturing() const { return false; }
 
   // Flight recorder: ring of the last K collectives issued on this rank.
   struct Record { uint64_t seq; std::string op; int64_t numel; std::string dtype; double t_enqueue; };

@@ -35,6 +35,8 @@ class CudaCommBase : public Comm {
   bool is_cuda() const override { return true; }
   int device() const { return device_; }
   c10::cuda::CUDAStream comm_stream() const { return comm_stream_; }
+  std::shared_ptr<DeviceStamp> stamp(bool on_comm_stream = false) override;   // timing event on the compute / comm stream
+  bool capturing() const override;
 
  protected:
   // Runs fn(stream) on the comm stream, ordered after the caller's current stream; the tensors
@@ -67,6 +69,9 @@ class SymmComm : public CudaCommBase {
   std::shared_ptr<CommWork> recv(at::Tensor t, int src) override;
   std::shared_ptr<CommWork> barrier() override;
   void shutdown() override;
+  // ONE kernel on the comm stream: one-shot mean-allreduce of the gradient chunk + SGD update (+ buffer broadcast).
+  std::shared_ptr<CommWork> allreduce_sgd(at::Tensor grad, at::Tensor param, at::Tensor momentum_buf, const FusedSgd& h, at::Tensor bcast,
+                                          int bcast_root) override;
 
   // Same collective launched directly on the caller's current stream (channel kChanInline):
   // no stream hop — used where the result is needed by the very next kernel (SyncBatchNorm).
@@ -102,6 +107,7 @@ class SymmComm : public CudaCommBase {
   std::shared_ptr<SymmetricHeap> heap_;  // shared with every tensor carved out of it (see alloc_flat)
   std::shared_ptr<Store> store_;         // control plane of send/recv
   uint64_t send_seq_[kSymmMaxWorld] = {}, recv_seq_[kSymmMaxWorld] = {};
+  uint64_t alloc_seq_ = 0;               // alloc_flat is collective: sequence number of the store exchange
   std::string pending_ack_;              // ack key of the message still parked in our staging area ("" = none)
   std::string algo_ = "auto";   // auto | oneshot | oneshot_mc | twoshot | nvls
   size_t oneshot_max_ = 512 * 1024;

@@ -2,7 +2,10 @@
 #include <c10/cuda/CUDACachingAllocator.h>
 #include <c10/cuda/CUDAGuard.h>
 
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <iterator>
 #include <sstream>
 
 #include "cuda_comm.h"
@@ -48,6 +51,29 @@ std::shared_ptr<CommWork> CudaCommBase::enqueue(const std::vector<at::Tensor>& t
   return work;
 }
 
+namespace {
+class CudaStamp : public DeviceStamp {
+ public:
+  explicit CudaStamp(c10::cuda::CUDAStream s) : ev_(cudaEventDefault) { ev_.record(s); }
+  bool ready() override { return ev_.query(); }
+  double us_since(DeviceStamp& earlier) override { return static_cast<double>(static_cast<CudaStamp&>(earlier).ev_.elapsed_time(ev_)) * 1e3; }
+
+ private:
+  at::cuda::CUDAEvent ev_;
+};
+}  // namespace
+
+std::shared_ptr<DeviceStamp> CudaCommBase::stamp(bool on_comm_stream) {
+  c10::cuda::CUDAGuard guard(device_);
+  return std::make_shared<CudaStamp>(on_comm_stream ? comm_stream_ : c10::cuda::getCurrentCUDAStream(device_));
+}
+
+bool CudaCommBase::capturing() const {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(c10::cuda::getCurrentCUDAStream(device_).stream(), &st);
+  return st != cudaStreamCaptureStatusNone;
+}
+
 // ---- SymmComm ---------------------------------------------------------------------------------------
 SymmComm::SymmComm(std::shared_ptr<Store> store, int rank, int size, int device, Millis timeout, size_t heap_bytes)
     : CudaCommBase(rank, size, device) {
@@ -84,7 +110,44 @@ std::string SymmComm::describe() const {
 at::Tensor SymmComm::alloc_flat(int64_t numel, at::ScalarType dtype, const at::Device& device) {
   TORCH_CHECK(device.is_cuda() && device.index() == device_, "alloc_flat: device mismatch");
   const size_t nbytes = static_cast<size_t>(std::max<int64_t>(numel, 1)) * c10::elementSize(dtype);
+  // alloc_flat is a *collective* (every rank calls it in the same order — DDP construction, bucket rebuild, optimizer
+  // fusion).  Kernels address peers as peer[r] + local_offset, so the allocator state must be identical everywhere:
+  //  (1) blocks parked by tensor deleters are released only if *every* rank has parked them (set intersection
+  //      exchanged through the store), after the device has drained (no in-flight kernel can still touch them);
+  //  (2) the offset handed out is cross-checked against rank 0's and a mismatch raises instead of corrupting memory.
+  const uint64_t seq = alloc_seq_++;
+  const std::string base = "symm/alloc/" + std::to_string(seq) + "/";
+  if (size_ > 1) {
+    std::vector<size_t> mine = heap_->pending_frees();
+    std::string blob(reinterpret_cast<const char*>(mine.data()), mine.size() * sizeof(size_t));
+    store_->set(base + "f/" + std::to_string(rank_), blob);
+    std::vector<size_t> common = mine;
+    for (int r = 0; r < size_ && !common.empty(); ++r) {
+      if (r == rank_) continue;
+      const std::string theirs = store_->get(base + "f/" + std::to_string(r));
+      std::vector<size_t> v(theirs.size() / sizeof(size_t));
+      std::memcpy(v.data(), theirs.data(), v.size() * sizeof(size_t));
+      std::vector<size_t> both;
+      std::set_intersection(common.begin(), common.end(), v.begin(), v.end(), std::back_inserter(both));
+      common.swap(both);
+    }
+    if (!common.empty()) {
+      c10::cuda::CUDAGuard guard(device_);
+      PDT_CUDA_CHECK(cudaDeviceSynchronize());
+      heap_->apply_frees(common);
+    }
+  }
   void* p = heap_->alloc(nbytes, 256);
+  if (size_ > 1) {
+    const std::string off = std::to_string(heap_->offset_of(p));
+    store_->set(base + "o/" + std::to_string(rank_), off);
+    const std::string off0 = rank_ == 0 ? off : store_->get(base + "o/0");
+    if (off0 != off) {
+      heap_->free(p);
+      TORCH_CHECK(false, "symmetric heap diverged: allocation #", seq, " (", nbytes, " B) landed at offset ", off, " on rank ", rank_,
+                  " but at ", off0, " on rank 0 — ranks must issue the same sequence of alloc_flat calls");
+    }
+  }
   // the tensor co-owns the heap: parameters/buckets may outlive the communicator object
   std::shared_ptr<SymmetricHeap> heap = heap_;
   at::Tensor t = at::from_blob(p, {numel}, [heap, p](void*) { heap->free(p); }, at::TensorOptions().dtype(dtype).device(device));
@@ -209,6 +272,38 @@ void SymmComm::allreduce_sgd_inline(at::Tensor grad, at::Tensor param, c10::opti
                                lr_tensor.has_value() ? lr_tensor->data_ptr<float>() : nullptr, static_cast<float>(lr),
                                static_cast<float>(momentum), static_cast<float>(dampening), static_cast<float>(weight_decay), nesterov,
                                first_step, heap_->has_multicast() && algo_ != "oneshot", cfg_, s);
+}
+
+std::shared_ptr<CommWork> SymmComm::allreduce_sgd(at::Tensor grad, at::Tensor param, at::Tensor momentum_buf, const FusedSgd& h, at::Tensor bcast,
+                                                  int bcast_root) {
+  check(grad, "allreduce_sgd grad");
+  check(param, "allreduce_sgd param");
+  const bool fits = grad.scalar_type() == at::kFloat && param.scalar_type() == at::kFloat && grad.numel() == param.numel() &&
+                    grad.numel() % 4 == 0 && reinterpret_cast<uintptr_t>(grad.data_ptr()) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(param.data_ptr()) % 16 == 0 &&
+                    (!momentum_buf.defined() || reinterpret_cast<uintptr_t>(momentum_buf.data_ptr()) % 16 == 0);
+  const size_t bc_bytes = (bcast.defined() && size_ > 1) ? bcast.nbytes() : 0;
+  const bool bc_ok = bc_bytes == 0 || (bcast.is_cuda() && bcast.is_contiguous() && bc_bytes % 16 == 0 &&
+                                       reinterpret_cast<uintptr_t>(bcast.data_ptr()) % 16 == 0);
+  const size_t need = grad.nbytes() * static_cast<size_t>(size_) + bc_bytes;
+  if (size_ == 1 || !fits || !bc_ok || need > heap_->staging_half_bytes(kChanComm))
+    return Comm::allreduce_sgd(grad, param, momentum_buf, h, bcast, bcast_root);  // composition: allreduce + ATen + broadcast
+  TORCH_CHECK(h.momentum == 0 || (momentum_buf.defined() && momentum_buf.numel() == grad.numel()), "allreduce_sgd: momentum buffer required");
+  record("allreduce_sgd", &grad);
+  std::vector<at::Tensor> keep{grad, param};
+  if (momentum_buf.defined()) keep.push_back(momentum_buf);
+  if (bc_bytes) keep.push_back(bcast);
+  if (h.lr_tensor.defined()) keep.push_back(h.lr_tensor);
+  return enqueue(keep, [&](cudaStream_t s) {
+    const int parity = heap_->next_parity(kChanComm);
+    launch_allreduce_sgd_oneshot(heap_->dev(kChanComm), grad.data_ptr<float>(), param.data_ptr<float>(),
+                                 (h.momentum != 0 && momentum_buf.defined()) ? momentum_buf.data_ptr<float>() : nullptr,
+                                 heap_->staging_off(kChanComm, parity), static_cast<size_t>(grad.numel()), 1.0f / size_,
+                                 h.lr_tensor.defined() ? h.lr_tensor.data_ptr<float>() : nullptr, static_cast<float>(h.lr),
+                                 static_cast<float>(h.momentum), static_cast<float>(h.dampening), static_cast<float>(h.weight_decay),
+                                 h.nesterov, h.first_step, heap_->has_multicast() && algo_ != "oneshot", cfg_, s,
+                                 bc_bytes ? bcast.data_ptr() : nullptr, bc_bytes, bcast_root);
+  });
 }
 
 void SymmComm::do_broadcast(at::Tensor& t, int root, int channel, cudaStream_t s) {

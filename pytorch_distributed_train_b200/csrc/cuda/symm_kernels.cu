@@ -120,12 +120,21 @@ __global__ void __launch_bounds__(512) allreduce_oneshot_push_kernel(const __gri
   ep.commit(d, blockIdx.x);
 }
 
-// ---- fused one-shot allreduce + SGD ------------------------------------------------------------------
+// ---- fused one-shot allreduce + SGD (+ optional broadcast) ---------------------------------------------------
+// The DDP reducer's per-chunk launch when the optimizer is fused into the reduction.  One cross-GPU barrier:
+//   push my gradient chunk into slot[rank] of every peer's staging half  (P2P stores, or one multimem.st)
+//   [root only] push `bc_nvec` vectors of the module-buffer arena into every peer's staging, behind the slots
+//   barrier
+//   rank-ordered sum × scale → averaged gradient (kept in `grad`, like the reference's allreduce) → SGD update
+//   copy the broadcast payload from my staging into my buffer arena
+// The broadcast goes through staging, not straight into the peers' arenas: a slower peer may still be running the
+// forward pass that read-modify-writes its own running statistics.
 template <bool MC>
 __global__ void __launch_bounds__(512) allreduce_sgd_oneshot_kernel(const __grid_constant__ SymmDev d, float4* grad, float4* param, float4* mom,
                                                                     size_t stage_off, size_t nvec, float scale,
                                                                     const float* lr_dev, float lr_host, float momentum,
-                                                                    float dampening, float wd, int nesterov, int first_step) {
+                                                                    float dampening, float wd, int nesterov, int first_step,
+                                                                    uint4* bc_buf, size_t bc_nvec, int bc_root) {
   SymmEpoch ep(d, blockIdx.x);
   const size_t slot_bytes = nvec * 16;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -139,6 +148,19 @@ __global__ void __launch_bounds__(512) allreduce_sgd_oneshot_kernel(const __grid
 #pragma unroll
       for (int r = 0; r < kSymmMaxWorld; ++r)
         if (r < d.world) st_vec_sys(d.peer[r] + off, v);
+    }
+  }
+  const size_t bc_off = stage_off + static_cast<size_t>(d.world) * slot_bytes;
+  if (bc_nvec && d.rank == bc_root) {
+    for (size_t i = first; i < bc_nvec; i += stride) {
+      uint4 v = ld_vec(bc_buf + i);
+      if constexpr (MC) {
+        mc_st_vec(d.mc + bc_off + i * 16, v);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kSymmMaxWorld; ++r)
+          if (r < d.world) st_vec_sys(d.peer[r] + bc_off + i * 16, v);
+      }
     }
   }
   const float lr = lr_dev ? *lr_dev : lr_host;
@@ -166,6 +188,10 @@ __global__ void __launch_bounds__(512) allreduce_sgd_oneshot_kernel(const __grid
     }
     p.x -= lr * g.x; p.y -= lr * g.y; p.z -= lr * g.z; p.w -= lr * g.w;
     param[i] = p;
+  }
+  if (bc_nvec && d.rank != bc_root) {
+    const char* src = d.peer[d.rank] + bc_off;
+    for (size_t i = first; i < bc_nvec; i += stride) st_vec(bc_buf + i, ld_vec_nc(src + i * 16));
   }
   ep.commit(d, blockIdx.x);
 }
@@ -326,20 +352,24 @@ void launch_allreduce_oneshot_push(const SymmDev& d, const void* in, void* out, 
 void launch_allreduce_sgd_oneshot(const SymmDev& d, float* grad, float* param, float* momentum_buf, size_t stage_off,
                                   size_t count, float scale, const float* lr_dev, float lr, float momentum, float dampening,
                                   float weight_decay, bool nesterov, bool first_step, bool use_mc, SymmLaunchCfg cfg,
-                                  cudaStream_t s) {
+                                  cudaStream_t s, void* bcast_buf, size_t bcast_bytes, int bcast_root) {
   if (count % 4 != 0) throw std::invalid_argument("allreduce_sgd: element count must be a multiple of 4");
+  if (bcast_bytes % 16 != 0) throw std::invalid_argument("allreduce_sgd: broadcast payload must be a multiple of 16 bytes");
   const size_t nvec = count / 4;
   if (nvec == 0) return;
   const int threads = cfg.threads ? cfg.threads : 256;
   const int blocks = std::min(cfg.blocks ? cfg.blocks : auto_blocks(nvec, threads, 64), kSymmMaxBlocks);
+  const size_t bc_nvec = bcast_buf ? bcast_bytes / 16 : 0;
   if (use_mc)
     allreduce_sgd_oneshot_kernel<true><<<blocks, threads, 0, s>>>(d, reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(param),
                                                                   reinterpret_cast<float4*>(momentum_buf), stage_off, nvec, scale, lr_dev, lr,
-                                                                  momentum, dampening, weight_decay, nesterov, first_step);
+                                                                  momentum, dampening, weight_decay, nesterov, first_step,
+                                                                  static_cast<uint4*>(bcast_buf), bc_nvec, bcast_root);
   else
     allreduce_sgd_oneshot_kernel<false><<<blocks, threads, 0, s>>>(d, reinterpret_cast<float4*>(grad), reinterpret_cast<float4*>(param),
                                                                    reinterpret_cast<float4*>(momentum_buf), stage_off, nvec, scale, lr_dev, lr,
-                                                                   momentum, dampening, weight_decay, nesterov, first_step);
+                                                                   momentum, dampening, weight_decay, nesterov, first_step,
+                                                                   static_cast<uint4*>(bcast_buf), bc_nvec, bcast_root);
   check_launch("allreduce_sgd_oneshot");
 }
 

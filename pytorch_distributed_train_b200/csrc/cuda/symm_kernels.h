@@ -47,10 +47,12 @@ void launch_barrier(const SymmDev& d, cudaStream_t s);
 
 // Fused: mean-allreduce of a flat fp32 gradient vector (one-shot push) + SGD update of the flat
 // fp32 parameter vector with the same layout:  g <- mean_r(g_r);  p <- p - lr * (g [+ wd*p]).
-// The grad allreduce and the optimizer step of a small model in ONE launch.
+// The grad allreduce and the optimizer step of a small model in ONE launch.  Optional rider: `bcast_bytes` of
+// `bcast_buf` (a local pointer, same meaning on every rank) are replaced by `bcast_root`'s contents, staged behind
+// the world gradient slots (staging must hold world × count × 4 + bcast_bytes).
 void launch_allreduce_sgd_oneshot(const SymmDev& d, float* grad, float* param, float* momentum_buf, size_t stage_off,
                                   size_t count, float scale, const float* lr_dev, float lr, float momentum, float dampening,
                                   float weight_decay, bool nesterov, bool first_step, bool use_mc, SymmLaunchCfg cfg,
-                                  cudaStream_t s);
+                                  cudaStream_t s, void* bcast_buf = nullptr, size_t bcast_bytes = 0, int bcast_root = 0);
 
 }  // namespace pdt

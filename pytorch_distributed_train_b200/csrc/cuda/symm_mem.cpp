@@ -328,8 +328,33 @@ void* SymmetricHeap::alloc(size_t nbytes, size_t align) {
 }
 
 void SymmetricHeap::free(void* p) {
+  // Deleters run whenever Python drops the last reference — a moment that differs between ranks (refcounts, cyclic GC).
+  // The block is only *parked* here; it returns to the allocator at the next collective point (SymmComm::alloc_flat),
+  // where the ranks agree on the set of blocks everybody has released, so the first-fit state stays identical on all
+  // ranks and never recycles memory a comm-stream kernel may still be using.
   std::lock_guard<std::mutex> g(mu_);
   size_t off = static_cast<char*>(p) - peer_base_[rank_];
+  if (used_.find(off) == used_.end()) return;
+  if (world_ == 1) {
+    release_locked(off);
+    return;
+  }
+  pending_.insert(off);
+}
+
+std::vector<size_t> SymmetricHeap::pending_frees() const {
+  std::lock_guard<std::mutex> g(mu_);
+  return std::vector<size_t>(pending_.begin(), pending_.end());
+}
+
+void SymmetricHeap::apply_frees(const std::vector<size_t>& offsets) {
+  std::lock_guard<std::mutex> g(mu_);
+  for (size_t off : offsets) {
+    if (pending_.erase(off)) release_locked(off);
+  }
+}
+
+void SymmetricHeap::release_locked(size_t off) {
   auto it = used_.find(off);
   if (it == used_.end()) return;
   size_t sz = it->second;

@@ -17,6 +17,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -52,10 +53,13 @@ class SymmetricHeap {
   int next_parity(int channel) { return parity_[channel]++ & 1; }
   int peek_parity(int channel) const { return parity_[channel] & 1; }
 
-  // User area. Offsets are identical across ranks as long as every rank performs the same
-  // sequence of alloc/free calls (DDP construction is deterministic).
+  // User area.  Offsets are identical across ranks because every rank performs the same sequence of alloc calls and
+  // frees are applied only at collective points: free() parks the block; SymmComm::alloc_flat exchanges the parked
+  // sets and releases exactly the blocks every rank has dropped (pending_frees / apply_frees).
   void* alloc(size_t nbytes, size_t align = 256);
   void free(void* p);
+  std::vector<size_t> pending_frees() const;
+  void apply_frees(const std::vector<size_t>& offsets);
   bool contains(const void* p, size_t nbytes) const;
   size_t offset_of(const void* p) const { return static_cast<const char*>(p) - peer_base_[rank_]; }
   size_t user_bytes_in_use() const;
@@ -92,6 +96,8 @@ class SymmetricHeap {
   mutable std::mutex mu_;
   std::map<size_t, size_t> free_;    // offset -> size
   std::map<size_t, size_t> used_;    // offset -> size
+  std::set<size_t> pending_;         // parked frees (offsets), released at the next collective alloc
+  void release_locked(size_t off);
 
   // driver handles (VMM path)
   std::vector<unsigned long long> handles_;

@@ -26,9 +26,6 @@ bool same_view(const at::Tensor& a, const at::Tensor& b) {
          a.strides() == b.strides() && a.scalar_type() == b.scalar_type();
 }
 
-double us_between(std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-  return std::chrono::duration<double, std::micro>(b - a).count();
-}
 }  // namespace
 
 Reducer::Reducer(std::vector<at::Tensor> params, std::vector<std::vector<int64_t>> bucket_indices,
@@ -114,6 +111,7 @@ void Reducer::build_buckets(const std::vector<std::vector<int64_t>>& bucket_indi
       }
       bk.views.push_back(std::move(v));
     }
+    plan_chunks(bk);
     fresh.push_back(std::move(bk));
   }
   for (size_t i = 0; i < seen.size(); ++i) TORCH_CHECK(seen[i], "Reducer: parameter ", i, " is in no bucket");
@@ -139,6 +137,86 @@ void Reducer::build_buckets(const std::vector<std::vector<int64_t>>& bucket_indi
   }
 }
 
+void Reducer::plan_chunks(Bucket& bk) const {
+  // Contiguous slot ranges in bucket order (= grad-ready order after the rebuild).  A chunk closes once it holds at
+  // least `target` bytes; the remainder forms the last chunk.  Slot offsets are 16-byte aligned, so are the ranges.
+  bk.chunks.clear();
+  bk.slot_chunk.assign(bk.params.size(), 0);
+  const int64_t esize = static_cast<int64_t>(bk.flat.element_size());
+  const int64_t total = bk.flat.numel();
+  const int64_t nmax = (has_comm_hook_ || max_chunks_ < 1) ? 1 : max_chunks_;
+  const int64_t target = std::max<int64_t>(min_chunk_bytes_, (total * esize + nmax - 1) / nmax);
+  Chunk cur;
+  cur.first_slot = 0;
+  cur.off = 0;
+  for (size_t s = 0; s < bk.params.size(); ++s) {
+    const int64_t end = (s + 1 < bk.params.size()) ? bk.offsets[s + 1] : total;
+    const bool last_slot = (s + 1 == bk.params.size());
+    const bool room = static_cast<int64_t>(bk.chunks.size()) + 1 < nmax;
+    if (last_slot || (room && (end - cur.off) * esize >= target)) {
+      cur.end_slot = s + 1;
+      cur.len = end - cur.off;
+      for (size_t q = cur.first_slot; q < cur.end_slot; ++q) bk.slot_chunk[q] = bk.chunks.size();
+      bk.chunks.push_back(cur);
+      cur = Chunk();
+      cur.first_slot = s + 1;
+      cur.off = end;
+    }
+  }
+}
+
+void Reducer::set_chunking(int64_t min_chunk_bytes, int64_t max_chunks) {
+  std::lock_guard<std::mutex> g(mu_);
+  TORCH_CHECK(!expect_hooks_, "set_chunking must not run between forward and backward");
+  min_chunk_bytes_ = std::max<int64_t>(min_chunk_bytes, 16);
+  max_chunks_ = std::max<int64_t>(max_chunks, 1);
+  for (auto& bk : buckets_) plan_chunks(bk);
+}
+
+void Reducer::set_fused_sgd(at::Tensor param_flat, at::Tensor momentum_flat, FusedSgd hyper, at::Tensor bcast, int64_t bcast_root) {
+  std::lock_guard<std::mutex> g(mu_);
+  TORCH_CHECK(!expect_hooks_, "set_fused_sgd must not run between forward and backward");
+  if (!param_flat.defined()) {
+    fused_param_ = at::Tensor();
+    fused_momentum_ = at::Tensor();
+    fused_bcast_ = at::Tensor();
+    return;
+  }
+  TORCH_CHECK(buckets_.size() == 1 && !has_comm_hook_ && !find_unused_, "fused optimizer needs a single bucket, no comm hook, no unused-parameter search");
+  TORCH_CHECK(param_flat.numel() == buckets_[0].flat.numel() && param_flat.scalar_type() == buckets_[0].flat.scalar_type() &&
+                  param_flat.is_contiguous(), "fused optimizer: the flat parameter vector must mirror the bucket");
+  TORCH_CHECK(hyper.momentum == 0 || (momentum_flat.defined() && momentum_flat.numel() == param_flat.numel()),
+              "fused optimizer: momentum needs a flat buffer shaped like the bucket");
+  fused_param_ = std::move(param_flat);
+  fused_momentum_ = std::move(momentum_flat);
+  fused_hyper_ = std::move(hyper);
+  fused_bcast_ = std::move(bcast);
+  fused_bcast_root_ = static_cast<int>(bcast_root);
+}
+
+void Reducer::resolve_timings() {
+  // fold every iteration whose marks the device has passed into the statistics (never blocks)
+  while (!unresolved_.empty()) {
+    Marks& m = unresolved_.front();
+    if (!(m.after_wait && m.after_wait->ready())) break;
+    if (m.fwd_start && m.bwd_start) stats_.forward_us = m.bwd_start->us_since(*m.fwd_start);
+    if (m.bwd_start && m.before_wait) stats_.backward_compute_us = m.before_wait->us_since(*m.bwd_start);
+    if (m.first_ready && m.comm_end && m.comm_end->ready()) stats_.backward_comm_us = m.comm_end->us_since(*m.first_ready);
+    if (m.before_wait) stats_.backward_comm_exposed_us = m.after_wait->us_since(*m.before_wait);
+    if (m.bwd_start) stats_.backward_total_us = m.after_wait->us_since(*m.bwd_start);
+    constexpr int64_t kStatsWarmup = 10;
+    if (m.iteration > kStatsWarmup) {
+      const double n = static_cast<double>(++stats_.timed_iterations);
+      stats_.avg_forward_us += (stats_.forward_us - stats_.avg_forward_us) / n;
+      stats_.avg_backward_compute_us += (stats_.backward_compute_us - stats_.avg_backward_compute_us) / n;
+      stats_.avg_backward_comm_us += (stats_.backward_comm_us - stats_.avg_backward_comm_us) / n;
+      stats_.avg_backward_comm_exposed_us += (stats_.backward_comm_exposed_us - stats_.avg_backward_comm_exposed_us) / n;
+    }
+    unresolved_.pop_front();
+  }
+  while (unresolved_.size() > 16) unresolved_.pop_front();
+}
+
 void Reducer::prepare_for_forward() {
   std::lock_guard<std::mutex> g(mu_);
   // A synchronised backward that started (some hook fired) but never reached its last bucket means some parameter
@@ -158,12 +236,15 @@ void Reducer::prepare_for_forward() {
                 "sure all `forward` outputs participate in calculating loss.");
   }
   ++stats_.num_iterations;
-  t_forward_start_ = HClock::now();
+  resolve_timings();
+  timing_this_iter_ = !comm_->capturing();
+  cur_ = Marks();
+  cur_.iteration = stats_.num_iterations;
+  if (timing_this_iter_) cur_.fwd_start = comm_->stamp();
 }
 
 void Reducer::prepare_for_backward(const std::vector<at::Tensor>& outputs) {
   std::lock_guard<std::mutex> g(mu_);
-  stats_.forward_us = us_between(t_forward_start_, HClock::now());
   expect_hooks_ = require_sync_;
   callback_queued_ = false;
   saw_first_hook_ = false;
@@ -178,6 +259,11 @@ void Reducer::prepare_for_backward(const std::vector<at::Tensor>& outputs) {
     bk.work.reset();
     bk.py_future = py::object();
     bk.hook_result = at::Tensor();
+    bk.next_chunk = 0;
+    for (auto& c : bk.chunks) {
+      c.pending = c.end_slot - c.first_slot;
+      c.work.reset();
+    }
   }
   if (expect_hooks_ && find_unused_ && !outputs.empty()) search_unused(outputs);
 }
@@ -216,6 +302,7 @@ void Reducer::search_unused(const std::vector<at::Tensor>& outputs) {
     buckets_[l.bucket].views[l.slot].zero_();
     ready_[i] = 1;
     --buckets_[l.bucket].pending;
+    --buckets_[l.bucket].chunks[buckets_[l.bucket].slot_chunk[l.slot]].pending;
   }
   // a bucket made entirely of unused params is launched by the first real hook (keeps the
   // collective inside backward and in bucket order)
@@ -226,7 +313,7 @@ void Reducer::autograd_hook(size_t index) {
   if (!expect_hooks_) return;  // no_sync(), or a backward that was not preceded by our forward
   if (!saw_first_hook_) {
     saw_first_hook_ = true;
-    t_backward_start_ = HClock::now();
+    if (timing_this_iter_) cur_.bwd_start = comm_->stamp();
   }
   TORCH_CHECK(!ready_[index] || static_graph_,
               "pdt Reducer: parameter ", index,
@@ -255,12 +342,27 @@ void Reducer::mark_variable_ready(size_t index) {
   }
   TORCH_CHECK(bk.pending > 0, "pdt Reducer: bucket bookkeeping underflow");
   --bk.pending;
+  --bk.chunks[bk.slot_chunk[l.slot]].pending;
   launch_ready_buckets();
 }
 
 void Reducer::launch_ready_buckets() {
-  while (next_bucket_ < buckets_.size() && buckets_[next_bucket_].pending == 0) {
-    launch_bucket(next_bucket_);
+  // strictly in (bucket, chunk) order — the same order on every rank
+  while (next_bucket_ < buckets_.size()) {
+    Bucket& bk = buckets_[next_bucket_];
+    const bool whole = has_comm_hook_ || defer_comm_;  // a hook / the optimizer consumes whole buckets
+    if (whole) {
+      if (bk.pending != 0) break;
+      launch_bucket(next_bucket_);
+    } else {
+      while (bk.next_chunk < bk.chunks.size() && bk.chunks[bk.next_chunk].pending == 0) {
+        launch_chunk(next_bucket_, bk.next_chunk);
+        ++bk.next_chunk;
+      }
+      if (bk.next_chunk < bk.chunks.size()) break;
+      bk.launched = true;
+      ++stats_.num_buckets_reduced;
+    }
     ++next_bucket_;
   }
   if (next_bucket_ == buckets_.size() && !callback_queued_) {
@@ -269,11 +371,25 @@ void Reducer::launch_ready_buckets() {
   }
 }
 
+void Reducer::launch_chunk(size_t b, size_t c) {
+  Bucket& bk = buckets_[b];
+  Chunk& ch = bk.chunks[c];
+  if (timing_this_iter_ && !cur_.first_ready) cur_.first_ready = comm_->stamp();
+  at::Tensor piece = (ch.off == 0 && ch.len == bk.flat.numel()) ? bk.flat : bk.flat.narrow(0, ch.off, ch.len);
+  if (fused_param_.defined()) {
+    const bool last = (b + 1 == buckets_.size()) && (c + 1 == bk.chunks.size());
+    at::Tensor mom = fused_momentum_.defined() ? fused_momentum_.narrow(0, ch.off, ch.len) : at::Tensor();
+    ch.work = comm_->allreduce_sgd(piece, fused_param_.narrow(0, ch.off, ch.len), mom, fused_hyper_,
+                                   last ? fused_bcast_ : at::Tensor(), fused_bcast_root_);
+  } else {
+    ch.work = comm_->allreduce(piece, ReduceOp::SUM, postscale_);
+  }
+  if (timing_this_iter_) cur_.comm_end = comm_->stamp(/*on_comm_stream=*/true);
+}
+
 void Reducer::launch_bucket(size_t b) {
   Bucket& bk = buckets_[b];
-  auto now = HClock::now();
-  if (b == 0) t_first_launch_ = now;
-  t_last_launch_ = now;
+  if (timing_this_iter_ && !cur_.first_ready) cur_.first_ready = comm_->stamp();
   bk.launched = true;
   ++stats_.num_buckets_reduced;
   if (has_comm_hook_) {
@@ -290,13 +406,15 @@ void Reducer::launch_bucket(size_t b) {
   } else if (!defer_comm_) {
     bk.work = comm_->allreduce(bk.flat, ReduceOp::SUM, postscale_);
   }
+  if (timing_this_iter_) cur_.comm_end = comm_->stamp(/*on_comm_stream=*/true);
 }
 
 void Reducer::finalize_backward() {
   std::lock_guard<std::mutex> g(mu_);
   if (!expect_hooks_) return;
   expect_hooks_ = false;
-  auto t0 = HClock::now();
+  if (timing_this_iter_) cur_.before_wait = comm_->stamp();
+  int64_t launched_chunks = 0;
   for (size_t b = 0; b < buckets_.size(); ++b) {
     Bucket& bk = buckets_[b];
     TORCH_CHECK(bk.launched, "pdt Reducer: bucket ", b, " was never launched");
@@ -312,9 +430,20 @@ void Reducer::finalize_backward() {
     } else if (bk.work) {
       bk.work->wait();
       bk.work.reset();
+      ++launched_chunks;
     }
+    for (auto& c : bk.chunks)
+      if (c.work) {
+        c.work->wait();   // CUDA: the compute stream waits for the comm stream; never blocks the host
+        c.work.reset();
+        ++launched_chunks;
+      }
   }
-  auto t1 = HClock::now();
+  stats_.reduce_chunks = launched_chunks;
+  if (timing_this_iter_) {
+    cur_.after_wait = comm_->stamp();
+    unresolved_.push_back(cur_);
+  }
   // globally-unused detection: a parameter unused on every rank keeps grad=None
   std::vector<char> globally_unused(params_.size(), 0);
   bool any_local_unused = false;
@@ -342,21 +471,6 @@ void Reducer::finalize_backward() {
     } else {
       if (!grad.defined()) grad = at::empty_like(params_[i]);
       if (!same_view(grad, view)) grad.copy_(view);
-    }
-  }
-  auto t2 = HClock::now();
-  if (saw_first_hook_) {
-    stats_.backward_total_us = us_between(t_backward_start_, t2);
-    stats_.backward_compute_us = us_between(t_backward_start_, t_last_launch_);
-    stats_.backward_comm_us = us_between(t_first_launch_, t1);
-    stats_.backward_comm_exposed_us = us_between(t0, t1);
-    constexpr int64_t kStatsWarmup = 10;
-    if (stats_.num_iterations > kStatsWarmup) {
-      const double n = static_cast<double>(++stats_.timed_iterations);
-      stats_.avg_forward_us += (stats_.forward_us - stats_.avg_forward_us) / n;
-      stats_.avg_backward_compute_us += (stats_.backward_compute_us - stats_.avg_backward_compute_us) / n;
-      stats_.avg_backward_comm_us += (stats_.backward_comm_us - stats_.avg_backward_comm_us) / n;
-      stats_.avg_backward_comm_exposed_us += (stats_.backward_comm_exposed_us - stats_.avg_backward_comm_exposed_us) / n;
     }
   }
   stats_.grad_ready_order = ready_order_;
@@ -399,6 +513,7 @@ void Reducer::register_comm_hook(py::object hook) {
 
 ReducerStats Reducer::stats() const {
   std::lock_guard<std::mutex> g(mu_);
+  const_cast<Reducer*>(this)->resolve_timings();
   ReducerStats s = stats_;
   if (s.grad_ready_order.empty()) s.grad_ready_order = prev_ready_order_;
   return s;

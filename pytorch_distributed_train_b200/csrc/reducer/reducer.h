@@ -16,6 +16,7 @@
 #include <torch/csrc/autograd/function.h>
 
 #include <chrono>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <optional>
@@ -45,9 +46,11 @@ struct ReducerStats {
   std::vector<int64_t> bucket_sizes_bytes;
   std::vector<int64_t> grad_ready_order;  // previous iteration
   std::vector<std::vector<int64_t>> bucket_indices;
-  // host-side wall times of the last sampled iteration, microseconds
+  // DEVICE times of the last resolved iteration, microseconds: event marks on the compute / comm streams for CUDA
+  // backends (host clock for the CPU backend).  Iterations recorded into a CUDA graph are not timed.
   double forward_us = 0, backward_compute_us = 0, backward_comm_us = 0, backward_total_us = 0;
-  double backward_comm_exposed_us = 0;    // time finalize spent waiting on collectives
+  double backward_comm_exposed_us = 0;    // how long the compute stream stalled at the end of backward waiting for the reduction
+  int64_t reduce_chunks = 0;              // collectives launched per synchronised backward (sub-bucket chunks)
   // running means over the synchronised iterations after the first kStatsWarmup (the reference's logger samples
   // the same quantities every 100 iterations after the first 10, hdr:reducer.hpp:33,166-170)
   int64_t timed_iterations = 0;
@@ -92,10 +95,28 @@ class Reducer {
   // backward, but no collective is launched (a fused allreduce+update kernel consumes the flat buckets).
   void set_defer_comm(bool on) { defer_comm_ = on; }
   bool defer_comm() const { return defer_comm_; }
+  // Sub-bucket overlap: a bucket is reduced in up to `max_chunks` contiguous pieces of at least
+  // `min_chunk_bytes`, each launched from the autograd hook as soon as its last gradient is ready, so the transfer
+  // of early layers' gradients overlaps the rest of backward even when the whole model fits one bucket.
+  void set_chunking(int64_t min_chunk_bytes, int64_t max_chunks);
+  // Optimizer fused into the reduction: every chunk is reduced AND applied (Comm::allreduce_sgd) from the hook; the
+  // last chunk also carries the module-buffer broadcast.  `param_flat` / `momentum_flat` mirror bucket 0 element
+  // for element.  Requires a single bucket and no comm hook.  Pass an undefined param_flat to switch it off.
+  void set_fused_sgd(at::Tensor param_flat, at::Tensor momentum_flat, FusedSgd hyper, at::Tensor bcast, int64_t bcast_root);
+  bool fused_sgd() const { return fused_param_.defined(); }
 
  private:
+  struct Chunk {
+    size_t first_slot = 0, end_slot = 0;  // slots [first, end) of the bucket
+    int64_t off = 0, len = 0;             // element range of bucket.flat (16-byte aligned on both ends)
+    size_t pending = 0;
+    std::shared_ptr<CommWork> work;
+  };
   struct Bucket {
     at::Tensor flat;
+    std::vector<Chunk> chunks;
+    std::vector<size_t> slot_chunk;        // slot -> chunk index
+    size_t next_chunk = 0;
     std::vector<int64_t> params;          // global param indices
     std::vector<at::Tensor> views;        // same order as params
     std::vector<int64_t> offsets, lengths;
@@ -112,6 +133,9 @@ class Reducer {
   void mark_variable_ready(size_t index);
   void launch_ready_buckets();
   void launch_bucket(size_t b);
+  void launch_chunk(size_t b, size_t c);
+  void plan_chunks(Bucket& bk) const;
+  void resolve_timings();
   void finalize_backward();
   void search_unused(const std::vector<at::Tensor>& outputs);
 
@@ -138,8 +162,19 @@ class Reducer {
   bool has_comm_hook_ = false;
   mutable std::mutex mu_;
 
-  using HClock = std::chrono::steady_clock;
-  HClock::time_point t_forward_start_, t_backward_start_, t_first_launch_, t_last_launch_;
+  int64_t min_chunk_bytes_ = 32 * 1024, max_chunks_ = 4;
+  at::Tensor fused_param_, fused_momentum_, fused_bcast_;
+  FusedSgd fused_hyper_;
+  int fused_bcast_root_ = 0;
+
+  // device-time marks of one iteration (see ReducerStats); resolved lazily once the device has passed them
+  struct Marks {
+    std::shared_ptr<DeviceStamp> fwd_start, bwd_start, first_ready, comm_end, before_wait, after_wait;
+    int64_t iteration = 0;
+  };
+  Marks cur_;
+  std::deque<Marks> unresolved_;
+  bool timing_this_iter_ = false;
   bool saw_first_hook_ = false;
   ReducerStats stats_;
 };

@@ -9,8 +9,9 @@ B200-first changes (the host must keep a ~20 µs training step fed):
   synthetic datasets do) are sliced with one ``index_select`` per field instead of a Python loop
   over samples plus ``default_collate`` (the reference pays 100 PIL round trips per step here,
   SURVEY §2.2 B16);
-* **pinned ring**: batches are written straight into a small ring of pinned staging buffers
-  (no per-batch ``pin_memory()`` allocation);
+* **pinned batches**: every batch is copied into a fresh pinned tensor from torch's event-tracked caching host
+  allocator (a free-list pop after warm-up), so a consumer that runs ahead of the GPU can never see a batch
+  overwritten under a pending H2D copy;
 * **prefetch thread**: optional background producer (``prefetch=k``) so batch *i+1* is being
   assembled while step *i* runs;
 * :class:`DevicePrefetcher` overlaps the H2D copy of batch *i+1* with compute of batch *i* on a
@@ -63,40 +64,32 @@ def _map_tensors(obj, fn):
     return obj
 
 
-class _PinnedRing:
-    """Ring of pinned staging buffers keyed by (slot, field) — allocated on first use."""
+def _pin_batch(batch):
+    """Copy a batch into *fresh* pinned tensors from torch's caching host allocator.
 
-    def __init__(self, depth: int):
-        self.depth = max(2, depth)
-        self.slots: List[dict] = [dict() for _ in range(self.depth)]
-        self.i = 0
-        self.enabled = torch.cuda.is_available()
+    Fresh, not a private ring: the consumer issues ``.to(device, non_blocking=True)`` (ref: ddp_example.py:83-84) and
+    may run many batches ahead of the GPU (a graph-replayed step is ~0.1 ms).  The caching host allocator records a
+    CUDA event for every non-blocking copy out of a pinned block and recycles the block only after that event has
+    completed, so a batch can never be overwritten while its H2D copy is still pending — and two batches of one
+    ``list(loader)`` never alias.  After warm-up an allocation is a free-list pop (no ``cudaHostAlloc``)."""
+    if not torch.cuda.is_available():
+        return batch
 
-    def stage(self, batch):
-        if not self.enabled:
-            return batch
-        slot = self.slots[self.i % self.depth]
-        self.i += 1
-        counter = [0]
+    def pin(t: torch.Tensor):
+        if t.is_pinned():
+            return t
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t)
+        return buf
 
-        def pin(t: torch.Tensor):
-            k = counter[0]
-            counter[0] += 1
-            buf = slot.get(k)
-            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                slot[k] = buf
-            buf.copy_(t)
-            return buf
-
-        return _map_tensors(batch, pin)
+    return _map_tensors(batch, pin)
 
 
 class DataLoader:
     def __init__(self, dataset, batch_size: Optional[int] = 1, shuffle: bool = False, sampler=None,
                  batch_sampler=None, num_workers: int = 0, collate_fn: Optional[Callable] = None,
                  pin_memory: bool = False, drop_last: bool = False, prefetch: int = 0,
-                 generator: Optional[torch.Generator] = None, pin_ring_depth: int = 4):
+                 generator: Optional[torch.Generator] = None):
         if num_workers != 0:
             # worker *processes* are not needed for tensor-backed datasets; a thread prefetcher is
             # what keeps up with a graph-replayed step. Map the knob instead of failing.
@@ -117,7 +110,6 @@ class DataLoader:
             batch_sampler = BatchSampler(sampler, batch_size, drop_last) if batch_size is not None else None
         self.sampler = sampler
         self.batch_sampler = batch_sampler
-        self._ring = _PinnedRing(max(pin_ring_depth, prefetch + 2)) if pin_memory else None
         self._can_gather = collate_fn is None and hasattr(dataset, "gather")
 
     def __len__(self) -> int:
@@ -129,8 +121,8 @@ class DataLoader:
         else:
             samples = [self.dataset[i] for i in indices]
             batch = (self.collate_fn or default_collate)(samples)
-        if self._ring is not None:
-            batch = self._ring.stage(batch)
+        if self.pin_memory:
+            batch = _pin_batch(batch)
         return batch
 
     def _iter_sync(self) -> Iterator:

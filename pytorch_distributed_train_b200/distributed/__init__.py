@@ -341,9 +341,18 @@ def all_reduce(tensor: torch.Tensor, op=ReduceOp.SUM, group: Optional[ProcessGro
     return _finish(g.comm.allreduce(_contig(tensor, "all_reduce"), op, 1.0), async_op)
 
 
+def _group_rank(g: ProcessGroup, global_rank: int, what: str) -> int:
+    """torch's API takes *global* ranks for src / dst in every rooted and point-to-point op, also on subgroups;
+    the communicators index by rank inside the group."""
+    ranks = list(g.ranks)
+    if global_rank not in ranks:
+        raise ValueError(f"{what}: global rank {global_rank} is not part of the group (ranks {ranks})")
+    return ranks.index(global_rank)
+
+
 def broadcast(tensor: torch.Tensor, src: int, group: Optional[ProcessGroup] = None, async_op: bool = False):
     g = _group(group)
-    root = g.ranks.index(src) if group is not None and src in g.ranks else src
+    root = _group_rank(g, src, "broadcast")
     _precheck(g, "broadcast", [tensor], f"root={root}")
     return _finish(g.comm.broadcast(_contig(tensor, "broadcast"), root), async_op)
 
@@ -382,8 +391,9 @@ def all_gather(tensor_list: List[torch.Tensor], tensor: torch.Tensor, group: Opt
 
 def reduce(tensor: torch.Tensor, dst: int, op=ReduceOp.SUM, group: Optional[ProcessGroup] = None, async_op: bool = False):
     g = _group(group)
-    _precheck(g, "reduce", [tensor], f"{op},dst={dst}")
-    return _finish(g.comm.reduce(_contig(tensor, "reduce"), op, dst), async_op)
+    root = _group_rank(g, dst, "reduce")
+    _precheck(g, "reduce", [tensor], f"{op},dst={root}")
+    return _finish(g.comm.reduce(_contig(tensor, "reduce"), op, root), async_op)
 
 
 def reduce_scatter_tensor(output: torch.Tensor, input: torch.Tensor, op=ReduceOp.SUM,
@@ -396,6 +406,7 @@ def reduce_scatter_tensor(output: torch.Tensor, input: torch.Tensor, op=ReduceOp
 def gather(tensor: torch.Tensor, gather_list: Optional[List[torch.Tensor]] = None, dst: int = 0,
            group: Optional[ProcessGroup] = None):
     g = _group(group)
+    dst = _group_rank(g, dst, "gather")
     out = torch.empty((g.size(),) + tuple(tensor.shape), dtype=tensor.dtype, device=tensor.device) if g.rank() == dst else tensor.new_empty(0)
     g.comm.gather(out.view(-1), _contig(tensor, "gather").view(-1), dst).wait()
     if g.rank() == dst and gather_list is not None:
@@ -406,6 +417,7 @@ def gather(tensor: torch.Tensor, gather_list: Optional[List[torch.Tensor]] = Non
 def scatter(tensor: torch.Tensor, scatter_list: Optional[List[torch.Tensor]] = None, src: int = 0,
             group: Optional[ProcessGroup] = None):
     g = _group(group)
+    src = _group_rank(g, src, "scatter")
     inp = torch.stack(list(scatter_list)).contiguous().view(-1) if g.rank() == src else tensor.new_empty(0)
     g.comm.scatter(_contig(tensor, "scatter").view(-1), inp, src).wait()
 
@@ -417,19 +429,23 @@ def all_to_all_single(output: torch.Tensor, input: torch.Tensor, group: Optional
 
 
 def send(tensor: torch.Tensor, dst: int, group: Optional[ProcessGroup] = None):
-    _group(group).comm.send(_contig(tensor, "send"), dst).wait()
+    g = _group(group)
+    g.comm.send(_contig(tensor, "send"), _group_rank(g, dst, "send")).wait()
 
 
 def recv(tensor: torch.Tensor, src: int, group: Optional[ProcessGroup] = None):
-    _group(group).comm.recv(_contig(tensor, "recv"), src).wait()
+    g = _group(group)
+    g.comm.recv(_contig(tensor, "recv"), _group_rank(g, src, "recv")).wait()
 
 
 def isend(tensor: torch.Tensor, dst: int, group: Optional[ProcessGroup] = None):
-    return _group(group).comm.send(_contig(tensor, "isend"), dst)
+    g = _group(group)
+    return g.comm.send(_contig(tensor, "isend"), _group_rank(g, dst, "isend"))
 
 
 def irecv(tensor: torch.Tensor, src: int, group: Optional[ProcessGroup] = None):
-    return _group(group).comm.recv(_contig(tensor, "irecv"), src)
+    g = _group(group)
+    return g.comm.recv(_contig(tensor, "irecv"), _group_rank(g, src, "irecv"))
 
 
 def barrier(group: Optional[ProcessGroup] = None, async_op: bool = False):
@@ -496,6 +512,7 @@ def broadcast_object(obj, src: int = 0, group: Optional[ProcessGroup] = None):
     import pickle
 
     g = _group(group)
+    src = _group_rank(g, src, "broadcast_object")
     key = _object_key(g, "bco")
     if g.rank() == src:
         g.store.set(key, pickle.dumps(obj))
@@ -508,7 +525,8 @@ def broadcast_object(obj, src: int = 0, group: Optional[ProcessGroup] = None):
 
 def broadcast_object_list(object_list: list, src: int = 0, group: Optional[ProcessGroup] = None) -> None:
     """torch signature: ``object_list`` is overwritten in place with ``src``'s list (same length on every rank)."""
-    got = broadcast_object(list(object_list) if _group(group).rank() == src else None, src, group)
+    g0 = _group(group)
+    got = broadcast_object(list(object_list) if g0.rank() == _group_rank(g0, src, "broadcast_object_list") else None, src, group)
     if len(got) != len(object_list):
         raise ValueError(f"broadcast_object_list: rank {_group(group).rank()} passed {len(object_list)} slots, src sent {len(got)}")
     object_list[:] = got
@@ -516,6 +534,7 @@ def broadcast_object_list(object_list: list, src: int = 0, group: Optional[Proce
 
 def gather_object(obj, object_gather_list: Optional[list] = None, dst: int = 0, group: Optional[ProcessGroup] = None) -> None:
     g = _group(group)
+    dst = _group_rank(g, dst, "gather_object")
     if g.rank() == dst and (object_gather_list is None or len(object_gather_list) != g.size()):
         raise ValueError("gather_object: the destination rank must pass a list with world_size slots")
     allobjs = all_gather_object(obj, g)
@@ -531,6 +550,7 @@ def scatter_object_list(scatter_object_output_list: list, scatter_object_input_l
     g = _group(group)
     if not scatter_object_output_list:
         raise ValueError("scatter_object_list: the output list needs at least one slot")
+    src = _group_rank(g, src, "scatter_object_list")
     key = _object_key(g, "sco")
     keys = [f"{key}/{r}" for r in range(g.size())]
     if g.rank() == src:

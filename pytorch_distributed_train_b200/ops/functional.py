@@ -21,10 +21,27 @@ from .. import _C
 from .. import distributed as dist
 
 
+_claim_epoch = 0   # bumped by DistributedDataParallel.forward: one direct write per parameter per iteration
+
+
+def begin_iteration() -> None:
+    """Called by DDP at every training forward: bucket slots may be claimed (once each) by the coming backward."""
+    global _claim_epoch
+    _claim_epoch += 1
+
+
 def _grad_dst(param: Optional[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
-    """Where a parameter gradient should be written: the DDP bucket slot when that is safe."""
+    """Where a parameter gradient should be written: the DDP bucket slot when that is safe.
+
+    Safe = ``.grad`` is None, DDP has published a view for this parameter, and the slot has not been handed out
+    yet in this iteration.  A parameter used twice in one forward (tied weights, siamese towers, recurrent use) gets
+    the slot for its first backward call only; later calls write a temporary that autograd *adds* into the slot,
+    so the result is dW1 + dW2 rather than two aliases of one buffer.  The same guard makes ``torch.autograd.grad``
+    / a backward outside ``DDP.forward`` fall back to temporaries instead of clobbering live bucket memory."""
     view = getattr(param, "_pdt_grad_view", None) if param is not None else None
-    if view is not None and param.grad is None and view.shape == like.shape and view.is_contiguous():
+    if (view is not None and param.grad is None and view.shape == like.shape and view.is_contiguous()
+            and getattr(param, "_pdt_grad_claim", -1) != _claim_epoch):
+        param._pdt_grad_claim = _claim_epoch
         return view.detach().view(like.shape)  # fresh alias: autograd may adopt it without copying
     return torch.empty_like(like, memory_format=torch.contiguous_format)
 

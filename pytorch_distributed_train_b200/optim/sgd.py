@@ -63,19 +63,22 @@ class SGD(torch.optim.Optimizer):
                 ent[0].fill_(float(group["lr"]))
                 ent[1] = float(group["lr"])
 
-    # ---- DDP fusion: gradient mean-allreduce + update in one kernel ------------------------------------
+    # ---- DDP fusion: the update rides on the gradient reduction ----------------------------------------
     def fuse_with_ddp(self, ddp) -> "SGD":
-        """Let ``step()`` perform the gradient allreduce itself, fused with the parameter update.
+        """Fuse this optimizer into DDP's gradient reduction.
 
-        The reference's step is ``backward`` (→ NCCL allreduce of the bucket) followed by a foreach
-        SGD kernel (ddp_example.py:89-92).  When the wrapped model's gradients fit one bucket on the
-        NVLink backend, ours turns the pair into ONE kernel: every rank pushes its flat gradient into
-        its peers' staging slots, crosses one device-side barrier, folds the ``world`` slots in rank
-        order and applies the update to the (bucket-mirroring) flat parameter arena.  The reducer still
-        fills the bucket and re-points ``.grad`` but launches no collective of its own.
-        Activation happens on the first ``step()`` after the reducer has settled its bucket layout;
-        until then (and whenever the preconditions do not hold) the ordinary two-kernel path runs.
-        On backends without the fused kernel the same protocol runs as allreduce + update."""
+        The reference's step is ``backward`` (→ NCCL allreduce of the bucket, launched after the last gradient)
+        followed by a foreach SGD kernel (ddp_example.py:89-92).  Fused, every *reduce chunk* the reducer launches
+        from the autograd hook — a contiguous piece of the bucket in grad-ready order — is ONE kernel on the comm
+        stream that pushes the chunk into the peers' staging slots, crosses one device-side barrier, folds the
+        ``world`` slots in rank order and applies the SGD update to the parameters the chunk belongs to
+        (``Comm.allreduce_sgd``), so the reduction *and* the update of the late layers overlap the backward pass
+        of the early ones.  The last chunk also carries DDP's per-step BatchNorm-buffer broadcast.
+        ``step()`` then only has bookkeeping left; ``.grad`` reads as the averaged gradient, as in the reference.
+
+        Contract: between ``backward()`` and ``step()`` the parameters are already updated — gradient clipping or a
+        skipped ``step()`` are not expressible in this mode.  Takes effect on the first ``step()`` after the reducer
+        has settled its bucket layout; until then (and whenever the preconditions fail) the ordinary path runs."""
         self._ddp = ddp
         return self
 
@@ -91,6 +94,10 @@ class SGD(torch.optim.Optimizer):
             return
         if any(p.dtype != torch.float32 for p in mine):
             return
+        if group["momentum"] != 0:
+            missing = [self.state[p].get("momentum_buffer") is None for p in ddp._params]
+            if any(missing) and not all(missing) and group["dampening"] != 0:
+                return  # "first step" is a per-parameter rule; wait until every parameter has its buffer
         if not ddp.enable_optimizer_fusion():
             return
         if group["momentum"] != 0:
@@ -103,38 +110,37 @@ class SGD(torch.optim.Optimizer):
                     st["momentum_buffer"] = view
             self._flat_momentum = flat
         self._fused_active = True
+        ddp._rearm_fused_optimizer = self._arm_fused
+        self._arm_fused()
+
+    def _arm_fused(self) -> None:
+        """(Re-)install the update the reducer applies with every reduce chunk of the *next* backward."""
+        ddp, group = self._ddp, self.param_groups[0]
+        first = False
+        if group["momentum"] != 0:
+            # zero buffer + "not first" is exact when dampening == 0 (b = μ·0 + g); a uniform first step sets the flag
+            first = all(self.state[p].get("momentum_buffer") is None for p in ddp._params)
+        self._armed = (float(group["lr"]), bool(first))
+        ddp.reducer.set_fused_sgd(ddp.param_arena, self._flat_momentum, lr=float(group["lr"]),
+                                  lr_tensor=self._lr_tensor(0, group, ddp.param_arena.device), momentum=float(group["momentum"]),
+                                  dampening=float(group["dampening"]), weight_decay=float(group["weight_decay"]),
+                                  nesterov=bool(group["nesterov"]), first_step=bool(first), bcast=ddp.tail_broadcast_buffer(),
+                                  bcast_root=0)
 
     def _fused_step(self) -> bool:
         ddp = self._ddp
-        if not (self._fused_active and ddp.reducer.defer_comm and ddp.require_backward_grad_sync):
+        if not (self._fused_active and ddp.reducer.fused_sgd):
             return False
+        if not ddp.require_backward_grad_sync:
+            return True   # no_sync(): gradients accumulate locally; the next synchronised backward reduces and applies them
         group = self.param_groups[0]
-        bucket = ddp.reducer.bucket_buffers()[0]
-        arena = ddp.param_arena
-        momentum = group["momentum"]
-        first = False
-        if momentum != 0:
-            first = any(self.state[p].get("momentum_buffer") is None for p in ddp._params)
-        comm = ddp.comm
-        if hasattr(comm, "allreduce_sgd_inline") and bucket.is_cuda:
-            comm.allreduce_sgd_inline(bucket, arena, self._flat_momentum, float(group["lr"]),
-                                      self._lr_tensor(0, group, arena.device), float(momentum), float(group["dampening"]),
-                                      float(group["weight_decay"]), bool(group["nesterov"]), bool(first))
-        else:
-            from ..distributed import ReduceOp
-
-            comm.allreduce(bucket, ReduceOp.SUM, 1.0 / ddp.process_group.size()).wait()
-            g = bucket if group["weight_decay"] == 0 else bucket.add(arena, alpha=group["weight_decay"])
-            if momentum != 0:
-                if first:
-                    self._flat_momentum.copy_(g)
-                else:
-                    self._flat_momentum.mul_(momentum).add_(g, alpha=1 - group["dampening"])
-                g = g.add(self._flat_momentum, alpha=momentum) if group["nesterov"] else self._flat_momentum
-            arena.add_(g, alpha=-group["lr"])
-        if first:
+        # the reduction of this iteration's backward has already applied the update (see fuse_with_ddp)
+        if group["momentum"] != 0:
             for p, off in zip(ddp._params, ddp._param_offsets):
-                self.state[p]["momentum_buffer"] = self._flat_momentum[off:off + p.numel()].view(p.shape)
+                if self.state[p].get("momentum_buffer") is None:
+                    self.state[p]["momentum_buffer"] = self._flat_momentum[off:off + p.numel()].view(p.shape)
+        if self._armed != (float(group["lr"]), False):
+            self._arm_fused()   # first-step flag drops after one update; a changed learning rate is picked up
         return True
 
     def load_state_dict(self, state_dict) -> None:
@@ -193,18 +199,25 @@ class SGD(torch.optim.Optimizer):
                     p.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous() and g.dtype == torch.float32
                     for p, g in zip(params, grads))
             if use_fused:
-                first = False
-                mbufs = None
-                if momentum != 0:
-                    first = any(st["momentum_buffer"] is None for st in bufs)
-                    for st, p in zip(bufs, params):
-                        if st["momentum_buffer"] is None:
-                            st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                    mbufs = [st["momentum_buffer"] for st in bufs]
-                ops.sgd_step(params, grads, mbufs, lr=group["lr"], momentum=momentum, dampening=group["dampening"],
-                             weight_decay=group["weight_decay"], nesterov=group["nesterov"],
-                             maximize=group["maximize"], first_step=first,
-                             lr_tensor=self._lr_tensor(gi, group, params[0].device))
+                if momentum == 0:
+                    ops.sgd_step(params, grads, None, lr=group["lr"], momentum=0.0, dampening=group["dampening"],
+                                 weight_decay=group["weight_decay"], nesterov=group["nesterov"], maximize=group["maximize"],
+                                 first_step=False, lr_tensor=self._lr_tensor(gi, group, params[0].device))
+                    continue
+                # "first step" (buf = g, no dampening) is a per-parameter decision, as in torch: parameters that see
+                # their first gradient now go through one launch with first_step=True, the rest through another
+                for want_first in (True, False):
+                    sel = [i for i, st in enumerate(bufs) if (st["momentum_buffer"] is None) == want_first]
+                    if not sel:
+                        continue
+                    ps, gs_ = [params[i] for i in sel], [grads[i] for i in sel]
+                    if want_first:
+                        for i in sel:
+                            bufs[i]["momentum_buffer"] = torch.zeros_like(params[i], memory_format=torch.contiguous_format)
+                    ops.sgd_step(ps, gs_, [bufs[i]["momentum_buffer"] for i in sel], lr=group["lr"], momentum=momentum,
+                                 dampening=group["dampening"], weight_decay=group["weight_decay"], nesterov=group["nesterov"],
+                                 maximize=group["maximize"], first_step=want_first,
+                                 lr_tensor=self._lr_tensor(gi, group, params[0].device))
                 continue
             # reference math through foreach ops (CPU / exotic dtypes)
             gs = [(-g if group["maximize"] else g) for g in grads] if group["maximize"] else list(grads)

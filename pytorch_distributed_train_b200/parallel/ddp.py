@@ -36,6 +36,7 @@ import torch.nn as nn
 
 from .. import _C
 from .. import distributed as dist
+from ..ops.functional import begin_iteration as _begin_iteration
 
 _DEFAULT_FIRST_BUCKET_BYTES = 1024 * 1024
 _BROADCAST_BUCKET_BYTES = 250 * 1024 * 1024
@@ -250,22 +251,20 @@ class DistributedDataParallel(nn.Module):
                     self.buffer_arenas[dtype] = region
 
     def enable_optimizer_fusion(self) -> bool:
-        """Prepare for a fused allreduce+update optimizer step (``optim.SGD.fuse_with_ddp``): once the
-        reducer has settled on a single bucket, re-home the parameters into an arena that mirrors
-        the bucket element for element and stop the reducer from launching its own collective.
-        Returns False (and changes nothing) when the preconditions do not hold."""
-        if getattr(self, "_defer_comm", False):
+        """Prepare for an optimizer fused into the gradient reduction (``optim.SGD.fuse_with_ddp``): once the
+        reducer has settled on a single bucket, re-home the parameters into an arena that mirrors the bucket
+        element for element, so that every reduce chunk launched from the autograd hook can also apply the update
+        to "its" parameters (``Reducer.set_fused_sgd``).  Returns False (and changes nothing) when the
+        preconditions do not hold."""
+        if getattr(self, "_fused_optimizer", False):
             return True
         st = self.reducer.stats()
         if (not st["has_rebuilt_buckets"] or len(st["bucket_indices"]) != 1 or self._comm_hook_registered
-                or self.find_unused_parameters or not self.gradient_as_bucket_view):
+                or self.find_unused_parameters or not self.gradient_as_bucket_view or self._join_active):
             return False
         flat = self.reducer.bucket_buffers()[0]
         views = self.reducer.grad_views()
         if flat.dtype != torch.float32 or any(not v.is_contiguous() for v in views):
-            return False
-        limit = getattr(self.comm, "fused_step_max_bytes", None)
-        if limit is not None and flat.numel() * 4 > limit:
             return False
         offs = [(v.data_ptr() - flat.data_ptr()) // 4 for v in views]
         arena = self.comm.alloc_flat(flat.numel(), torch.float32, self.device)
@@ -276,9 +275,15 @@ class DistributedDataParallel(nn.Module):
                 view.copy_(p.data)
                 p.data = view
         self.param_arena, self._param_offsets = arena, offs
-        self._defer_comm = True
-        self.reducer.set_defer_comm(True)
+        self._fused_optimizer = True
+        # the last reduce chunk of every step carries rank 0's module buffers to everybody (C4 riding on C5): the
+        # separate barrier-synchronised broadcast kernel in front of every forward is no longer needed
+        self._tail_broadcast = bool(self.broadcast_buffers and self.buffer_arena is not None and self.process_group.size() > 1)
         return True
+
+    def tail_broadcast_buffer(self):
+        """The byte arena the fused last chunk broadcasts from rank 0 (None: buffers are synced before forward)."""
+        return self.buffer_arena if getattr(self, "_tail_broadcast", False) else None
 
     def _sync_module_states(self):
         if self.process_group.size() == 1:
@@ -295,7 +300,12 @@ class DistributedDataParallel(nn.Module):
     def syncs_buffers_every_step(self) -> bool:
         """True when every training forward runs a barrier-synchronised buffer broadcast (C4) — which
         also orders consecutive steps across ranks (engine.GraphedTrainStep relies on it)."""
+        if self._buffers_ride_on_reduce():
+            return False
         return bool(self.broadcast_buffers and self._buffers_to_sync and self.process_group.size() > 1)
+
+    def _buffers_ride_on_reduce(self) -> bool:
+        return bool(getattr(self, "_tail_broadcast", False) and self.reducer.fused_sgd and self.require_backward_grad_sync)
 
     def _sync_buffers(self):
         if not self._buffers_to_sync or self.process_group.size() == 1:
@@ -346,9 +356,10 @@ class DistributedDataParallel(nn.Module):
         if rebuilt:
             self.reducer.apply_rebuild(layout)
             self._rebuild_checked = True
-        if getattr(self, "_defer_comm", False):
-            self.reducer.set_defer_comm(True)
         self._publish_grad_views()
+        rearm = getattr(self, "_rearm_fused_optimizer", None)
+        if rearm is not None:
+            rearm()  # the optimizer re-installs its fused update on the new reducer
 
     def _publish_grad_views(self):
         """Let our backward kernels write weight gradients straight into the bucket (ops.functional._grad_dst)."""
@@ -363,8 +374,8 @@ class DistributedDataParallel(nn.Module):
             return
         self._rebuild_checked = True
         g = self.process_group
-        proposal = self.reducer.propose_rebuild() if g.rank() == 0 else None
-        layout = dist.broadcast_object(proposal, 0, g) if g.size() > 1 else proposal  # C6: agree on rank 0's layout
+        proposal = self.reducer.propose_rebuild() if g.rank() == 0 else None  # group rank 0 proposes
+        layout = dist.broadcast_object(proposal, g.ranks[0], g) if g.size() > 1 else proposal  # C6: agree on rank 0's layout
         self.reducer.apply_rebuild(layout)
         self._publish_grad_views()
 
@@ -375,7 +386,7 @@ class DistributedDataParallel(nn.Module):
             self._maybe_rebuild_buckets()
         if self._join_active:
             self._join_notify_active()
-        if self.broadcast_buffers and self.require_forward_param_sync and self.module.training:
+        if self.broadcast_buffers and self.require_forward_param_sync and self.module.training and not self._buffers_ride_on_reduce():
             self._sync_buffers()
         if self.device_ids:
             inputs = _to_device(inputs, self.device)
@@ -386,6 +397,7 @@ class DistributedDataParallel(nn.Module):
         inputs, kwargs = self._pre_forward(inputs, kwargs)
         out = self.module(*inputs, **kwargs)
         if torch.is_grad_enabled():
+            _begin_iteration()  # bucket slots may be written directly, once per parameter, by this iteration's backward
             self.reducer.set_require_sync(self.require_backward_grad_sync)
             self.reducer.prepare_for_backward(_flatten_outputs(out) if self.find_unused_parameters else [])
         return out
@@ -417,6 +429,8 @@ class DistributedDataParallel(nn.Module):
             "num_parameter_tensors": len(self._params), "device_ids": self.device_ids,
             "bucket_cap_bytes": self.bucket_bytes_cap, "static_graph": self.static_graph,
             "params_flattened": self.param_arena is not None,
+            "fused_optimizer": bool(self.reducer.fused_sgd),
+            "buffers_ride_on_reduce": bool(getattr(self, "_tail_broadcast", False) and self.reducer.fused_sgd),
         })
         return s
 
@@ -433,12 +447,15 @@ class DistributedDataParallel(nn.Module):
         distributed.py:1798).  Gradients are divided by the full world size."""
         if not divide_by_initial_world_size:
             raise NotImplementedError("join(divide_by_initial_world_size=False) is not supported")
-        if getattr(self, "_defer_comm", False):
-            # a joined rank shadows the reducer's per-bucket allreduce; with the fused step the collective lives in
-            # optimizer.step(), which a rank without data never calls
-            raise RuntimeError("join() cannot be combined with the fused allreduce+optimizer step (optim.SGD.fuse_with_ddp)")
+        if getattr(self, "_fused_optimizer", False):
+            # a joined rank shadows plain bucket allreduces; the fused chunks also update parameters and carry buffers
+            raise RuntimeError("join() cannot be combined with the optimizer fused into the reduction (optim.SGD.fuse_with_ddp)")
         self._join_active = True
         self._join_iters = 0
+        # A rank that runs out of data cannot take part in the one-time bucket rebuild agreement (C6) of the ranks that
+        # keep training — worse, rank 0 (the proposer) may be the one that stopped.  Every rank enters join() before its
+        # loop, so all of them freeze the bucket layout here and the shadowed allreduces keep matching sizes.
+        self._rebuild_checked = True
         try:
             yield
             # this rank is out of data: mirror the others until everybody is done
