@@ -144,7 +144,7 @@ def verify_ours(pdt, ddp, criterion, dev, rank, world, x, y):
     ours = torch.cat([p.grad.reshape(-1) for p in module.parameters()])
     denom = float(ref_grads.abs().max())
     out["grad_max_rel_err"] = float((ours - ref_grads).abs().max()) / max(denom, 1e-30)
-    out["loss_abs_err"] = abs(float(loss) - float(loss_ref))
+    out["loss_abs_err"] = abs(float(loss.detach()) - float(loss_ref.detach()))
     with torch.no_grad():  # leave no trace: restore BN running statistics, drop the gradients
         for k, v in module.named_buffers():
             v.copy_(bufs[k])
@@ -237,12 +237,15 @@ def run_ours(args):
         edges = sorted({round(n_timed * w / WINDOWS) for w in range(WINDOWS + 1)})
         c0 = _C.kernel_launch_count()
         t0 = time.perf_counter()
+        host_t = [0.0] * (n_timed + 1)
         for i in range(n_timed):
             if i in edges:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
                 marks.append((i, e))
+            host_t[i] = time.perf_counter()
             run_step(n_warm + i)
+        host_t[n_timed] = time.perf_counter()
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         marks.append((n_timed, e))
@@ -250,7 +253,12 @@ def run_ours(args):
         wall_ms = (time.perf_counter() - t0) * 1e3
         pdt.distributed.barrier()
         torch.cuda.synchronize()
-        return marks[0][1].elapsed_time(marks[-1][1]), wall_ms, _C.kernel_launch_count() - c0, window_stats(marks)
+        ws = window_stats(marks)
+        if ws is not None:  # host-side view: the slowest individual steps (index, ms) — loader stalls / GIL hand-offs show up here
+            per = sorted(((host_t[i + 1] - host_t[i]) * 1e3, i) for i in range(n_timed))
+            ws["host_median_ms_per_step"] = per[len(per) // 2][0]
+            ws["host_slowest_steps"] = [(i, round(ms, 3)) for ms, i in per[-3:]]
+        return marks[0][1].elapsed_time(marks[-1][1]), wall_ms, _C.kernel_launch_count() - c0, ws
 
     # ---- device-timed steps, inputs rotate through a device pool larger than L2 ------------------------
     last = {}

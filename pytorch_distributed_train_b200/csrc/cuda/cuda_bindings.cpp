@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "conv_tcgen05.h"
+#include "fused_convnet.h"
 #include "cuda_comm.h"
 #include "cuda_utils.h"
 #include "ops_kernels.h"
@@ -190,6 +191,91 @@ void register_cuda_bindings(py::module_& m) {
     if (tc) launch_conv5x5_wgrad_tcgen05(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
     else launch_conv5x5_wgrad(dy.data_ptr<float>(), x.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), s, scratch(x), cur_stream(x));
   }, py::arg("dy"), py::arg("x"), py::arg("dw"), py::arg("db") = py::none(), py::arg("impl") = "auto");
+
+  // ---- cooperative fused ConvNet layers (fused_convnet.cu): one CTA per image, grid barrier for the batch statistics ----
+  m.def("fused_convnet_supported", [](int64_t B) { return fused_convnet_supported(static_cast<int>(B)); });
+  m.def("convnet_l1_fwd", [](const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> gamma,
+                             c10::optional<at::Tensor> beta, c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
+                             c10::optional<at::Tensor> nbt, double momentum, double eps) {
+    chk(x, "x"); chk(w, "w");
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.numel() % 784 == 0 && w.numel() == 400, "convnet_l1_fwd: x [B,1,28,28] and w [16,1,5,5] expected");
+    const int B = static_cast<int>(x.numel() / 784);
+    TORCH_CHECK(fused_convnet_supported(B), "convnet_l1_fwd: batch ", B, " exceeds one CTA per SM");
+    at::Tensor y = at::empty({B, 28, 28, 16}, x.options());
+    at::Tensor out = at::empty({B, 14, 14, 16}, x.options());
+    at::Tensor saved = at::empty({32}, x.options());
+    long long* nbt_p = nullptr;
+    if (nbt.has_value() && nbt->defined()) { chk(*nbt, "num_batches_tracked", at::kLong); nbt_p = reinterpret_cast<long long*>(nbt->data_ptr<int64_t>()); }
+    ReduceScratch scr = scratch(x);
+    TORCH_CHECK(static_cast<long long>(B) * 512 <= scr.capacity_floats, "fused convnet: reduction scratch too small");
+    launch_convnet_l1_fwd(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), opt_ptr(gamma, "gamma"), opt_ptr(beta, "beta"),
+                          y.data_ptr<float>(), out.data_ptr<float>(), saved.data_ptr<float>(), opt_mut(running_mean, "running_mean"),
+                          opt_mut(running_var, "running_var"), nbt_p, static_cast<float>(momentum), static_cast<float>(eps), B, scr.partials,
+                          GridSync{scr.counter + scr.counters - 2, scr.counter + scr.counters - 1}, cur_stream(x));
+    return py::make_tuple(out, y, saved);
+  });
+  m.def("convnet_l1_bwd", [](const at::Tensor& dp, const at::Tensor& y, const at::Tensor& x, const at::Tensor& saved,
+                             c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta, at::Tensor dgamma, at::Tensor dbeta, at::Tensor dw,
+                             c10::optional<at::Tensor> db) {
+    chk(dp, "dp"); chk(y, "y"); chk(x, "x"); chk(saved, "saved"); chk(dgamma, "dgamma"); chk(dbeta, "dbeta"); chk(dw, "dw");
+    c10::cuda::CUDAGuard g(x.device());
+    const int B = static_cast<int>(y.size(0));
+    TORCH_CHECK(dp.numel() == static_cast<int64_t>(B) * 3136 && x.numel() == static_cast<int64_t>(B) * 784 && dw.numel() == 400 &&
+                    dgamma.numel() == 16 && dbeta.numel() == 16, "convnet_l1_bwd: shape mismatch");
+    ReduceScratch scr = scratch(x);
+    launch_convnet_l1_bwd(dp.data_ptr<float>(), y.data_ptr<float>(), x.data_ptr<float>(), saved.data_ptr<float>(), opt_ptr(gamma, "gamma"),
+                          opt_ptr(beta, "beta"), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), B,
+                          scr.partials, scr.partials + static_cast<size_t>(B) * 64,
+                          GridSync{scr.counter + scr.counters - 2, scr.counter + scr.counters - 1}, cur_stream(x));
+  });
+  m.def("convnet_l2_fwd", [](const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> gamma,
+                             c10::optional<at::Tensor> beta, c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
+                             c10::optional<at::Tensor> nbt, double momentum, double eps, c10::optional<at::Tensor> fcw,
+                             c10::optional<at::Tensor> fcb) {
+    chk(x, "x"); chk(w, "w");
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.dim() == 4 && x.size(1) == 14 && x.size(2) == 14 && x.size(3) == 16 && w.numel() == 12800,
+                "convnet_l2_fwd: x [B,14,14,16] (NHWC) and w [32,16,5,5] expected");
+    const int B = static_cast<int>(x.size(0));
+    TORCH_CHECK(fused_convnet_supported(B), "convnet_l2_fwd: batch ", B, " exceeds one CTA per SM");
+    at::Tensor y = at::empty({B, 14, 14, 32}, x.options());
+    at::Tensor out = at::empty({B, 32, 7, 7}, x.options());
+    at::Tensor saved = at::empty({64}, x.options());
+    at::Tensor logits;
+    int ncls = 0;
+    if (fcw.has_value() && fcw->defined()) {
+      chk(*fcw, "fc weight");
+      TORCH_CHECK(fcw->dim() == 2 && fcw->size(1) == 1568, "convnet_l2_fwd: fc weight [classes, 1568] expected");
+      ncls = static_cast<int>(fcw->size(0));
+      logits = at::empty({B, ncls}, x.options());
+    }
+    long long* nbt_p = nullptr;
+    if (nbt.has_value() && nbt->defined()) { chk(*nbt, "num_batches_tracked", at::kLong); nbt_p = reinterpret_cast<long long*>(nbt->data_ptr<int64_t>()); }
+    ReduceScratch scr = scratch(x);
+    launch_convnet_l2_fwd(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), opt_ptr(gamma, "gamma"), opt_ptr(beta, "beta"),
+                          y.data_ptr<float>(), out.data_ptr<float>(), saved.data_ptr<float>(), opt_mut(running_mean, "running_mean"),
+                          opt_mut(running_var, "running_var"), nbt_p, static_cast<float>(momentum), static_cast<float>(eps),
+                          ncls ? fcw->data_ptr<float>() : nullptr, ncls ? opt_ptr(fcb, "fc bias") : nullptr,
+                          ncls ? logits.data_ptr<float>() : nullptr, ncls, B, scr.partials,
+                          GridSync{scr.counter + scr.counters - 2, scr.counter + scr.counters - 1}, cur_stream(x));
+    return py::make_tuple(out, y, saved, logits);
+  });
+  m.def("convnet_l2_bwd", [](const at::Tensor& dout, const at::Tensor& y, const at::Tensor& saved, c10::optional<at::Tensor> gamma,
+                             c10::optional<at::Tensor> beta, const at::Tensor& w, at::Tensor dgamma, at::Tensor dbeta) {
+    chk(dout, "dout"); chk(y, "y"); chk(saved, "saved"); chk(w, "w"); chk(dgamma, "dgamma"); chk(dbeta, "dbeta");
+    c10::cuda::CUDAGuard g(y.device());
+    const int B = static_cast<int>(y.size(0));
+    TORCH_CHECK(dout.numel() == static_cast<int64_t>(B) * 1568 && y.numel() == static_cast<int64_t>(B) * 6272 && w.numel() == 12800 &&
+                    dgamma.numel() == 32 && dbeta.numel() == 32, "convnet_l2_bwd: shape mismatch");
+    at::Tensor dy = at::empty({B, 14, 14, 32}, y.options());
+    at::Tensor dx = at::empty({B, 14, 14, 16}, y.options());
+    ReduceScratch scr = scratch(y);
+    launch_convnet_l2_bwd(dout.data_ptr<float>(), y.data_ptr<float>(), saved.data_ptr<float>(), opt_ptr(gamma, "gamma"), opt_ptr(beta, "beta"),
+                          w.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dy.data_ptr<float>(), dx.data_ptr<float>(), B,
+                          scr.partials, GridSync{scr.counter + scr.counters - 2, scr.counter + scr.counters - 1}, cur_stream(y));
+    return py::make_tuple(dy, dx);
+  });
 
   // ---- BN + ReLU + pool ------------------------------------------------------------------------------
   m.def("bn_relu_pool_fwd", [](const at::Tensor& y, const at::Tensor& stats, c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta,

@@ -1,0 +1,829 @@
+// Cooperative fused layer kernels for the reference ConvNet (ref: ddp_example.py:22-41) — one CTA per image.
+//
+// A ConvNet step is ~10 µs of work spread over dependent kernel boundaries (profiles/roofline.md): every per-op kernel
+// pays launch + ramp + drain + a grid-wide reduction.  Here a whole layer is ONE kernel: everything that belongs to an
+// image stays inside its CTA (registers / shared memory / TMEM), and the only grid-wide dependency of a layer — the
+// BatchNorm batch statistics (forward) and the Σdz, Σdz·x̂ sums (backward) — is a device-side grid barrier in the middle
+// of the kernel instead of a kernel boundary:
+//
+//   l1_fwd : conv1 5x5 (1→16) + bias  ──grid barrier (Σy, Σy²)──  BN + ReLU + MaxPool2          (ref :25-28)
+//   l2_fwd : conv2 5x5 (16→32) on tcgen05 (window trick: ONE TMA load of the zero-haloed image, the 25 taps are
+//            row-shifted UMMA descriptors into it; accumulators in TMEM)  ──barrier──  BN + ReLU + MaxPool2 + fc  (ref :30-34,40)
+//   l2_bwd : MaxPool/ReLU/BN backward  ──barrier (Σdz, Σdz·x̂)──  dy → conv2 data gradient on tcgen05
+//   l1_bwd : MaxPool/ReLU/BN backward  ──barrier──  dy → conv1 weight gradient  ──barrier──  deterministic fold
+//
+// All cross-CTA sums are "every CTA writes one partial row, barrier, every CTA folds the rows in the same fixed order",
+// so results are bit-reproducible and identical in every CTA.  The kernels are launched cooperatively (all CTAs
+// co-resident: one per image, at most one per SM).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+#include "cuda_utils.h"
+#include "fused_convnet.h"
+#include "umma_ptx.cuh"
+
+namespace pdt {
+
+namespace {
+
+using namespace ptx;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// grid barrier (sense = generation counter; count returns to zero, so the words are reusable across launches/replays)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void grid_barrier(GridSync gs) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int gen = ld_acquire_gpu(gs.gen);  // cannot advance before this CTA arrives
+    __threadfence();
+    const unsigned int prev = atomicAdd(gs.count, 1u);
+    if (prev == gridDim.x - 1) {
+      *gs.count = 0u;
+      __threadfence();
+      st_release_gpu(gs.gen, gen + 1u);
+    } else {
+      while (ld_acquire_gpu(gs.gen) == gen) {}
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Sum `rows` partial rows of `W` floats (written by other CTAs before a grid barrier) in a fixed order.
+// Called by all threads; the totals land in s_out[0..W).  s_tmp: [4][W] floats.  Needs blockDim.x >= 4*W.
+template <int W>
+__device__ __forceinline__ void fold_rows(const float* __restrict__ partials, int rows, float* s_tmp, float* s_out) {
+  const int tid = threadIdx.x;
+  if (tid < 4 * W) {
+    const int col = tid % W, grp = tid / W;
+    float s = 0.f;
+    for (int r = grp; r < rows; r += 4) s += __ldcg(partials + static_cast<size_t>(r) * W + col);
+    s_tmp[grp * W + col] = s;
+  }
+  __syncthreads();
+  if (tid < W) s_out[tid] = (s_tmp[tid] + s_tmp[W + tid]) + (s_tmp[2 * W + tid] + s_tmp[3 * W + tid]);
+  __syncthreads();
+}
+
+// Warp-level reduction of 32 per-thread values with 31 shuffles: after the call lane l holds Σ_lanes v[l] in v[0].
+__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, half = 16; off >= 1; off >>= 1, half >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+// =====================================================================================================================
+// Layer 1 — conv1 is 1→16 channels on a 28×28 image: K = 25 per output, 31 MFLOP per batch of 100.  One thread per
+// output pixel, 16 accumulators in registers that *stay* in registers across the grid barrier.  Threads are ordered
+// by pooling window (4 consecutive lanes = one 2×2 window), so max-pooling is two shuffles and the y / pooled
+// stores are fully coalesced.
+// =====================================================================================================================
+constexpr int kL1Threads = 800;  // 784 pixels rounded up to whole warps
+constexpr int kL1Warps = kL1Threads / 32;
+
+struct L1Map {
+  int win, d, ph, pw, r, c;
+  bool valid;
+  __device__ __forceinline__ explicit L1Map(int tid) {
+    valid = tid < 784;
+    const int t = valid ? tid : 0;
+    win = t >> 2;
+    d = t & 3;
+    ph = win / 14;
+    pw = win - ph * 14;
+    r = 2 * ph + (d >> 1);
+    c = 2 * pw + (d & 1);
+  }
+};
+
+__device__ __forceinline__ void l1_load_image(const float* __restrict__ x, float* xs /*[32][32]*/, int tid) {
+  for (int i = tid; i < 1024; i += kL1Threads) xs[i] = 0.f;
+  __syncthreads();
+  if (tid < 784) {
+    const int rr = tid / 28, cc = tid - rr * 28;
+    xs[(rr + 2) * 32 + cc + 2] = x[tid];
+  }
+}
+
+__global__ void __launch_bounds__(kL1Threads, 1)
+convnet_l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ out,
+                      float* saved, float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
+                      float* partials, GridSync gs) {
+  __shared__ float xs[32 * 32];
+  __shared__ __align__(16) float ws[25 * 16];
+  __shared__ float red[kL1Warps * 32];
+  __shared__ float s_tmp[4 * 32];
+  __shared__ float s_tot[32];
+  __shared__ float s_scale[16], s_shift[16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
+  const L1Map m(tid);
+
+  l1_load_image(x + static_cast<size_t>(n) * 784, xs, tid);
+  if (tid < 400) {
+    const int tap = tid >> 4, co = tid & 15;
+    ws[tid] = w[co * 25 + tap];
+  }
+  __syncthreads();
+
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = bias ? __ldg(bias + j) : 0.f;
+#pragma unroll 1
+  for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < 5; ++kw) {
+      const float xv = xs[(m.r + kh) * 32 + m.c + kw];
+      const float4* wt = reinterpret_cast<const float4*>(ws + (kh * 5 + kw) * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 wv = wt[q];
+        acc[4 * q + 0] = fmaf(xv, wv.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
+      }
+    }
+  }
+  if (m.valid) {  // conv output is kept for the backward pass (BatchNorm needs x̂ at every position)
+    float4* yp = reinterpret_cast<float4*>(y + ((static_cast<size_t>(n) * 28 + m.r) * 28 + m.c) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) yp[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+  {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] = m.valid ? acc[j] : 0.f;
+      v[16 + j] = m.valid ? acc[j] * acc[j] : 0.f;
+    }
+    warp_transpose_reduce32(v, lane);
+    red[warp * 32 + lane] = v[0];
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.f;
+#pragma unroll 5
+    for (int wi = 0; wi < kL1Warps; ++wi) s += red[wi * 32 + tid];
+    partials[static_cast<size_t>(n) * 32 + tid] = s;
+  }
+  grid_barrier(gs);
+  fold_rows<32>(partials, B, s_tmp, s_tot);
+  if (tid < 16) {
+    const float cnt = static_cast<float>(B) * 784.f;
+    const float mean = s_tot[tid] / cnt;
+    const float var = fmaxf(s_tot[16 + tid] / cnt - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    const float g = gamma ? gamma[tid] : 1.f, b = beta ? beta[tid] : 0.f;
+    s_scale[tid] = g * invstd;
+    s_shift[tid] = b - mean * g * invstd;
+    if (n == 0) {
+      saved[tid] = mean;
+      saved[16 + tid] = invstd;
+      if (running_mean) {
+        const float unbiased = var * (cnt / fmaxf(cnt - 1.f, 1.f));
+        running_mean[tid] = (1.f - momentum) * running_mean[tid] + momentum * mean;
+        running_var[tid] = (1.f - momentum) * running_var[tid] + momentum * unbiased;
+      }
+      if (nbt && tid == 0) *nbt += 1;
+    }
+  }
+  __syncthreads();
+  float z[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float t = fmaxf(fmaf(acc[j], s_scale[j], s_shift[j]), 0.f);
+    t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+    t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2));
+    z[j] = t;
+  }
+  if (m.valid) {  // lane d of the window writes channels 4d..4d+3: one 64-byte row per window
+    float4 o;
+    if (m.d == 0) o = make_float4(z[0], z[1], z[2], z[3]);
+    else if (m.d == 1) o = make_float4(z[4], z[5], z[6], z[7]);
+    else if (m.d == 2) o = make_float4(z[8], z[9], z[10], z[11]);
+    else o = make_float4(z[12], z[13], z[14], z[15]);
+    reinterpret_cast<float4*>(out + ((static_cast<size_t>(n) * 14 + m.ph) * 14 + m.pw) * 16)[m.d] = o;
+  }
+}
+
+// ---- layer 1 backward -------------------------------------------------------------------------------------------------
+// dynamic smem: dys [784][16] | fold [25 warps][26 lanes][16]
+constexpr int kL1BwdSmem = (784 * 16 + kL1Warps * 26 * 16) * 4;
+
+__global__ void __launch_bounds__(kL1Threads, 1)
+convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ saved,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* dgamma, float* dbeta, float* dw, float* db,
+                      float* partials, float* partials_w, GridSync gs) {
+  extern __shared__ __align__(16) float dsm[];
+  float* dys = dsm;                  // [784][16]
+  float* fold = dsm + 784 * 16;      // [25][26][16]
+  __shared__ float xs[32 * 32];
+  __shared__ float red[kL1Warps * 32];
+  __shared__ float s_tmp[4 * 32];
+  __shared__ float s_tot[32];
+  __shared__ float s_scale[16], s_shift[16], s_mean[16], s_invstd[16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
+  const L1Map m(tid);
+
+  l1_load_image(x + static_cast<size_t>(n) * 784, xs, tid);
+  if (tid < 16) {
+    const float mean = saved[tid], invstd = saved[16 + tid];
+    const float g = gamma ? gamma[tid] : 1.f, b = beta ? beta[tid] : 0.f;
+    s_mean[tid] = mean;
+    s_invstd[tid] = invstd;
+    s_scale[tid] = g * invstd;
+    s_shift[tid] = b - mean * g * invstd;
+  }
+  __syncthreads();
+
+  float yv[16], dz[16];
+  {
+    const float4* yp = reinterpret_cast<const float4*>(y + ((static_cast<size_t>(n) * 28 + m.r) * 28 + m.c) * 16);
+    const float4* gp = reinterpret_cast<const float4*>(dp + ((static_cast<size_t>(n) * 14 + m.ph) * 14 + m.pw) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = m.valid ? yp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g4 = m.valid ? gp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      yv[4 * q] = a.x; yv[4 * q + 1] = a.y; yv[4 * q + 2] = a.z; yv[4 * q + 3] = a.w;
+      dz[4 * q] = g4.x; dz[4 * q + 1] = g4.y; dz[4 * q + 2] = g4.z; dz[4 * q + 3] = g4.w;
+    }
+  }
+  // route the pooled gradient to the arg-max of the window (first maximum wins, like torch) and through the ReLU
+  unsigned int mine = 0;
+  float zmax[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float z = fmaf(yv[j], s_scale[j], s_shift[j]);
+    float t = fmaxf(z, __shfl_xor_sync(0xffffffffu, z, 1));
+    t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2));
+    zmax[j] = t;
+    mine |= (z == t ? 1u : 0u) << j;
+  }
+  unsigned int lower = 0;  // positions of the window that come before this one
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const unsigned int other = __shfl_sync(0xffffffffu, mine, (lane & ~3) + k);
+    if (k < m.d) lower |= other;
+  }
+  const unsigned int win = mine & ~lower;
+  {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const bool take = m.valid && ((win >> j) & 1u) && zmax[j] > 0.f;
+      dz[j] = take ? dz[j] : 0.f;
+      const float xhat = (yv[j] - s_mean[j]) * s_invstd[j];
+      yv[j] = xhat;  // from here on yv holds x̂
+      v[j] = dz[j];
+      v[16 + j] = dz[j] * xhat;
+    }
+    warp_transpose_reduce32(v, lane);
+    red[warp * 32 + lane] = v[0];
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.f;
+#pragma unroll 5
+    for (int wi = 0; wi < kL1Warps; ++wi) s += red[wi * 32 + tid];
+    partials[static_cast<size_t>(n) * 32 + tid] = s;
+  }
+  grid_barrier(gs);
+  fold_rows<32>(partials, B, s_tmp, s_tot);  // [0..16) Σdz, [16..32) Σdz·x̂
+  if (n == 0 && tid < 16) {
+    if (dbeta) dbeta[tid] = s_tot[tid];
+    if (dgamma) dgamma[tid] = s_tot[16 + tid];
+  }
+  const float inv_cnt = 1.f / (static_cast<float>(B) * 784.f);
+  if (m.valid) {
+    float4* dst = reinterpret_cast<float4*>(dys + (m.r * 28 + m.c) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * q + e;
+        o[e] = s_scale[j] * (dz[j] - s_tot[j] * inv_cnt - yv[j] * (s_tot[16 + j] * inv_cnt));
+      }
+      dst[q] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __syncthreads();
+  // conv1 weight gradient of this image: lane = filter tap (lane 25 = the bias), warps split the pixels
+  {
+    float a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = 0.f;
+    if (lane < 26) {
+      const int kh = lane / 5, kw = lane - kh * 5;
+      for (int p = warp; p < 784; p += kL1Warps) {
+        const int pr = p / 28, pc = p - pr * 28;
+        const float xv = lane < 25 ? xs[(pr + kh) * 32 + pc + kw] : 1.f;
+        const float4* d4 = reinterpret_cast<const float4*>(dys + p * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 dv = d4[q];
+          a[4 * q + 0] = fmaf(xv, dv.x, a[4 * q + 0]);
+          a[4 * q + 1] = fmaf(xv, dv.y, a[4 * q + 1]);
+          a[4 * q + 2] = fmaf(xv, dv.z, a[4 * q + 2]);
+          a[4 * q + 3] = fmaf(xv, dv.w, a[4 * q + 3]);
+        }
+      }
+      float4* f4 = reinterpret_cast<float4*>(fold + (warp * 26 + lane) * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) f4[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+    }
+  }
+  __syncthreads();
+  if (tid < 416) {
+    float s = 0.f;
+#pragma unroll 5
+    for (int wi = 0; wi < kL1Warps; ++wi) s += fold[wi * 416 + tid];
+    partials_w[static_cast<size_t>(n) * 416 + tid] = s;   // index = tap·16 + co  (tap 25 = bias)
+  }
+  grid_barrier(gs);
+  // every CTA folds a few of the 416 outputs over the B partial rows: one warp per output, fixed order
+  for (int j = n + warp * B; j < 416; j += kL1Warps * B) {
+    float s = 0.f;
+    for (int r = lane; r < B; r += 32) s += __ldcg(partials_w + static_cast<size_t>(r) * 416 + j);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+      const int tap = j >> 4, co = j & 15;
+      if (tap < 25) dw[co * 25 + tap] = s;
+      else if (db) db[co] = s;
+    }
+  }
+}
+
+// =====================================================================================================================
+// Layer 2 — conv2 (16→32, 5x5) is 88 % of the model's FLOPs: tcgen05.  One CTA = one 14×14 image.
+// The zero-haloed input (18×18 positions × 128-byte rows, channels 16..31 zero-filled by TMA) is loaded ONCE; output
+// pixel (oh, ow) is MMA row p = oh·18 + ow of one of two M = 128 tiles (rows 0..125 ↔ oh 0..6, 126..251 ↔ oh 7..13;
+// ow ≥ 14 rows are padding), and filter tap (kh, kw) is the same buffer read through a K-major SWIZZLE_128B descriptor
+// that starts (kh·18 + kw) rows further in (swizzle phase follows the absolute address: verified on hardware by
+// tools/exp_rowshift.py, profiles/rowshift_probe.md).  Weights are swizzled into shared memory by the CTA itself.
+// =====================================================================================================================
+constexpr int kL2Threads = 256;
+constexpr int kPW = 18;                          // padded width
+constexpr int kPatchRows = 18 * 18;              // 324 positions
+constexpr int kPatchBytes = kPatchRows * 128;    // 41,472
+constexpr int kPatchAlloc = 43008;               // + slack rows read by the padding rows of tile 1 (multiple of 1024)
+
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk16) { return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk16 ^ (row & 7)) << 4); }
+
+struct L2FwdSmem {
+  static constexpr int kB = 25 * 32 * 128;       // weights: [tap][32 co][128 B] (ci 0..15 used)            102,400
+  static constexpr int kYs = 196 * 32 * 4;       // conv output of the image, [pixel][32]                     25,088
+  static constexpr int kTotal = 1024 + kPatchAlloc + kB + kYs + 8192;
+};
+
+__global__ void __launch_bounds__(kL2Threads, 1)
+convnet_l2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ w, const float* __restrict__ bias,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ out,
+                      float* saved, float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
+                      const float* __restrict__ fcw, const float* __restrict__ fcb, float* __restrict__ logits, int ncls,
+                      float* partials, GridSync gs) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                                  // input patch (TMA, SWIZZLE_128B)
+  uint8_t* sb = sa + kPatchAlloc;                      // weights
+  float* ys = reinterpret_cast<float*>(sb + L2FwdSmem::kB);
+  float* misc = ys + 196 * 32;                         // 2048 floats
+  float* s_part = misc;                                // [4][64]
+  float* s_tmp = misc + 256;                           // [4][64]
+  float* s_tot = misc + 512;                           // [64]
+  float* s_scale = misc + 576;                         // [32]
+  float* s_shift = misc + 608;                         // [32]
+
+  __shared__ uint64_t bar_x, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_x);
+    mbar_init(&bar_x, 1);
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<64>(&tmem_slot);
+  // zero the slack behind the patch (read only by padding rows, but keep NaNs out of TMEM)
+  for (int i = tid; i < (kPatchAlloc - kPatchBytes) / 16; i += kL2Threads) reinterpret_cast<float4*>(sa + kPatchBytes)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_x, kPatchBytes);
+    tma_load_4d(sa, &tm_x, &bar_x, 0, -2, -2, n);      // channels ≥ 16 and the 2-pixel halo: out-of-bounds zero fill
+  }
+  // B[tap][co][ci] = w[co][ci][tap], K-major rows of 128 B, SWIZZLE_128B
+  for (int i = tid; i < 32 * 16 * 25; i += kL2Threads) {
+    const int co = i / 400, rem = i - co * 400, ci = rem / 25, tap = rem - ci * 25;
+    *reinterpret_cast<float*>(sb + tap * 4096 + sw128_off(co, ci >> 2) + (ci & 3) * 4) = w[i];
+  }
+  fence_proxy_async_smem();   // generic-proxy writes of B → visible to the tensor core
+  __syncthreads();
+  if (warp == 0) {
+    mbar_wait(&bar_x, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
+      const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sb);
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll 1
+        for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+          for (int kw = 0; kw < 5; ++kw) {
+            const uint32_t arow = a0 + static_cast<uint32_t>((7 * t + kh) * kPW + kw) * 128u;
+            const uint32_t brow = b0 + static_cast<uint32_t>(kh * 5 + kw) * 4096u;
+#pragma unroll
+            for (int k = 0; k < 2; ++k)   // K = 16 input channels = two K=8 steps; the zero upper half is never multiplied
+              umma_tf32(tmem_base + t * 32, umma_desc_kmajor<128>(arow + k * 32), umma_desc_kmajor<128>(brow + k * 32), idesc, (kh | kw | k) != 0);
+          }
+        }
+      }
+      umma_commit(&bar_mma);
+    }
+    __syncwarp();
+  }
+  // ---- epilogue: warps 4..7 own TMEM lane quadrants 0..3 ----------------------------------------------------------------
+  if (warp >= 4) {
+    mbar_wait(&bar_mma, 0);
+    __syncwarp();
+    tc_fence_after();
+    const int quad = warp & 3, rr = quad * 32 + lane;   // MMA row inside the tile
+    const int orow = rr / kPW, ow = rr - orow * kPW;
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      float v[32];
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float t16[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + t * 32 + c0, t16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c0 + j] = t16[j];
+      }
+      if (rr < 126 && ow < 14) {
+        const int oh = 7 * t + orow, pix = oh * 14 + ow;
+        float4* yg = reinterpret_cast<float4*>(y + (static_cast<size_t>(n) * 196 + pix) * 32);
+        float4* yl = reinterpret_cast<float4*>(ys + pix * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (bias) { o.x += __ldg(bias + 4 * q); o.y += __ldg(bias + 4 * q + 1); o.z += __ldg(bias + 4 * q + 2); o.w += __ldg(bias + 4 * q + 3); }
+          yg[q] = o;
+          yl[(q + pix) & 7] = o;   // rotate the 16-byte chunks by the pixel index: conflict-free column reads below
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  // ---- per-channel Σy, Σy² of this image: thread = (channel, quarter of the pixels) --------------------------------------
+  if (tid < 128) {
+    const int c = tid & 31, part = tid >> 5;
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = part * 49; p < part * 49 + 49; ++p) {
+      const float val = ys[p * 32 + ((((c >> 2) + p) & 7) << 2) + (c & 3)];
+      s1 += val;
+      s2 = fmaf(val, val, s2);
+    }
+    s_part[part * 64 + c] = s1;
+    s_part[part * 64 + 32 + c] = s2;
+  }
+  __syncthreads();
+  if (tid < 64) partials[static_cast<size_t>(n) * 64 + tid] = (s_part[tid] + s_part[64 + tid]) + (s_part[128 + tid] + s_part[192 + tid]);
+  grid_barrier(gs);
+  fold_rows<64>(partials, B, s_tmp, s_tot);
+  if (tid < 32) {
+    const float cnt = static_cast<float>(B) * 196.f;
+    const float mean = s_tot[tid] / cnt;
+    const float var = fmaxf(s_tot[32 + tid] / cnt - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    const float g = gamma ? gamma[tid] : 1.f, b = beta ? beta[tid] : 0.f;
+    s_scale[tid] = g * invstd;
+    s_shift[tid] = b - mean * g * invstd;
+    if (n == 0) {
+      saved[tid] = mean;
+      saved[32 + tid] = invstd;
+      if (running_mean) {
+        const float unbiased = var * (cnt / fmaxf(cnt - 1.f, 1.f));
+        running_mean[tid] = (1.f - momentum) * running_mean[tid] + momentum * mean;
+        running_var[tid] = (1.f - momentum) * running_var[tid] + momentum * unbiased;
+      }
+      if (nbt && tid == 0) *nbt += 1;
+    }
+  }
+  __syncthreads();
+  // ---- BN + ReLU + MaxPool 2×2 → NCHW [32][7][7] (the flatten order of the classifier, ref :39) ------------------------
+  float* pool = reinterpret_cast<float*>(sb);   // the weights are dead after the MMAs: reuse their space
+  for (int i = tid; i < 1568; i += kL2Threads) {
+    const int c = i & 31, pp = i >> 5, ph = pp / 7, pw = pp - ph * 7;
+    const float sc = s_scale[c], sh = s_shift[c];
+    float mx = 0.f;   // the ReLU floor doubles as the identity of max
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int p = (2 * ph + (d >> 1)) * 14 + 2 * pw + (d & 1);
+      mx = fmaxf(mx, fmaf(ys[p * 32 + ((((c >> 2) + p) & 7) << 2) + (c & 3)], sc, sh));
+    }
+    pool[c * 49 + pp] = mx;
+  }
+  __syncthreads();
+  for (int i = tid; i < 1568; i += kL2Threads) out[static_cast<size_t>(n) * 1568 + i] = pool[i];
+  // ---- classifier head riding on the pooled activations still in shared memory: logits = fc(pool) ----------------------
+  if (logits != nullptr) {
+    // warp k computes classes k, k+8, ...: 1568-long dot products, lanes stride the features
+    for (int cls = warp; cls < ncls; cls += kL2Threads / 32) {
+      const float* wr = fcw + static_cast<size_t>(cls) * 1568;
+      float s = 0.f;
+      for (int k = lane; k < 1568; k += 32) s = fmaf(pool[k], __ldg(wr + k), s);
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) logits[static_cast<size_t>(n) * ncls + cls] = s + (fcb ? fcb[cls] : 0.f);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<64>(tmem_base);
+}
+
+// ---- layer 2 backward: pool/ReLU/BN backward + conv2 data gradient ---------------------------------------------------------
+struct L2BwdSmem {
+  static constexpr int kB = 25 * 16 * 128;       // dgrad weights: [tap][16 ci][128 B = 32 co]                  51,200
+  static constexpr int kTotal = 1024 + kPatchAlloc + kB + 4096;
+};
+
+__global__ void __launch_bounds__(kL2Threads, 1)
+convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float* __restrict__ y /*[B,14,14,32]*/,
+                      const float* __restrict__ saved, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ w, float* dgamma, float* dbeta, float* __restrict__ dy /*[B,14,14,32]*/,
+                      float* __restrict__ dx /*[B,14,14,16]*/, float* partials, GridSync gs) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                                  // dy patch, written by the CTA in the TMA/UMMA SWIZZLE_128B layout
+  uint8_t* sb = sa + kPatchAlloc;
+  float* misc = reinterpret_cast<float*>(sb + L2BwdSmem::kB);   // 1024 floats
+  float* s_part = misc;                                // [8][64]
+  float* s_tmp = misc + 512;                           // [4][64]
+  float* s_tot = misc + 768;                           // [64]
+  float* s_scale = misc + 832;
+  float* s_shift = misc + 864;
+  float* s_mean = misc + 896;
+  float* s_invstd = misc + 928;
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
+
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<32>(&tmem_slot);
+  for (int i = tid; i < kPatchAlloc / 16; i += kL2Threads) reinterpret_cast<float4*>(sa)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // halo = 0
+  if (tid < 32) {
+    const float mean = saved[tid], invstd = saved[32 + tid];
+    const float g = gamma ? gamma[tid] : 1.f, b = beta ? beta[tid] : 0.f;
+    s_mean[tid] = mean;
+    s_invstd[tid] = invstd;
+    s_scale[tid] = g * invstd;
+    s_shift[tid] = b - mean * g * invstd;
+  }
+  // Bd[tap][ci][co] = w[co][ci][24 − tap]: the data gradient is a correlation with the flipped filter
+  for (int i = tid; i < 32 * 16 * 25; i += kL2Threads) {
+    const int co = i / 400, rem = i - co * 400, ci = rem / 25, tap = 24 - (rem - ci * 25);
+    *reinterpret_cast<float*>(sb + tap * 2048 + sw128_off(ci, co >> 2) + (co & 3) * 4) = w[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // thread = (channel c, window group g): windows pp = g, g+8, ... (≤ 7 per thread); y values stay in registers
+  const int c = tid & 31, g = tid >> 5;
+  float yv[7][4], dzv[7];
+  int arg[7];
+  float s1 = 0.f, s2 = 0.f;
+  const float sc = s_scale[c], sh = s_shift[c], mu = s_mean[c], is = s_invstd[c];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int pp = g + 8 * k;
+    dzv[k] = 0.f;
+    arg[k] = 0;
+    if (pp < 49) {
+      const int ph = pp / 7, pw = pp - ph * 7;
+      float best = -INFINITY;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int p = (2 * ph + (d >> 1)) * 14 + 2 * pw + (d & 1);
+        yv[k][d] = y[(static_cast<size_t>(n) * 196 + p) * 32 + c];
+        const float z = fmaf(yv[k][d], sc, sh);
+        if (z > best) { best = z; arg[k] = d; }
+      }
+      const float go = dout[static_cast<size_t>(n) * 1568 + c * 49 + pp];
+      dzv[k] = best > 0.f ? go : 0.f;
+      float xh = 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) if (d == arg[k]) xh = (yv[k][d] - mu) * is;
+      s1 += dzv[k];
+      s2 = fmaf(dzv[k], xh, s2);
+    }
+  }
+  s_part[g * 64 + c] = s1;
+  s_part[g * 64 + 32 + c] = s2;
+  __syncthreads();
+  if (tid < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += s_part[q * 64 + tid];
+    partials[static_cast<size_t>(n) * 64 + tid] = s;
+  }
+  grid_barrier(gs);
+  fold_rows<64>(partials, B, s_tmp, s_tot);
+  if (n == 0 && tid < 32) {
+    if (dbeta) dbeta[tid] = s_tot[tid];
+    if (dgamma) dgamma[tid] = s_tot[32 + tid];
+  }
+  {
+    const float inv_cnt = 1.f / (static_cast<float>(B) * 196.f);
+    const float m1 = s_tot[c] * inv_cnt, m2 = s_tot[32 + c] * inv_cnt;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int pp = g + 8 * k;
+      if (pp < 49) {
+        const int ph = pp / 7, pw = pp - ph * 7;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const int oh = 2 * ph + (d >> 1), ow = 2 * pw + (d & 1);
+          const float xh = (yv[k][d] - mu) * is;
+          const float v = sc * ((d == arg[k] ? dzv[k] : 0.f) - m1 - xh * m2);
+          dy[(static_cast<size_t>(n) * 196 + oh * 14 + ow) * 32 + c] = v;           // kept for the weight-gradient kernel
+          const int P = (oh + 2) * kPW + ow + 2;
+          *reinterpret_cast<float*>(sa + sw128_off(P, c >> 2) + (c & 3) * 4) = v;   // haloed patch for the data-gradient MMAs
+        }
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, 16);
+      const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sb);
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll 1
+        for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+          for (int kw = 0; kw < 5; ++kw) {
+            const uint32_t arow = a0 + static_cast<uint32_t>((7 * t + kh) * kPW + kw) * 128u;
+            const uint32_t brow = b0 + static_cast<uint32_t>(kh * 5 + kw) * 2048u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // K = 32 output channels = four K=8 steps
+              umma_tf32(tmem_base + t * 16, umma_desc_kmajor<128>(arow + k * 32), umma_desc_kmajor<128>(brow + k * 32), idesc, (kh | kw | k) != 0);
+          }
+        }
+      }
+      umma_commit(&bar_mma);
+    }
+    __syncwarp();
+  }
+  if (warp >= 4) {
+    mbar_wait(&bar_mma, 0);
+    __syncwarp();
+    tc_fence_after();
+    const int quad = warp & 3, rr = quad * 32 + lane;
+    const int orow = rr / kPW, ow = rr - orow * kPW;
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      float v[16];
+      tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + t * 16, v);
+      if (rr < 126 && ow < 14) {
+        float4* o = reinterpret_cast<float4*>(dx + (static_cast<size_t>(n) * 196 + (7 * t + orow) * 14 + ow) * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<32>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("launch of ") + what + " failed: " + cudaGetErrorString(e));
+  count_kernel_launch();
+}
+
+bool cooperative_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PDT_FUSED_COOPERATIVE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+void launch_coop(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, const char* what, Args&&... args) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(smem) for ") + what + ": " + cudaGetErrorString(e));
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: they wait for each other at the grid barrier
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cooperative_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("launch of ") + what + " failed: " + cudaGetErrorString(e));
+  count_kernel_launch();
+}
+
+int sm_count() {
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+CUtensorMap make_patch_map(const float* base, int C, int W, int H, int N) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4, static_cast<cuuint64_t>(H) * W * C * 4};
+  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(W + 4), static_cast<cuuint32_t>(H + 4), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = driver().cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(fused conv2 patch) failed: " + cu_error(r));
+  return m;
+}
+
+}  // namespace
+
+bool fused_convnet_supported(int B) { return B >= 1 && B <= sm_count(); }
+
+void launch_convnet_l1_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float* y, float* out,
+                           float* saved, float* running_mean, float* running_var, long long* nbt, float momentum, float eps, int B,
+                           float* partials, GridSync gs, cudaStream_t st) {
+  launch_coop(convnet_l1_fwd_kernel, B, kL1Threads, 0, st, "convnet_l1_fwd", x, w, bias, gamma, beta, y, out, saved, running_mean, running_var, nbt,
+              momentum, eps, partials, gs);
+}
+
+void launch_convnet_l1_bwd(const float* dp, const float* y, const float* x, const float* saved, const float* gamma, const float* beta,
+                           float* dgamma, float* dbeta, float* dw, float* db, int B, float* partials, float* partials_w, GridSync gs,
+                           cudaStream_t st) {
+  launch_coop(convnet_l1_bwd_kernel, B, kL1Threads, static_cast<size_t>(kL1BwdSmem), st, "convnet_l1_bwd", dp, y, x, saved, gamma, beta, dgamma, dbeta,
+              dw, db, partials, partials_w, gs);
+}
+
+void launch_convnet_l2_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float* y, float* out,
+                           float* saved, float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
+                           const float* fcw, const float* fcb, float* logits, int ncls, int B, float* partials, GridSync gs, cudaStream_t st) {
+  CUtensorMap tm_x = make_patch_map(x, 16, 14, 14, B);
+  launch_coop(convnet_l2_fwd_kernel, B, kL2Threads, static_cast<size_t>(L2FwdSmem::kTotal), st, "convnet_l2_fwd", tm_x, w, bias, gamma, beta, y, out,
+              saved, running_mean, running_var, nbt, momentum, eps, fcw, fcb, logits, ncls, partials, gs);
+}
+
+void launch_convnet_l2_bwd(const float* dout, const float* y, const float* saved, const float* gamma, const float* beta, const float* w,
+                           float* dgamma, float* dbeta, float* dy, float* dx, int B, float* partials, GridSync gs, cudaStream_t st) {
+  launch_coop(convnet_l2_bwd_kernel, B, kL2Threads, static_cast<size_t>(L2BwdSmem::kTotal), st, "convnet_l2_bwd", dout, y, saved, gamma, beta, w, dgamma,
+              dbeta, dy, dx, partials, gs);
+}
+
+}  // namespace pdt

@@ -236,8 +236,8 @@ void Reducer::prepare_for_forward() {
                 "sure all `forward` outputs participate in calculating loss.");
   }
   ++stats_.num_iterations;
-  resolve_timings();
   timing_this_iter_ = !comm_->capturing();
+  if (timing_this_iter_) resolve_timings();   // event queries are not allowed while a CUDA graph is being captured
   cur_ = Marks();
   cur_.iteration = stats_.num_iterations;
   if (timing_this_iter_) cur_.fwd_start = comm_->stamp();
@@ -513,7 +513,7 @@ void Reducer::register_comm_hook(py::object hook) {
 
 ReducerStats Reducer::stats() const {
   std::lock_guard<std::mutex> g(mu_);
-  const_cast<Reducer*>(this)->resolve_timings();
+  if (!comm_->capturing()) const_cast<Reducer*>(this)->resolve_timings();
   ReducerStats s = stats_;
   if (s.grad_ready_order.empty()) s.grad_ready_order = prev_ready_order_;
   return s;

@@ -115,6 +115,102 @@ class _ConvBnReluPool(torch.autograd.Function):
         return dx, dw, db, (dgamma if g_p is not None else None), (dbeta if be_p is not None else None), None, None, None, None, None, None, None, None, None
 
 
+# =====================================================================================================
+# Cooperative fused layers of the reference ConvNet (csrc/cuda/fused_convnet.cu): one kernel per layer and direction
+# =====================================================================================================
+def fused_convnet_ok(x: torch.Tensor, model) -> bool:
+    """The per-image cooperative kernels cover exactly the reference architecture (ref: ddp_example.py:22-41) in
+    training mode with local BatchNorm statistics; everything else takes the per-op kernels."""
+    if os.environ.get("PDT_FUSED_LAYERS", "1") == "0" or not hasattr(_C, "convnet_l1_fwd"):
+        return False
+    c1, b1, c2, b2, fc = model.layer1[0], model.layer1[1], model.layer2[0], model.layer2[1], model.fc
+    if not (x.dim() == 4 and x.shape[1:] == (1, 28, 28) and x.is_contiguous() and _C.fused_convnet_supported(x.shape[0])):
+        return False
+    if not (c1.weight.shape == (16, 1, 5, 5) and c2.weight.shape == (32, 16, 5, 5) and fc.weight.shape[1] == 1568 and fc.weight.shape[0] <= 64):
+        return False
+    for bn in (b1, b2):
+        if not bn.training or type(bn).__name__ == "SyncBatchNorm" or not bn.track_running_stats or bn.momentum is None or not bn.affine:
+            return False
+    return all(p.is_contiguous() for p in (c1.weight, c2.weight, fc.weight))
+
+
+class _FusedLayer1(torch.autograd.Function):
+    """conv1 + BN1 + ReLU + pool1 forward, and its whole backward, as one cooperative kernel each."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps):
+        out, y, saved = _C.convnet_l1_fwd(x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps)
+        ctx.save_for_backward(x, y, saved, gamma, beta)
+        ctx.params = (w, b, gamma, beta)
+        return out  # [B,14,14,16] NHWC
+
+    @staticmethod
+    def backward(ctx, dp):
+        x, y, saved, gamma, beta = ctx.saved_tensors
+        w_p, b_p, g_p, be_p = ctx.params
+        dw = _grad_dst(w_p, w_p)
+        db = _grad_dst(b_p, b_p) if b_p is not None else None
+        dg = _grad_dst(g_p, gamma)
+        dbe = _grad_dst(be_p, beta)
+        _C.convnet_l1_bwd(dp.contiguous(), y, x, saved, gamma, beta, dg, dbe, dw, db)
+        return None, dw, db, dg, dbe, None, None, None, None, None
+
+
+class _FusedLayer2(torch.autograd.Function):
+    """conv2 (tcgen05) + BN2 + ReLU + pool2 (+ the classifier's logits, which ride on the pooled activations while they
+    are still in shared memory) forward; pool/ReLU/BN backward + conv2 data gradient as one kernel backward, then the
+    tensor-core weight gradient."""
+
+    @staticmethod
+    def forward(ctx, p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb):
+        out, y, saved, logits = _C.convnet_l2_fwd(p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb)
+        ctx.save_for_backward(p1, y, saved, gamma, beta, w)
+        ctx.params = (w, b, gamma, beta)
+        ctx.mark_non_differentiable(logits)
+        return out, logits  # [B,32,7,7] NCHW, [B,classes]
+
+    @staticmethod
+    def backward(ctx, dout, _dlogits):
+        p1, y, saved, gamma, beta, w = ctx.saved_tensors
+        w_p, b_p, g_p, be_p = ctx.params
+        dg = _grad_dst(g_p, gamma)
+        dbe = _grad_dst(be_p, beta)
+        dy, dp1 = _C.convnet_l2_bwd(dout.contiguous(), y, saved, gamma, beta, w, dg, dbe)
+        dw = _grad_dst(w_p, w)
+        db = _grad_dst(b_p, b_p) if b_p is not None else None
+        _C.conv5x5_wgrad(dy, p1, dw, db, "auto")
+        return dp1, dw, db, dg, dbe, None, None, None, None, None, None, None
+
+
+class _FusedClassifier(torch.autograd.Function):
+    """Autograd node of the classifier whose forward value was already produced by the layer-2 kernel."""
+
+    @staticmethod
+    def forward(ctx, feat, w, b, logits):
+        ctx.save_for_backward(feat, w)
+        ctx.params = (w, b)
+        return logits.view_as(logits)
+
+    @staticmethod
+    def backward(ctx, dout):
+        feat, w = ctx.saved_tensors
+        w_p, b_p = ctx.params
+        dw = _grad_dst(w_p, w)
+        db = _grad_dst(b_p, b_p) if b_p is not None else None
+        dx = _C.linear_bwd(dout.contiguous(), feat.reshape(feat.shape[0], -1), w, True, dw, db)
+        return dx.view_as(feat), dw, db, None
+
+
+def fused_convnet_forward(x: torch.Tensor, model) -> torch.Tensor:
+    """The reference ConvNet's training forward as TWO kernels (ref: ddp_example.py:36-41)."""
+    c1, b1, c2, b2, fc = model.layer1[0], model.layer1[1], model.layer2[0], model.layer2[1], model.fc
+    p1 = _FusedLayer1.apply(x, c1.weight, c1.bias, b1.weight, b1.bias, b1.running_mean, b1.running_var, b1.num_batches_tracked,
+                            float(b1.momentum), float(b1.eps))
+    p2, logits = _FusedLayer2.apply(p1, c2.weight, c2.bias, b2.weight, b2.bias, b2.running_mean, b2.running_var, b2.num_batches_tracked,
+                                    float(b2.momentum), float(b2.eps), fc.weight, fc.bias)
+    return _FusedClassifier.apply(p2, fc.weight, fc.bias, logits)
+
+
 def conv_bn_relu_pool(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.Module, out_nchw: Optional[bool] = None,
                       impl: str = "auto") -> torch.Tensor:
     """Conv5×5(pad 2) → BatchNorm (batch stats, optionally synchronised) → ReLU → MaxPool2×2 as two

@@ -206,8 +206,9 @@ class SGD(torch.optim.Optimizer):
                     continue
                 # "first step" (buf = g, no dampening) is a per-parameter decision, as in torch: parameters that see
                 # their first gradient now go through one launch with first_step=True, the rest through another
+                fresh = [st["momentum_buffer"] is None for st in bufs]   # decided before any buffer is created below
                 for want_first in (True, False):
-                    sel = [i for i, st in enumerate(bufs) if (st["momentum_buffer"] is None) == want_first]
+                    sel = [i for i, f in enumerate(fresh) if f == want_first]
                     if not sel:
                         continue
                     ps, gs_ = [params[i] for i in sel], [grads[i] for i in sel]

@@ -226,6 +226,59 @@ def test_convnet_fused_matches_unfused(syncbn_module):
     assert torch.allclose(net(x).double(), ref(x.double()), atol=3e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("B", [100, 3, 148])
+def test_cooperative_fused_layers_match_per_op_kernels(B, monkeypatch):
+    """csrc/cuda/fused_convnet.cu (one cooperative kernel per layer and direction, grid barrier for the batch
+    statistics) against the per-op kernels on the same weights and data: same TF32 convolution, same fp32 rest —
+    only summation orders differ."""
+    torch.manual_seed(2)
+    a = pdt.models.ConvNet(fused=True).to(dev())
+    b = pdt.models.ConvNet(fused=True).to(dev())
+    b.load_state_dict(a.state_dict())
+    x = torch.rand(B, 1, 28, 28, device=dev())
+    t = torch.randint(0, 10, (B,), device=dev())
+    crit = pdt.nn.CrossEntropyLoss()
+    before = _C.kernel_launch_count()
+    la = crit(a(x), t)
+    la.backward()
+    fused_launches = _C.kernel_launch_count() - before
+    monkeypatch.setenv("PDT_FUSED_LAYERS", "0")
+    before = _C.kernel_launch_count()
+    lb = crit(b(x), t)
+    lb.backward()
+    per_op_launches = _C.kernel_launch_count() - before
+    monkeypatch.delenv("PDT_FUSED_LAYERS")
+    assert fused_launches < per_op_launches, (fused_launches, per_op_launches)
+    assert abs(la.item() - lb.item()) < 1e-4, (la.item(), lb.item())
+    for (n1, p1), (_, p2) in zip(a.named_parameters(), b.named_parameters()):
+        scale = p2.grad.abs().max().item() + 1e-6
+        assert (p1.grad - p2.grad).abs().max().item() <= 2e-2 * scale + 1e-6, (n1, (p1.grad - p2.grad).abs().max().item(), scale)  # TF32 operand rounding of slightly different dy
+    for (n1, b1), (_, b2) in zip(a.named_buffers(), b.named_buffers()):
+        assert torch.allclose(b1.float(), b2.float(), atol=1e-5, rtol=1e-5), n1
+
+
+def test_cooperative_layer2_exact_on_small_integers():
+    """Integer-valued inputs/weights are exact in TF32 and in fp32 accumulation: the fused conv2 forward (window
+    descriptors over the haloed image) and data gradient must reproduce a float64 convolution bit for bit."""
+    B = 5
+    p1 = torch.randint(-3, 4, (B, 14, 14, 16), device=dev()).float()
+    w = torch.randint(-2, 3, (32, 16, 5, 5), device=dev()).float()
+    bias = torch.randint(-2, 3, (32,), device=dev()).float()
+    gamma, beta = torch.ones(32, device=dev()), torch.zeros(32, device=dev())
+    out, y, saved, logits = _C.convnet_l2_fwd(p1, w, bias, gamma, beta, None, None, None, 0.1, 1e-5, None, None)
+    ref = F.conv2d(p1.permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=2)
+    assert torch.equal(y.permute(0, 3, 1, 2).double(), ref)
+    mean = ref.mean((0, 2, 3))
+    assert torch.allclose(saved[:32].double(), mean, atol=1e-4, rtol=1e-5)
+    # data gradient: feed a gradient that passes the pool/ReLU/BN backward, compare the conv part through dy
+    dout = torch.randn(B, 32, 7, 7, device=dev())
+    dg, db = torch.empty(32, device=dev()), torch.empty(32, device=dev())
+    dy, dx = _C.convnet_l2_bwd(dout, y, saved, gamma, beta, w, dg, db)
+    ref_dx = torch.nn.grad.conv2d_input((B, 16, 14, 14), w.double(), dy.permute(0, 3, 1, 2).double(), padding=2)
+    err = (dx.permute(0, 3, 1, 2).double() - ref_dx).abs().max().item()
+    assert err <= 2e-3 * ref_dx.abs().max().item() + 1e-5, err   # dy is not integer valued: TF32 operand rounding
+
+
 def test_generic_bn_kernels_match_torch():
     x = torch.randn(8, 12, 9, 7, device=dev()) * 3 + 1
     st = ops.bn_local_stats(x)
