@@ -291,10 +291,15 @@ def run_ours(args):
 
             it = batches()
 
+            stall = {"loader": (0.0, -1), "step": (0.0, -1), "readback": (0.0, -1)}
+
             def e2e_step(i):
+                t0 = time.perf_counter()
                 images, labels = next(it)                     # pinned host tensors from the loader
+                t1 = time.perf_counter()
                 state["h2d"] = images.numel() * images.element_size() + labels.numel() * labels.element_size()
                 loss = step(images, labels)                   # H2D of this batch into the step's inputs + graph replay
+                t2 = time.perf_counter()
                 if i >= R:
                     evs[i % R].synchronize()                  # the slot's previous loss has reached the host
                 host_loss[i % R].copy_(loss.detach(), non_blocking=True)   # D2H of every step's loss
@@ -302,8 +307,15 @@ def run_ours(args):
                 if (i + 1) % 10 == 0 and rank == 0:           # the reference's logging cadence: a blocking read (ref: ddp_example.py:93-95)
                     evs[i % R].synchronize()
                     state["logged"] = float(host_loss[i % R])
+                t3 = time.perf_counter()
+                if i >= W:   # where the host spends its worst moments (ms, timed step index)
+                    for k, d in (("loader", t1 - t0), ("step", t2 - t1), ("readback", t3 - t2)):
+                        if d * 1e3 > stall[k][0]:
+                            stall[k] = (round(d * 1e3, 3), i - W)
 
             ms_e2e_dev, ms_e2e_wall, _, e2e_windows = timed(e2e_step, W, K)
+            if e2e_windows is not None:
+                e2e_windows["host_worst_ms"] = stall
             e2e = {"ms": max(ms_e2e_dev, ms_e2e_wall), "dev_ms": ms_e2e_dev, "wall_ms": ms_e2e_wall, "windows": e2e_windows,
                    "h2d": state["h2d"], "loss": float(host_loss[(W + K - 1) % R])}
     ms_dev = max_over_ranks(ms_dev)

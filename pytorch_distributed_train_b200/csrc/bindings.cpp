@@ -5,6 +5,7 @@
 #include <torch/extension.h>
 
 #include "comm/comm.h"
+#include "data/batch_loader.h"
 #include "common/net.h"
 #include "reducer/bucket_plan.h"
 #include "reducer/reducer.h"
@@ -165,6 +166,23 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("parameters", [](GradBucket& b) { return b.parameters; })
       .def("offsets", [](GradBucket& b) { return b.offsets; })
       .def("lengths", [](GradBucket& b) { return b.lengths; });
+
+  py::class_<BatchStager, std::shared_ptr<BatchStager>>(m, "BatchStager")
+      .def(py::init<at::Tensor, at::Tensor, std::vector<int64_t>, int64_t, bool, double, int64_t, bool, int>(), py::arg("data"), py::arg("targets"),
+           py::arg("sample_shape"), py::arg("batch_size"), py::arg("drop_last") = false, py::arg("scale") = 1.0, py::arg("depth") = 8,
+           py::arg("pin_memory") = false, py::arg("device") = -1)
+      .def("start", &BatchStager::start, py::arg("indices"))
+      .def("num_batches", &BatchStager::num_batches)
+      .def("next", [](BatchStager& s) -> py::object {
+        at::Tensor images, targets;
+        bool ok;
+        {
+          py::gil_scoped_release r;   // the worker thread may still be staging this batch
+          ok = s.next(&images, &targets);
+        }
+        if (!ok) return py::none();
+        return py::make_tuple(images, targets);
+      });
 
   py::class_<Reducer, std::shared_ptr<Reducer>>(m, "Reducer")
       .def(py::init<std::vector<at::Tensor>, std::vector<std::vector<int64_t>>, std::shared_ptr<Comm>, int64_t, int64_t, bool, bool, bool>(),

@@ -973,6 +973,167 @@ __global__ void __launch_bounds__(256) wgrad_fold_kernel(const float* __restrict
 }
 
 // =====================================================================================================
+// conv2 weight gradient, fully TMA-fed ("window" formulation; used by the cooperative fused layers, whose activations
+// live in zero-haloed 18×18 frames):   dWᵀ[(kh, kw, ci)][co] = Σ_P  xpad[P + (kh−2)·18 + (kw−2)][ci] · dypad[P][co]
+// over the padded positions P of every image (dypad is zero outside the 14×14 interior, so the halo and the frame
+// padding contribute nothing).  Both operands are MN-major as in the kernel above, but the im2col gather is gone:
+// two horizontally adjacent taps of one pixel are 32 *contiguous* floats of the NHWC frame, so an A atom
+// [64 positions][2 taps × 16 ch] is ONE 2-D TMA box over an overlapping-row view of xpad (row pitch 64 B, row length
+// 128 B).  15 tap pairs (kh, {0-1, 2-3, 4-5}) → M = 480 (pair (kh,4-5) carries a dummy sixth column), four 128-row
+// TMEM accumulators; K = 256 positions per image in two 128-row tiles starting at the first interior position.
+// One CTA per image; per-CTA partial [512][32]; the bias gradient comes from per-image Σdy rows (layer-2 backward).
+// =====================================================================================================
+struct WgradWinCfg {
+  static constexpr int kFrame = 18 * 18;              // padded positions per image
+  static constexpr int kFirst = 2 * 18 + 2;           // first interior position
+  static constexpr int kMRows = 512;
+  static constexpr int kStages = 5;
+  static constexpr int kAStageBytes = 4 * 8 * 1024;   // [4 pairs][64 positions][128 B]
+  static constexpr int kBStages = 2, kBStageBytes = kTileM * 128;
+  static constexpr int kTmemCols = 128;
+  static constexpr int kThreads = 192;
+  static constexpr size_t kSmem = 1024 + kStages * kAStageBytes + kBStages * kBStageBytes + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1) conv5x5_wgrad_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
+                                                                   float* __restrict__ partials, int B) {
+  using Cfg = WgradWinCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;
+  uint8_t* sb = sa + Cfg::kStages * Cfg::kAStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb + Cfg::kBStages * Cfg::kBStageBytes);
+  uint64_t* afull = bars;
+  uint64_t* aempty = afull + Cfg::kStages;
+  uint64_t* bfull = aempty + Cfg::kStages;
+  uint64_t* bempty = bfull + Cfg::kBStages;
+  uint64_t* acc_full = bempty + Cfg::kBStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int num_tiles = 2 * B;   // (image, half)
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_dy);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    if (elect_one()) {
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int n = tile >> 1, h = tile & 1;
+        const int row0 = n * Cfg::kFrame + Cfg::kFirst + 128 * h;          // first dy position of this K tile
+        const int bs = it % Cfg::kBStages;
+        mbar_wait(&bempty[bs], ((it / Cfg::kBStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bfull[bs], Cfg::kBStageBytes);
+        tma_load_2d(sb + bs * Cfg::kBStageBytes, &tm_dy, &bfull[bs], 0, row0);
+        for (int mt = 0; mt < 4; ++mt) {
+          const int npairs = mt == 3 ? 3 : 4;                               // pair 15 does not exist
+          for (int half = 0; half < 2; ++half, ++g) {
+            const int s = g % Cfg::kStages;
+            mbar_wait(&aempty[s], ((g / Cfg::kStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&afull[s], npairs * 8192);
+            for (int a = 0; a < npairs; ++a) {
+              const int q = mt * 4 + a, kh = q / 3, kw = 2 * (q - kh * 3);
+              // x position of dy position P for tap (kh, kw): P + (kh-2)·18 + (kw-2); negative / past-the-end rows are zero-filled
+              tma_load_2d(sa + s * Cfg::kAStageBytes + a * 8192, &tm_x, &afull[s], 0, row0 + 64 * half + (kh - 2) * 18 + (kw - 2));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    constexpr uint32_t idesc = umma_idesc_tf32(kTileM, 32) | (1u << 15) | (1u << 16);  // A and B are MN-major
+    int g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int bs = it % Cfg::kBStages;
+      mbar_wait(&bfull[bs], (it / Cfg::kBStages) & 1);
+      for (int mt = 0; mt < 4; ++mt) {
+        for (int h = 0; h < 2; ++h, ++g) {
+          const int s = g % Cfg::kStages;
+          mbar_wait(&afull[s], (g / Cfg::kStages) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a0 = smem_u32(sa + s * Cfg::kAStageBytes), b0 = smem_u32(sb + bs * Cfg::kBStageBytes) + h * 8 * 1024;
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb)
+              umma_tf32(tmem_base + mt * 32, umma_desc_mn_sw128_32b(a0 + kb * 1024, 8 * 1024, 512),
+                        umma_desc_mn_sw128_32b(b0 + kb * 1024, 1024, 512), idesc, (it | h | kb) != 0);
+            umma_commit(&aempty[s]);
+            if (mt == 3 && h == 1) umma_commit(&bempty[bs]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
+  } else {
+    // ---- epilogue (warps 0-3): four accumulators → this CTA's partial [512][32] ------------------------------------
+    mbar_wait(acc_full, 0);
+    __syncwarp();
+    tc_fence_after();
+    for (int mt = 0; mt < 4; ++mt) {
+      const int m = mt * kTileM + tid;
+      float v[32];
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float t[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + mt * 32 + c0, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c0 + j] = t[j];
+      }
+      float* o = partials + (static_cast<size_t>(blockIdx.x) * Cfg::kMRows + m) * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// dw[co][ci][kh][kw] = Σ_cta partial[cta][q·32 + (kw&1)·16 + ci][co] with q = 3·kh + kw/2;  db[co] = Σ_n dysum[n][co]
+__global__ void __launch_bounds__(256) wgrad_win_fold_kernel(const float* __restrict__ partials, int nparts, const float* __restrict__ dysum, int B,
+                                                             float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float s_sub[8][32];
+  const int i = blockIdx.x, co = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float s0 = 0.f, s1 = 0.f;
+  if (i < 400) {
+    const int tap = i >> 4, ci = i & 15, kh = tap / 5, kw = tap - kh * 5;
+    const int m = (3 * kh + (kw >> 1)) * 32 + (kw & 1) * 16 + ci;
+    const float* p = partials + static_cast<size_t>(m) * 32 + co;
+    const size_t stride = static_cast<size_t>(WgradWinCfg::kMRows) * 32;
+    int c = warp;
+    for (; c + 8 < nparts; c += 16) {
+      s0 += p[c * stride];
+      s1 += p[(c + 8) * stride];
+    }
+    if (c < nparts) s0 += p[c * stride];
+  } else {
+    for (int n = warp; n < B; n += 8) s0 += dysum[static_cast<size_t>(n) * 32 + co];
+  }
+  s_sub[warp][co] = s0 + s1;
+  __syncthreads();
+  if (warp == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += s_sub[w8][co];
+    if (i < 400) dw[(co * 16 + (i & 15)) * 25 + (i >> 4)] = s;
+    else if (db) db[co] = s;
+  }
+}
+
+// =====================================================================================================
 // Hardware probe for the next conv design (profiles/conv_tma_ncu.md §3): can a K-major swizzled A operand
 // start at an arbitrary ROW of a larger smem buffer?  A [256][ROWB/4] tile is loaded once by TMA; the MMA
 // reads rows [shift, shift+128) through a descriptor whose start address is base + shift·ROWB, with the
@@ -1287,6 +1448,32 @@ void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, fl
   check_launch("conv5x5_wgrad_umma");
   wgrad_fold_kernel<<<401, 256, 0, st>>>(scr.partials, grid, dw, db);
   check_launch("wgrad_fold");
+}
+
+void launch_conv5x5_wgrad_win(const float* dy_pad, const float* x_pad, const float* dysum, float* dw, float* db, int B, ReduceScratch scr,
+                              cudaStream_t st) {
+  using Cfg = WgradWinCfg;
+  const int grid = std::min(B, sm_count());
+  if (static_cast<long long>(grid) * Cfg::kMRows * 32 > scr.capacity_floats) throw std::invalid_argument("conv5x5 wgrad (window): scratch too small");
+  const uint64_t rows = static_cast<uint64_t>(B) * Cfg::kFrame;
+  // overlapping-row view of the haloed NHWC frames: row r = the 32 floats starting at position r (two adjacent pixels × 16 ch)
+  CUtensorMap tm_x;
+  {
+    cuuint64_t dims[2] = {32, rows - 1};
+    cuuint64_t strides[1] = {64};
+    cuuint32_t box[2] = {32, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = driver().cuTensorMapEncodeTiled(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x_pad), dims, strides, box, estr,
+                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(overlapping rows) failed: " + cu_error(r));
+  }
+  CUtensorMap tm_dy = make_tmap_2d(dy_pad, 32, rows, 32, kTileM, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  opt_in_smem(conv5x5_wgrad_win_kernel, Cfg::kSmem);
+  conv5x5_wgrad_win_kernel<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tm_x, tm_dy, scr.partials, B);
+  check_launch("conv5x5_wgrad_win");
+  wgrad_win_fold_kernel<<<401, 256, 0, st>>>(scr.partials, grid, dysum, B, dw, db);
+  check_launch("wgrad_win_fold");
 }
 
 void launch_gemm_tf32_tcgen05(const float* a, const float* b, float* d, int M, int N, int K, cudaStream_t st) {

@@ -31,6 +31,11 @@ void launch_conv5x5_dgrad_win(const float* dy, const float* w, float* dx, ConvSh
 // pixel tiles with MN-major operands, four TMEM accumulators, deterministic fold of the per-CTA partials.
 void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, float* db, ConvShape s, ReduceScratch scr, cudaStream_t st);
 
+// Window formulation for zero-haloed 18×18 frames (cooperative fused layers): dy_pad [B,18,18,32], x_pad [B,18,18,16], dysum [B,32]
+// (per-image Σdy rows, folded into db).  All operands arrive by TMA: no im2col gather.
+void launch_conv5x5_wgrad_win(const float* dy_pad, const float* x_pad, const float* dysum, float* dw, float* db, int B, ReduceScratch scr,
+                              cudaStream_t st);
+
 // D[M,N] = A[M,K] · B[N,K]^T, fp32 in/out, TF32 tensor-core math (K % 4 == 0, N % 16 == 0, N <= 256).
 void launch_gemm_tf32_tcgen05(const float* a, const float* b, float* d, int M, int N, int K, cudaStream_t st);
 

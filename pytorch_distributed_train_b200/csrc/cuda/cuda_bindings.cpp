@@ -194,6 +194,12 @@ void register_cuda_bindings(py::module_& m) {
 
   // ---- cooperative fused ConvNet layers (fused_convnet.cu): one CTA per image, grid barrier for the batch statistics ----
   m.def("fused_convnet_supported", [](int64_t B) { return fused_convnet_supported(static_cast<int>(B)); });
+  m.def("fused_convnet_trace_enable", [](bool on) { fused_convnet_trace_enable(on); });
+  m.def("fused_convnet_trace_read", [] {
+    at::Tensor t = at::zeros({4, 160, 12}, at::kLong);
+    fused_convnet_trace_read(reinterpret_cast<unsigned long long*>(t.data_ptr<int64_t>()));
+    return t;
+  });
   m.def("convnet_l1_fwd", [](const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> gamma,
                              c10::optional<at::Tensor> beta, c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
                              c10::optional<at::Tensor> nbt, double momentum, double eps) {
@@ -203,7 +209,7 @@ void register_cuda_bindings(py::module_& m) {
     const int B = static_cast<int>(x.numel() / 784);
     TORCH_CHECK(fused_convnet_supported(B), "convnet_l1_fwd: batch ", B, " exceeds one CTA per SM");
     at::Tensor y = at::empty({B, 28, 28, 16}, x.options());
-    at::Tensor out = at::empty({B, 14, 14, 16}, x.options());
+    at::Tensor out = at::empty({B, 18, 18, 16}, x.options());   // zero-haloed frame
     at::Tensor saved = at::empty({32}, x.options());
     long long* nbt_p = nullptr;
     if (nbt.has_value() && nbt->defined()) { chk(*nbt, "num_batches_tracked", at::kLong); nbt_p = reinterpret_cast<long long*>(nbt->data_ptr<int64_t>()); }
@@ -212,7 +218,7 @@ void register_cuda_bindings(py::module_& m) {
     launch_convnet_l1_fwd(x.data_ptr<float>(), w.data_ptr<float>(), opt_ptr(bias, "bias"), opt_ptr(gamma, "gamma"), opt_ptr(beta, "beta"),
                           y.data_ptr<float>(), out.data_ptr<float>(), saved.data_ptr<float>(), opt_mut(running_mean, "running_mean"),
                           opt_mut(running_var, "running_var"), nbt_p, static_cast<float>(momentum), static_cast<float>(eps), B, scr.partials,
-                          GridSync{scr.counter + scr.counters - 2, scr.counter + scr.counters - 1}, cur_stream(x));
+                          GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x));
     return py::make_tuple(out, y, saved);
   });
   m.def("convnet_l1_bwd", [](const at::Tensor& dp, const at::Tensor& y, const at::Tensor& x, const at::Tensor& saved,
@@ -221,13 +227,13 @@ void register_cuda_bindings(py::module_& m) {
     chk(dp, "dp"); chk(y, "y"); chk(x, "x"); chk(saved, "saved"); chk(dgamma, "dgamma"); chk(dbeta, "dbeta"); chk(dw, "dw");
     c10::cuda::CUDAGuard g(x.device());
     const int B = static_cast<int>(y.size(0));
-    TORCH_CHECK(dp.numel() == static_cast<int64_t>(B) * 3136 && x.numel() == static_cast<int64_t>(B) * 784 && dw.numel() == 400 &&
+    TORCH_CHECK(dp.numel() == static_cast<int64_t>(B) * 5184 && x.numel() == static_cast<int64_t>(B) * 784 && dw.numel() == 400 &&
                     dgamma.numel() == 16 && dbeta.numel() == 16, "convnet_l1_bwd: shape mismatch");
     ReduceScratch scr = scratch(x);
     launch_convnet_l1_bwd(dp.data_ptr<float>(), y.data_ptr<float>(), x.data_ptr<float>(), saved.data_ptr<float>(), opt_ptr(gamma, "gamma"),
                           opt_ptr(beta, "beta"), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), B,
                           scr.partials, scr.partials + static_cast<size_t>(B) * 64,
-                          GridSync{scr.counter + scr.counters - 2, scr.counter + scr.counters - 1}, cur_stream(x));
+                          GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x));
   });
   m.def("convnet_l2_fwd", [](const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> gamma,
                              c10::optional<at::Tensor> beta, c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
@@ -235,8 +241,8 @@ void register_cuda_bindings(py::module_& m) {
                              c10::optional<at::Tensor> fcb) {
     chk(x, "x"); chk(w, "w");
     c10::cuda::CUDAGuard g(x.device());
-    TORCH_CHECK(x.dim() == 4 && x.size(1) == 14 && x.size(2) == 14 && x.size(3) == 16 && w.numel() == 12800,
-                "convnet_l2_fwd: x [B,14,14,16] (NHWC) and w [32,16,5,5] expected");
+    TORCH_CHECK(x.dim() == 4 && x.size(1) == 18 && x.size(2) == 18 && x.size(3) == 16 && w.numel() == 12800,
+                "convnet_l2_fwd: x [B,18,18,16] (zero-haloed NHWC frame) and w [32,16,5,5] expected");
     const int B = static_cast<int>(x.size(0));
     TORCH_CHECK(fused_convnet_supported(B), "convnet_l2_fwd: batch ", B, " exceeds one CTA per SM");
     at::Tensor y = at::empty({B, 14, 14, 32}, x.options());
@@ -258,7 +264,7 @@ void register_cuda_bindings(py::module_& m) {
                           opt_mut(running_var, "running_var"), nbt_p, static_cast<float>(momentum), static_cast<float>(eps),
                           ncls ? fcw->data_ptr<float>() : nullptr, ncls ? opt_ptr(fcb, "fc bias") : nullptr,
                           ncls ? logits.data_ptr<float>() : nullptr, ncls, B, scr.partials,
-                          GridSync{scr.counter + scr.counters - 2, scr.counter + scr.counters - 1}, cur_stream(x));
+                          GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x));
     return py::make_tuple(out, y, saved, logits);
   });
   m.def("convnet_l2_bwd", [](const at::Tensor& dout, const at::Tensor& y, const at::Tensor& saved, c10::optional<at::Tensor> gamma,
@@ -268,14 +274,25 @@ void register_cuda_bindings(py::module_& m) {
     const int B = static_cast<int>(y.size(0));
     TORCH_CHECK(dout.numel() == static_cast<int64_t>(B) * 1568 && y.numel() == static_cast<int64_t>(B) * 6272 && w.numel() == 12800 &&
                     dgamma.numel() == 32 && dbeta.numel() == 32, "convnet_l2_bwd: shape mismatch");
-    at::Tensor dy = at::empty({B, 14, 14, 32}, y.options());
-    at::Tensor dx = at::empty({B, 14, 14, 16}, y.options());
+    at::Tensor dy = at::empty({B, 18, 18, 32}, y.options());
+    at::Tensor dx = at::empty({B, 18, 18, 16}, y.options());
+    at::Tensor dysum = at::empty({B, 32}, y.options());
     ReduceScratch scr = scratch(y);
     launch_convnet_l2_bwd(dout.data_ptr<float>(), y.data_ptr<float>(), saved.data_ptr<float>(), opt_ptr(gamma, "gamma"), opt_ptr(beta, "beta"),
-                          w.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dy.data_ptr<float>(), dx.data_ptr<float>(), B,
-                          scr.partials, GridSync{scr.counter + scr.counters - 2, scr.counter + scr.counters - 1}, cur_stream(y));
-    return py::make_tuple(dy, dx);
+                          w.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dy.data_ptr<float>(), dx.data_ptr<float>(),
+                          dysum.data_ptr<float>(), B, scr.partials, GridSync{scr.counter + 512, scr.counter + 520},
+                          cur_stream(y));
+    return py::make_tuple(dy, dx, dysum);
   });
+  m.def("conv5x5_wgrad_win", [](const at::Tensor& dy_pad, const at::Tensor& x_pad, const at::Tensor& dysum, at::Tensor dw, c10::optional<at::Tensor> db) {
+    chk(dy_pad, "dy_pad"); chk(x_pad, "x_pad"); chk(dysum, "dysum"); chk(dw, "dw");
+    c10::cuda::CUDAGuard g(dy_pad.device());
+    const int B = static_cast<int>(dy_pad.size(0));
+    TORCH_CHECK(dy_pad.numel() == static_cast<int64_t>(B) * 324 * 32 && x_pad.numel() == static_cast<int64_t>(B) * 324 * 16 &&
+                    dysum.numel() == static_cast<int64_t>(B) * 32 && dw.numel() == 12800, "conv5x5_wgrad_win: shape mismatch");
+    launch_conv5x5_wgrad_win(dy_pad.data_ptr<float>(), x_pad.data_ptr<float>(), dysum.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), B,
+                             scratch(dy_pad), cur_stream(dy_pad));
+  }, py::arg("dy_pad"), py::arg("x_pad"), py::arg("dysum"), py::arg("dw"), py::arg("db") = py::none());
 
   // ---- BN + ReLU + pool ------------------------------------------------------------------------------
   m.def("bn_relu_pool_fwd", [](const at::Tensor& y, const at::Tensor& stats, c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta,
@@ -408,14 +425,14 @@ void register_cuda_bindings(py::module_& m) {
                       dw.data_ptr<float>(), opt_mut(db, "db"), x.size(0), x.size(1), w.size(0), cur_stream(x));
     return dx;
   });
-  m.def("cross_entropy_fwd", [](const at::Tensor& logits, const at::Tensor& target) {
+  m.def("cross_entropy_fwd", [](const at::Tensor& logits, const at::Tensor& target, bool emit_grad) {
     chk(logits, "logits"); chk(target, "target", at::kLong);
     c10::cuda::CUDAGuard g(logits.device());
     at::Tensor loss = at::empty({}, logits.options()), probs = at::empty_like(logits);
     launch_cross_entropy_fwd(logits.data_ptr<float>(), reinterpret_cast<const long long*>(target.data_ptr<int64_t>()), loss.data_ptr<float>(),
-                             probs.data_ptr<float>(), logits.size(0), logits.size(1), cur_stream(logits));
-    return py::make_tuple(loss, probs);
-  });
+                             probs.data_ptr<float>(), logits.size(0), logits.size(1), cur_stream(logits), emit_grad);
+    return py::make_tuple(loss, probs);  // emit_grad: the second tensor is d(loss)/d(logits) for a unit incoming gradient
+  }, py::arg("logits"), py::arg("target"), py::arg("emit_grad") = false);
   m.def("cross_entropy_bwd", [](const at::Tensor& probs, const at::Tensor& target, const at::Tensor& dloss) {
     chk(probs, "probs"); chk(target, "target", at::kLong); chk(dloss, "dloss");
     c10::cuda::CUDAGuard g(probs.device());

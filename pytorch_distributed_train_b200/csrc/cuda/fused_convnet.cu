@@ -42,26 +42,56 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ void grid_barrier(GridSync gs) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int gen = ld_acquire_gpu(gs.gen);  // cannot advance before this CTA arrives
-    __threadfence();
-    const unsigned int prev = atomicAdd(gs.count, 1u);
-    if (prev == gridDim.x - 1) {
-      *gs.count = 0u;
-      __threadfence();
-      st_release_gpu(gs.gen, gen + 1u);
-    } else {
-      while (ld_acquire_gpu(gs.gen) == gen) {}
+// Grid barrier: one arrival counter, one monotonically increasing epoch word.  Thread 0 of a CTA arrives with a fence +
+// atomicAdd; the last arriver zeroes the counter and publishes the barrier's epoch; everybody else polls the epoch word
+// with *relaxed* loads (one poller per CTA; an acquire per spin would invalidate L1 every iteration).  Everything read
+// after the barrier comes from L2 (ld.global.cg), the GPU's coherence point, so no trailing fence is needed.  Each CTA
+// tracks the epoch locally (read once at kernel start, +1 per barrier): no read of the word before arriving, nothing to
+// reset between launches or CUDA-graph replays, any grid size.  A flag-per-CTA variant (every CTA polling every flag)
+// was measured at 5.5 µs per barrier against 2-3 µs for the counter: 10^4 pollers on four cache lines (profiles/r2).
+struct GridBar {
+  unsigned int e;
+  __device__ __forceinline__ explicit GridBar(GridSync gs) : e(*reinterpret_cast<volatile unsigned int*>(gs.epoch)) {}
+  __device__ __forceinline__ void sync(GridSync gs) {
+    ++e;
+    __syncthreads();   // the CTA's partial row is complete
+    if (threadIdx.x == 0) {
+      __threadfence();   // ... and performed at GPU scope before the arrival (bar.sync makes the fence cumulative over the CTA)
+      const unsigned int prev = atomicAdd(gs.flags, 1u);
+      if (prev == gridDim.x - 1) {
+        st_relaxed_gpu(gs.flags, 0u);
+        __threadfence();
+        st_relaxed_gpu(gs.epoch, e);
+      } else {
+        while (static_cast<int>(ld_relaxed_gpu(gs.epoch) - e) < 0) {}
+      }
     }
-    __threadfence();
+    __syncthreads();
   }
-  __syncthreads();
+  __device__ __forceinline__ void finish(GridSync) {}
+};
+
+// ---- optional phase trace (PDT_FUSED_TRACE=1): globaltimer stamps of thread 0 of every CTA, read back by tools ----------
+__device__ unsigned long long g_trace[4][160][12];
+__device__ int g_trace_on = 0;
+__device__ __forceinline__ void trace(int kernel, int phase) {
+  if (g_trace_on && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[kernel][blockIdx.x][phase] = t;
+  }
 }
 
 // Sum `rows` partial rows of `W` floats (written by other CTAs before a grid barrier) in a fixed order.
@@ -72,7 +102,13 @@ __device__ __forceinline__ void fold_rows(const float* __restrict__ partials, in
   if (tid < 4 * W) {
     const int col = tid % W, grp = tid / W;
     float s = 0.f;
-    for (int r = grp; r < rows; r += 4) s += __ldcg(partials + static_cast<size_t>(r) * W + col);
+    for (int r = grp; r < rows; r += 32) {   // eight independent L2 loads in flight, summed in a fixed order
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = (r + 4 * j < rows) ? __ldcg(partials + static_cast<size_t>(r + 4 * j) * W + col) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += t[j];
+    }
     s_tmp[grp * W + col] = s;
   }
   __syncthreads();
@@ -140,6 +176,8 @@ convnet_l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   __shared__ float s_scale[16], s_shift[16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
   const L1Map m(tid);
+  GridBar bar(gs);
+  trace(0, 0);
 
   l1_load_image(x + static_cast<size_t>(n) * 784, xs, tid);
   if (tid < 400) {
@@ -167,11 +205,7 @@ convnet_l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
       }
     }
   }
-  if (m.valid) {  // conv output is kept for the backward pass (BatchNorm needs x̂ at every position)
-    float4* yp = reinterpret_cast<float4*>(y + ((static_cast<size_t>(n) * 28 + m.r) * 28 + m.c) * 16);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) yp[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-  }
+  trace(0, 1);
   {
     float v[32];
 #pragma unroll
@@ -189,8 +223,11 @@ convnet_l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     for (int wi = 0; wi < kL1Warps; ++wi) s += red[wi * 32 + tid];
     partials[static_cast<size_t>(n) * 32 + tid] = s;
   }
-  grid_barrier(gs);
+  trace(0, 2);
+  bar.sync(gs);
+  trace(0, 3);
   fold_rows<32>(partials, B, s_tmp, s_tot);
+  trace(0, 4);
   if (tid < 16) {
     const float cnt = static_cast<float>(B) * 784.f;
     const float mean = s_tot[tid] / cnt;
@@ -225,13 +262,39 @@ convnet_l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     else if (m.d == 1) o = make_float4(z[4], z[5], z[6], z[7]);
     else if (m.d == 2) o = make_float4(z[8], z[9], z[10], z[11]);
     else o = make_float4(z[12], z[13], z[14], z[15]);
-    reinterpret_cast<float4*>(out + ((static_cast<size_t>(n) * 14 + m.ph) * 14 + m.pw) * 16)[m.d] = o;
+    reinterpret_cast<float4*>(out + ((static_cast<size_t>(n) * 18 + m.ph + 2) * 18 + m.pw + 2) * 16)[m.d] = o;
   }
+  // the 2-position halo of the frame is zero: layer 2 reads it as the convolution's zero padding (forward: one TMA box
+  // per image; weight gradient: overlapping-row TMA view), so nobody has to special-case the image border
+  for (int i = tid; i < 324 * 4; i += kL1Threads) {
+    const int P = i >> 2, pr = P / 18, pc = P - pr * 18;
+    if (pr < 2 || pr >= 16 || pc < 2 || pc >= 16) reinterpret_cast<float4*>(out + (static_cast<size_t>(n) * 324 + P) * 16)[i & 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (m.valid) {  // conv output is kept for the backward pass (BatchNorm needs x̂ at every position); stored last: nothing
+                  // in this kernel waits for these 50 KB per CTA, least of all the fence in front of the grid barrier
+    float4* yp = reinterpret_cast<float4*>(y + ((static_cast<size_t>(n) * 28 + m.r) * 28 + m.c) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) yp[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+  bar.finish(gs);
+  trace(0, 5);
 }
 
 // ---- layer 1 backward -------------------------------------------------------------------------------------------------
-// dynamic smem: dys [784][16] | fold [25 warps][26 lanes][16]
-constexpr int kL1BwdSmem = (784 * 16 + kL1Warps * 26 * 16) * 4;
+// dynamic smem: dys [784][16] | fold [25 warps][16 co][32 taps]
+constexpr int kL1BwdSmem = (784 * 16 + kL1Warps * 512) * 4;
+
+__device__ __forceinline__ uint32_t f32_to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+// D(16×8) += A(16×8, row) · B(8×8, col); fragments per the PTX ISA m16n8k8 .tf32 layout
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 __global__ void __launch_bounds__(kL1Threads, 1)
 convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ saved,
@@ -239,7 +302,7 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
                       float* partials, float* partials_w, GridSync gs) {
   extern __shared__ __align__(16) float dsm[];
   float* dys = dsm;                  // [784][16]
-  float* fold = dsm + 784 * 16;      // [25][26][16]
+  float* fold = dsm + 784 * 16;      // [25 warps][16][32]
   __shared__ float xs[32 * 32];
   __shared__ float red[kL1Warps * 32];
   __shared__ float s_tmp[4 * 32];
@@ -247,6 +310,8 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
   __shared__ float s_scale[16], s_shift[16], s_mean[16], s_invstd[16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
   const L1Map m(tid);
+  GridBar bar(gs);
+  trace(1, 0);
 
   l1_load_image(x + static_cast<size_t>(n) * 784, xs, tid);
   if (tid < 16) {
@@ -262,7 +327,7 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
   float yv[16], dz[16];
   {
     const float4* yp = reinterpret_cast<const float4*>(y + ((static_cast<size_t>(n) * 28 + m.r) * 28 + m.c) * 16);
-    const float4* gp = reinterpret_cast<const float4*>(dp + ((static_cast<size_t>(n) * 14 + m.ph) * 14 + m.pw) * 16);
+    const float4* gp = reinterpret_cast<const float4*>(dp + ((static_cast<size_t>(n) * 18 + m.ph + 2) * 18 + m.pw + 2) * 16);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 a = m.valid ? yp[q] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -310,8 +375,11 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     for (int wi = 0; wi < kL1Warps; ++wi) s += red[wi * 32 + tid];
     partials[static_cast<size_t>(n) * 32 + tid] = s;
   }
-  grid_barrier(gs);
+  trace(1, 1);
+  bar.sync(gs);
+  trace(1, 2);
   fold_rows<32>(partials, B, s_tmp, s_tot);  // [0..16) Σdz, [16..32) Σdz·x̂
+  trace(1, 3);
   if (n == 0 && tid < 16) {
     if (dbeta) dbeta[tid] = s_tot[tid];
     if (dgamma) dgamma[tid] = s_tot[16 + tid];
@@ -331,51 +399,88 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     }
   }
   __syncthreads();
-  // conv1 weight gradient of this image: lane = filter tap (lane 25 = the bias), warps split the pixels
+  // conv1 weight gradient of this image on the tensor cores: dW[co][tap] = Σ_px dy[px][co] · x[px + tap] is a
+  // 16 × 32 × 784 GEMM (taps 25..31 padded; tap 25 multiplies a column of ones → the bias gradient).  M = 16 is below
+  // tcgen05's minimum tile, so this is warp-level mma.sync m16n8k8 (TF32 in, fp32 accumulate): a warp takes every
+  // 25th group of 8 pixels, builds the A fragment from the staged dy and the four B fragments (8 taps each) straight
+  // from the haloed image — no im2col buffer — and the 25 per-warp 16×32 accumulators are folded through smem.
   {
-    float a[16];
+    const int g = lane >> 2, t4 = lane & 3;
+    float c[4][4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = 0.f;
-    if (lane < 26) {
-      const int kh = lane / 5, kw = lane - kh * 5;
-      for (int p = warp; p < 784; p += kL1Warps) {
-        const int pr = p / 28, pc = p - pr * 28;
-        const float xv = lane < 25 ? xs[(pr + kh) * 32 + pc + kw] : 1.f;
-        const float4* d4 = reinterpret_cast<const float4*>(dys + p * 16);
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 dv = d4[q];
-          a[4 * q + 0] = fmaf(xv, dv.x, a[4 * q + 0]);
-          a[4 * q + 1] = fmaf(xv, dv.y, a[4 * q + 1]);
-          a[4 * q + 2] = fmaf(xv, dv.z, a[4 * q + 2]);
-          a[4 * q + 3] = fmaf(xv, dv.w, a[4 * q + 3]);
-        }
+      for (int e = 0; e < 4; ++e) c[j][e] = 0.f;
+    int toff[4];   // offset of tap 8j + g inside the 32-wide haloed image; < 0: padding tap (25 = ones column)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tap = 8 * j + g;
+      toff[j] = tap < 25 ? (tap / 5) * 32 + tap % 5 : (tap == 25 ? -1 : -2);
+    }
+    for (int ks = warp; ks < 98; ks += kL1Warps) {
+      const int pa = ks * 8 + t4, pb = pa + 4;          // the two pixels (K indices) this lane touches
+      const int ia = (pa / 28) * 32 + pa % 28, ib = (pb / 28) * 32 + pb % 28;
+      uint32_t af[4];
+      af[0] = f32_to_tf32(dys[pa * 16 + g]);
+      af[1] = f32_to_tf32(dys[pa * 16 + g + 8]);
+      af[2] = f32_to_tf32(dys[pb * 16 + g]);
+      af[3] = f32_to_tf32(dys[pb * 16 + g + 8]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xa = toff[j] >= 0 ? xs[ia + toff[j]] : (toff[j] == -1 ? 1.f : 0.f);
+        const float xb = toff[j] >= 0 ? xs[ib + toff[j]] : (toff[j] == -1 ? 1.f : 0.f);
+        mma_m16n8k8_tf32(c[j], af, f32_to_tf32(xa), f32_to_tf32(xb));
       }
-      float4* f4 = reinterpret_cast<float4*>(fold + (warp * 26 + lane) * 16);
+    }
+    // C fragment: c[j][0..1] = (co g, taps 8j + 2·t4 + {0,1}), c[j][2..3] = (co g + 8, same taps)
+    float* wf = fold + warp * 512;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) f4[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+    for (int j = 0; j < 4; ++j) {
+      *reinterpret_cast<float2*>(wf + g * 32 + 8 * j + 2 * t4) = make_float2(c[j][0], c[j][1]);
+      *reinterpret_cast<float2*>(wf + (g + 8) * 32 + 8 * j + 2 * t4) = make_float2(c[j][2], c[j][3]);
     }
   }
-  __syncthreads();
-  if (tid < 416) {
-    float s = 0.f;
-#pragma unroll 5
-    for (int wi = 0; wi < kL1Warps; ++wi) s += fold[wi * 416 + tid];
-    partials_w[static_cast<size_t>(n) * 416 + tid] = s;   // index = tap·16 + co  (tap 25 = bias)
+  // bias gradient in full fp32 (its true value behind a BatchNorm is zero: TF32-rounded dy would leave 1e-4 of noise):
+  // thread = (channel, one of 32 pixel classes), partial sums parked in the unused tap columns 26..31 of warp 0's tile
+  float dbp = 0.f;
+  if (tid < 512) {
+    const int co = tid & 15, part = tid >> 4;
+    for (int p = part; p < 784; p += 32) dbp += dys[p * 16 + co];
   }
-  grid_barrier(gs);
-  // every CTA folds a few of the 416 outputs over the B partial rows: one warp per output, fixed order
-  for (int j = n + warp * B; j < 416; j += kL1Warps * B) {
+  __syncthreads();
+  float* s_db = red;   // [32 parts][16]  (the statistics scratch is free again)
+  if (tid < 512) s_db[tid] = dbp;
+  __syncthreads();
+  if (tid < 512) {
+    float sacc = 0.f;
+    if ((tid & 31) == 25) {
+      const int co = tid >> 5;
+#pragma unroll 8
+      for (int part = 0; part < 32; ++part) sacc += s_db[part * 16 + co];
+    } else {
+#pragma unroll 5
+      for (int wi = 0; wi < kL1Warps; ++wi) sacc += fold[wi * 512 + tid];
+    }
+    partials_w[static_cast<size_t>(n) * 512 + tid] = sacc;   // index = co·32 + tap  (tap 25 = bias, 26..31 unused)
+  }
+  trace(1, 4);
+  bar.sync(gs);
+  trace(1, 5);
+  // every CTA folds a few of the 16 × 26 outputs over the B partial rows: one warp per output, fixed order
+  for (int j = n + warp * B; j < 512; j += kL1Warps * B) {
+    const int co = j >> 5, tap = j & 31;
+    if (tap > 25) continue;
     float s = 0.f;
-    for (int r = lane; r < B; r += 32) s += __ldcg(partials_w + static_cast<size_t>(r) * 416 + j);
+    for (int r = lane; r < B; r += 32) s += __ldcg(partials_w + static_cast<size_t>(r) * 512 + j);
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) {
-      const int tap = j >> 4, co = j & 15;
       if (tap < 25) dw[co * 25 + tap] = s;
       else if (db) db[co] = s;
     }
   }
+  bar.finish(gs);
+  trace(1, 6);
 }
 
 // =====================================================================================================================
@@ -422,6 +527,8 @@ convnet_l2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
 
+  GridBar bar(gs);
+  trace(2, 0);
   if (tid == 0) {
     tma_prefetch_desc(&tm_x);
     mbar_init(&bar_x, 1);
@@ -437,32 +544,48 @@ convnet_l2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
   const uint32_t tmem_base = tmem_slot;
   if (tid == 0) {
     mbar_arrive_expect_tx(&bar_x, kPatchBytes);
-    tma_load_4d(sa, &tm_x, &bar_x, 0, -2, -2, n);      // channels ≥ 16 and the 2-pixel halo: out-of-bounds zero fill
+    tma_load_4d(sa, &tm_x, &bar_x, 0, 0, 0, n);        // the frame carries its zero halo; channels ≥ 16: out-of-bounds zero fill
   }
   // B[tap][co][ci] = w[co][ci][tap], K-major rows of 128 B, SWIZZLE_128B
-  for (int i = tid; i < 32 * 16 * 25; i += kL2Threads) {
-    const int co = i / 400, rem = i - co * 400, ci = rem / 25, tap = rem - ci * 25;
-    *reinterpret_cast<float*>(sb + tap * 4096 + sw128_off(co, ci >> 2) + (ci & 3) * 4) = w[i];
+  {
+    // thread = two (co, ci) pairs; a pair's 25 taps are contiguous in w (a warp reads 3,200 contiguous bytes) and land
+    // 4,096 B apart in smem (one swizzled K-major tile per tap): all 50 loads are in flight before the first store
+    float wv[2][25];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float* src = w + (tid + j * kL2Threads) * 25;
+#pragma unroll
+      for (int tap = 0; tap < 25; ++tap) wv[j][tap] = __ldg(src + tap);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int pair = tid + j * kL2Threads, co = pair >> 4, ci = pair & 15;
+      uint8_t* dst = sb + sw128_off(co, ci >> 2) + (ci & 3) * 4;
+#pragma unroll
+      for (int tap = 0; tap < 25; ++tap) *reinterpret_cast<float*>(dst + tap * 4096) = wv[j][tap];
+    }
   }
   fence_proxy_async_smem();   // generic-proxy writes of B → visible to the tensor core
   __syncthreads();
+  trace(2, 1);
   if (warp == 0) {
     mbar_wait(&bar_x, 0);
     tc_fence_after();
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
-      const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sb);
+      // the start-address field is the low 14 bits (bytes >> 4): a descriptor is advanced by plain integer adds
+      const uint64_t ad0 = umma_desc_kmajor<128>(smem_u32(sa)), bd0 = umma_desc_kmajor<128>(smem_u32(sb));
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
 #pragma unroll 1
         for (int kh = 0; kh < 5; ++kh) {
+          const uint64_t ad = ad0 + static_cast<uint64_t>(((7 * t + kh) * kPW * 128) >> 4);
+          const uint64_t bd = bd0 + static_cast<uint64_t>((kh * 5 * 4096) >> 4);
 #pragma unroll
           for (int kw = 0; kw < 5; ++kw) {
-            const uint32_t arow = a0 + static_cast<uint32_t>((7 * t + kh) * kPW + kw) * 128u;
-            const uint32_t brow = b0 + static_cast<uint32_t>(kh * 5 + kw) * 4096u;
 #pragma unroll
             for (int k = 0; k < 2; ++k)   // K = 16 input channels = two K=8 steps; the zero upper half is never multiplied
-              umma_tf32(tmem_base + t * 32, umma_desc_kmajor<128>(arow + k * 32), umma_desc_kmajor<128>(brow + k * 32), idesc, (kh | kw | k) != 0);
+              umma_tf32(tmem_base + t * 32, ad + ((kw * 128 + k * 32) >> 4), bd + ((kw * 4096 + k * 32) >> 4), idesc, (kh | kw | k) != 0);
           }
         }
       }
@@ -489,13 +612,11 @@ convnet_l2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
       }
       if (rr < 126 && ow < 14) {
         const int oh = 7 * t + orow, pix = oh * 14 + ow;
-        float4* yg = reinterpret_cast<float4*>(y + (static_cast<size_t>(n) * 196 + pix) * 32);
         float4* yl = reinterpret_cast<float4*>(ys + pix * 32);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           if (bias) { o.x += __ldg(bias + 4 * q); o.y += __ldg(bias + 4 * q + 1); o.z += __ldg(bias + 4 * q + 2); o.w += __ldg(bias + 4 * q + 3); }
-          yg[q] = o;
           yl[(q + pix) & 7] = o;   // rotate the 16-byte chunks by the pixel index: conflict-free column reads below
         }
       }
@@ -503,6 +624,7 @@ convnet_l2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
     tc_fence_before();
   }
   __syncthreads();
+  trace(2, 2);
   // ---- per-channel Σy, Σy² of this image: thread = (channel, quarter of the pixels) --------------------------------------
   if (tid < 128) {
     const int c = tid & 31, part = tid >> 5;
@@ -517,8 +639,16 @@ convnet_l2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
   }
   __syncthreads();
   if (tid < 64) partials[static_cast<size_t>(n) * 64 + tid] = (s_part[tid] + s_part[64 + tid]) + (s_part[128 + tid] + s_part[192 + tid]);
-  grid_barrier(gs);
+  trace(2, 3);
+  bar.sync(gs);
+  trace(2, 4);
+  // conv output → global (kept for backward), after the barrier: un-rotate the 16-byte chunks on the way out
+  for (int i = tid; i < 196 * 8; i += kL2Threads) {
+    const int pix = i >> 3, q = i & 7;
+    reinterpret_cast<float4*>(y + (static_cast<size_t>(n) * 196 + pix) * 32)[q] = reinterpret_cast<const float4*>(ys + pix * 32)[(q + pix) & 7];
+  }
   fold_rows<64>(partials, B, s_tmp, s_tot);
+  trace(2, 5);
   if (tid < 32) {
     const float cnt = static_cast<float>(B) * 196.f;
     const float mean = s_tot[tid] / cnt;
@@ -554,8 +684,43 @@ convnet_l2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
   }
   __syncthreads();
   for (int i = tid; i < 1568; i += kL2Threads) out[static_cast<size_t>(n) * 1568 + i] = pool[i];
+  trace(2, 6);
   // ---- classifier head riding on the pooled activations still in shared memory: logits = fc(pool) ----------------------
-  if (logits != nullptr) {
+  if (logits != nullptr && ncls <= 16) {
+    // thread t owns features t, t+256, … (≤ 7) for every class: all weight loads are independent and in flight together
+    float pv[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) pv[j] = (tid + j * kL2Threads < 1568) ? pool[tid + j * kL2Threads] : 0.f;
+    float accv[16];
+#pragma unroll
+    for (int c16 = 0; c16 < 16; ++c16) {
+      float sacc = 0.f;
+      if (c16 < ncls) {
+        const float* wr = fcw + static_cast<size_t>(c16) * 1568 + tid;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+          if (tid + j * kL2Threads < 1568) sacc = fmaf(pv[j], __ldg(wr + j * kL2Threads), sacc);
+      }
+      accv[c16] = sacc;
+    }
+#pragma unroll
+    for (int c16 = 0; c16 < 16; ++c16) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) accv[c16] += __shfl_xor_sync(0xffffffffu, accv[c16], off);
+    }
+    float* s_fc = s_part;   // [8 warps][16]
+    if (lane == 0) {
+#pragma unroll
+      for (int c16 = 0; c16 < 16; ++c16) s_fc[warp * 16 + c16] = accv[c16];
+    }
+    __syncthreads();
+    if (tid < ncls) {
+      float sfin = fcb ? fcb[tid] : 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) sfin += s_fc[w8 * 16 + tid];
+      logits[static_cast<size_t>(n) * ncls + tid] = sfin;
+    }
+  } else if (logits != nullptr) {
     // warp k computes classes k, k+8, ...: 1568-long dot products, lanes stride the features
     for (int cls = warp; cls < ncls; cls += kL2Threads / 32) {
       const float* wr = fcw + static_cast<size_t>(cls) * 1568;
@@ -569,6 +734,8 @@ convnet_l2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
 
   tc_fence_before();
   __syncthreads();
+  bar.finish(gs);
+  trace(2, 7);
   if (warp == 1) tmem_dealloc<64>(tmem_base);
 }
 
@@ -581,8 +748,9 @@ struct L2BwdSmem {
 __global__ void __launch_bounds__(kL2Threads, 1)
 convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float* __restrict__ y /*[B,14,14,32]*/,
                       const float* __restrict__ saved, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      const float* __restrict__ w, float* dgamma, float* dbeta, float* __restrict__ dy /*[B,14,14,32]*/,
-                      float* __restrict__ dx /*[B,14,14,16]*/, float* partials, GridSync gs) {
+                      const float* __restrict__ w, float* dgamma, float* dbeta, float* __restrict__ dy /*[B,18,18,32] zero-haloed frame*/,
+                      float* __restrict__ dx /*[B,18,18,16] frame, interior written*/, float* __restrict__ dysum /*[B,32]*/,
+                      float* partials, GridSync gs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sa = smem;                                  // dy patch, written by the CTA in the TMA/UMMA SWIZZLE_128B layout
@@ -599,6 +767,8 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
 
+  GridBar bar(gs);
+  trace(3, 0);
   if (tid == 0) {
     mbar_init(&bar_mma, 1);
     fence_mbar_init();
@@ -614,14 +784,27 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
     s_shift[tid] = b - mean * g * invstd;
   }
   // Bd[tap][ci][co] = w[co][ci][24 − tap]: the data gradient is a correlation with the flipped filter
-  for (int i = tid; i < 32 * 16 * 25; i += kL2Threads) {
-    const int co = i / 400, rem = i - co * 400, ci = rem / 25, tap = 24 - (rem - ci * 25);
-    *reinterpret_cast<float*>(sb + tap * 2048 + sw128_off(ci, co >> 2) + (co & 3) * 4) = w[i];
+  {
+    float wv[2][25];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float* src = w + (tid + j * kL2Threads) * 25;
+#pragma unroll
+      for (int tap = 0; tap < 25; ++tap) wv[j][tap] = __ldg(src + tap);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int pair = tid + j * kL2Threads, co = pair >> 4, ci = pair & 15;
+      uint8_t* dst = sb + sw128_off(ci, co >> 2) + (co & 3) * 4;
+#pragma unroll
+      for (int tap = 0; tap < 25; ++tap) *reinterpret_cast<float*>(dst + (24 - tap) * 2048) = wv[j][tap];
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  trace(3, 1);
 
   // thread = (channel c, window group g): windows pp = g, g+8, ... (≤ 7 per thread); y values stay in registers
   const int c = tid & 31, g = tid >> 5;
@@ -662,8 +845,11 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
     for (int q = 0; q < 8; ++q) s += s_part[q * 64 + tid];
     partials[static_cast<size_t>(n) * 64 + tid] = s;
   }
-  grid_barrier(gs);
+  trace(3, 2);
+  bar.sync(gs);
+  trace(3, 3);
   fold_rows<64>(partials, B, s_tmp, s_tot);
+  trace(3, 4);
   if (n == 0 && tid < 32) {
     if (dbeta) dbeta[tid] = s_tot[tid];
     if (dgamma) dgamma[tid] = s_tot[32 + tid];
@@ -671,6 +857,7 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
   {
     const float inv_cnt = 1.f / (static_cast<float>(B) * 196.f);
     const float m1 = s_tot[c] * inv_cnt, m2 = s_tot[32 + c] * inv_cnt;
+    float dsum = 0.f;
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
       const int pp = g + 8 * k;
@@ -681,31 +868,45 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
           const int oh = 2 * ph + (d >> 1), ow = 2 * pw + (d & 1);
           const float xh = (yv[k][d] - mu) * is;
           const float v = sc * ((d == arg[k] ? dzv[k] : 0.f) - m1 - xh * m2);
-          dy[(static_cast<size_t>(n) * 196 + oh * 14 + ow) * 32 + c] = v;           // kept for the weight-gradient kernel
           const int P = (oh + 2) * kPW + ow + 2;
-          *reinterpret_cast<float*>(sa + sw128_off(P, c >> 2) + (c & 3) * 4) = v;   // haloed patch for the data-gradient MMAs
+          dy[(static_cast<size_t>(n) * 324 + P) * 32 + c] = v;                      // frame for the weight-gradient kernel (TMA)
+          *reinterpret_cast<float*>(sa + sw128_off(P, c >> 2) + (c & 3) * 4) = v;   // same frame in smem for the data-gradient MMAs
+          dsum += v;
         }
       }
     }
+    s_part[g * 64 + c] = dsum;
+  }
+  // zero halo of the global dy frame (the weight gradient sums over all 324 positions)
+  for (int i = tid; i < 324 * 8; i += kL2Threads) {
+    const int P = i >> 3, pr = P / 18, pc = P - pr * 18;
+    if (pr < 2 || pr >= 16 || pc < 2 || pc >= 16) reinterpret_cast<float4*>(dy + (static_cast<size_t>(n) * 324 + P) * 32)[i & 7] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   fence_proxy_async_smem();
   __syncthreads();
+  if (tid < 32) {   // Σdy of this image per channel: the conv2 bias gradient is the sum of these rows
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += s_part[q * 64 + tid];
+    dysum[static_cast<size_t>(n) * 32 + tid] = s;
+  }
+  trace(3, 5);
   if (warp == 0) {
     tc_fence_after();
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_tf32(128, 16);
-      const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sb);
+      const uint64_t ad0 = umma_desc_kmajor<128>(smem_u32(sa)), bd0 = umma_desc_kmajor<128>(smem_u32(sb));
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
 #pragma unroll 1
         for (int kh = 0; kh < 5; ++kh) {
+          const uint64_t ad = ad0 + static_cast<uint64_t>(((7 * t + kh) * kPW * 128) >> 4);
+          const uint64_t bd = bd0 + static_cast<uint64_t>((kh * 5 * 2048) >> 4);
 #pragma unroll
           for (int kw = 0; kw < 5; ++kw) {
-            const uint32_t arow = a0 + static_cast<uint32_t>((7 * t + kh) * kPW + kw) * 128u;
-            const uint32_t brow = b0 + static_cast<uint32_t>(kh * 5 + kw) * 2048u;
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // K = 32 output channels = four K=8 steps
-              umma_tf32(tmem_base + t * 16, umma_desc_kmajor<128>(arow + k * 32), umma_desc_kmajor<128>(brow + k * 32), idesc, (kh | kw | k) != 0);
+              umma_tf32(tmem_base + t * 16, ad + ((kw * 128 + k * 32) >> 4), bd + ((kw * 2048 + k * 32) >> 4), idesc, (kh | kw | k) != 0);
           }
         }
       }
@@ -724,7 +925,7 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
       float v[16];
       tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + t * 16, v);
       if (rr < 126 && ow < 14) {
-        float4* o = reinterpret_cast<float4*>(dx + (static_cast<size_t>(n) * 196 + (7 * t + orow) * 14 + ow) * 16);
+        float4* o = reinterpret_cast<float4*>(dx + (static_cast<size_t>(n) * 324 + (7 * t + orow + 2) * 18 + ow + 2) * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
@@ -733,6 +934,8 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
   }
   tc_fence_before();
   __syncthreads();
+  bar.finish(gs);
+  trace(3, 6);
   if (warp == 1) tmem_dealloc<32>(tmem_base);
 }
 
@@ -785,7 +988,7 @@ CUtensorMap make_patch_map(const float* base, int C, int W, int H, int N) {
   CUtensorMap m;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4, static_cast<cuuint64_t>(H) * W * C * 4};
-  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(W + 4), static_cast<cuuint32_t>(H + 4), 1};
+  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(W), static_cast<cuuint32_t>(H), 1};   // the whole (already haloed) frame
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = driver().cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -797,6 +1000,20 @@ CUtensorMap make_patch_map(const float* base, int C, int W, int H, int N) {
 }  // namespace
 
 bool fused_convnet_supported(int B) { return B >= 1 && B <= sm_count(); }
+
+void fused_convnet_trace_enable(bool on) {
+  const int v = on ? 1 : 0;
+  PDT_CUDA_CHECK(cudaMemcpyToSymbol(g_trace_on, &v, sizeof(v)));
+  if (on) {
+    void* p = nullptr;
+    PDT_CUDA_CHECK(cudaGetSymbolAddress(&p, g_trace));
+    PDT_CUDA_CHECK(cudaMemset(p, 0, sizeof(unsigned long long) * 4 * 160 * 12));
+  }
+}
+void fused_convnet_trace_read(unsigned long long* host /*[4][160][12]*/) {
+  PDT_CUDA_CHECK(cudaDeviceSynchronize());
+  PDT_CUDA_CHECK(cudaMemcpyFromSymbol(host, g_trace, sizeof(unsigned long long) * 4 * 160 * 12));
+}
 
 void launch_convnet_l1_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float* y, float* out,
                            float* saved, float* running_mean, float* running_var, long long* nbt, float momentum, float eps, int B,
@@ -815,15 +1032,16 @@ void launch_convnet_l1_bwd(const float* dp, const float* y, const float* x, cons
 void launch_convnet_l2_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float* y, float* out,
                            float* saved, float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
                            const float* fcw, const float* fcb, float* logits, int ncls, int B, float* partials, GridSync gs, cudaStream_t st) {
-  CUtensorMap tm_x = make_patch_map(x, 16, 14, 14, B);
+  CUtensorMap tm_x = make_patch_map(x, 16, 18, 18, B);
   launch_coop(convnet_l2_fwd_kernel, B, kL2Threads, static_cast<size_t>(L2FwdSmem::kTotal), st, "convnet_l2_fwd", tm_x, w, bias, gamma, beta, y, out,
               saved, running_mean, running_var, nbt, momentum, eps, fcw, fcb, logits, ncls, partials, gs);
 }
 
 void launch_convnet_l2_bwd(const float* dout, const float* y, const float* saved, const float* gamma, const float* beta, const float* w,
-                           float* dgamma, float* dbeta, float* dy, float* dx, int B, float* partials, GridSync gs, cudaStream_t st) {
+                           float* dgamma, float* dbeta, float* dy, float* dx, float* dysum, int B, float* partials, GridSync gs,
+                           cudaStream_t st) {
   launch_coop(convnet_l2_bwd_kernel, B, kL2Threads, static_cast<size_t>(L2BwdSmem::kTotal), st, "convnet_l2_bwd", dout, y, saved, gamma, beta, w, dgamma,
-              dbeta, dy, dx, partials, gs);
+              dbeta, dy, dx, dysum, partials, gs);
 }
 
 }  // namespace pdt

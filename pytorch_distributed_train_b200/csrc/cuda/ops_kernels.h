@@ -70,7 +70,9 @@ void launch_linear_fwd(const float* x, const float* w, const float* b, float* ou
 void launch_linear_bwd(const float* dout, const float* x, const float* w, float* dx, float* dw, float* db, int B, int K, int N,
                        cudaStream_t st);
 // loss (scalar, mean over B) and probs[B,C] (softmax, kept for backward)
-void launch_cross_entropy_fwd(const float* logits, const long long* target, float* loss, float* probs, int B, int C, cudaStream_t st);
+// emit_grad: `probs` receives (softmax − onehot)/B instead (the backward of a mean loss with unit incoming gradient)
+void launch_cross_entropy_fwd(const float* logits, const long long* target, float* loss, float* probs, int B, int C, cudaStream_t st,
+                              bool emit_grad = false);
 // dlogits = (probs - onehot) * (*dloss) / B
 void launch_cross_entropy_bwd(const float* probs, const long long* target, const float* dloss, float* dlogits, int B, int C,
                               cudaStream_t st);

@@ -691,11 +691,20 @@ __global__ void __launch_bounds__(256) linear_bwd_kernel(const float* __restrict
     for (int i = threadIdx.x; i < nb * N; i += blockDim.x) s_d[i] = dout[static_cast<size_t>(b0) * N + i];
     __syncthreads();
     if (k < K) {
-      for (int b = warp; b < nb; b += 8) {
-        const float xv = x[static_cast<size_t>(b0 + b) * K + k];
+      float xv[BC / 8];   // this warp's rows of the chunk: every load is issued before the first FMA needs one
 #pragma unroll
-        for (int n = 0; n < NMAX; ++n)
-          if (n < N) acc[n] = fmaf(xv, s_d[b * N + n], acc[n]);
+      for (int j = 0; j < BC / 8; ++j) {
+        const int b = warp + 8 * j;
+        xv[j] = b < nb ? x[static_cast<size_t>(b0 + b) * K + k] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < BC / 8; ++j) {
+        const int b = warp + 8 * j;
+        if (b < nb) {
+#pragma unroll
+          for (int n = 0; n < NMAX; ++n)
+            if (n < N) acc[n] = fmaf(xv[j], s_d[b * N + n], acc[n]);
+        }
       }
     }
     if (static_cast<int>(blockIdx.x) == dx_blocks && threadIdx.x < N)
@@ -718,9 +727,12 @@ __global__ void __launch_bounds__(256) linear_bwd_kernel(const float* __restrict
   if (db && static_cast<int>(blockIdx.x) == dx_blocks && threadIdx.x < N) db[threadIdx.x] = bsum;
 }
 
+// emit_grad: write d(loss)/d(logits) = (softmax − onehot)/B instead of the softmax — the whole backward of a mean
+// cross-entropy whose incoming gradient is 1, produced by the forward launch (the backward kernel disappears).
 __global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
-                                                                float* loss, float* __restrict__ probs, int B, int C) {
+                                                                float* loss, float* __restrict__ probs, int B, int C, int emit_grad) {
   float local = 0.f;
+  const float invB = 1.f / static_cast<float>(B);
   for (int r = threadIdx.x; r < B; r += blockDim.x) {
     const float* l = logits + static_cast<size_t>(r) * C;
     float m = l[0];
@@ -728,8 +740,11 @@ __global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(const float* __r
     float s = 0.f;
     for (int c = 0; c < C; ++c) s += __expf(l[c] - m);
     const float inv = 1.f / s, lse = m + __logf(s);
-    for (int c = 0; c < C; ++c) probs[static_cast<size_t>(r) * C + c] = __expf(l[c] - m) * inv;
     const long long t = target[r];
+    for (int c = 0; c < C; ++c) {
+      const float p = __expf(l[c] - m) * inv;
+      probs[static_cast<size_t>(r) * C + c] = emit_grad ? (p - (t == c ? 1.f : 0.f)) * invB : p;
+    }
     if (t >= 0 && t < C) local += lse - l[t];
   }
   // fixed-order block reduction (deterministic)
@@ -954,8 +969,9 @@ void launch_linear_bwd(const float* dout, const float* x, const float* w, float*
   linear_bwd_kernel<16><<<B + dw_blocks, 256, 128 * N * sizeof(float), st>>>(dout, x, w, dx, dw, db, B, K, N, B);
   check_launch("linear_bwd");
 }
-void launch_cross_entropy_fwd(const float* logits, const long long* target, float* loss, float* probs, int B, int C, cudaStream_t st) {
-  cross_entropy_fwd_kernel<<<1, 256, 0, st>>>(logits, target, loss, probs, B, C);
+void launch_cross_entropy_fwd(const float* logits, const long long* target, float* loss, float* probs, int B, int C, cudaStream_t st,
+                              bool emit_grad) {
+  cross_entropy_fwd_kernel<<<1, 256, 0, st>>>(logits, target, loss, probs, B, C, emit_grad ? 1 : 0);
   check_launch("cross_entropy_fwd");
 }
 void launch_cross_entropy_bwd(const float* probs, const long long* target, const float* dloss, float* dlogits, int B, int C,

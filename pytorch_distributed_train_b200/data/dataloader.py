@@ -12,6 +12,10 @@ B200-first changes (the host must keep a ~20 µs training step fed):
 * **pinned batches**: every batch is copied into a fresh pinned tensor from torch's event-tracked caching host
   allocator (a free-list pop after warm-up), so a consumer that runs ahead of the GPU can never see a batch
   overwritten under a pending H2D copy;
+* **native stager**: tensor-backed datasets (``native_source()``: MNIST, SyntheticMNIST) are batched by a C++ worker
+  thread (``_C.BatchStager``) that gathers the sampler's order, applies ToTensor's 1/255 and writes into a ring of
+  pinned buffers allocated once; a slot is reused only after the consumer's H2D copies out of it have completed (CUDA
+  event) and nobody holds the batch any more;
 * **prefetch thread**: optional background producer (``prefetch=k``) so batch *i+1* is being
   assembled while step *i* runs;
 * :class:`DevicePrefetcher` overlaps the H2D copy of batch *i+1* with compute of batch *i* on a
@@ -26,6 +30,12 @@ from typing import Any, Callable, Iterator, List, Optional, Sequence
 import torch
 
 from .sampler import BatchSampler, RandomSampler, SequentialSampler
+
+
+def _native_mod():
+    from .. import _C
+
+    return _C
 
 
 def default_collate(batch: Sequence[Any]):
@@ -64,6 +74,10 @@ def _map_tensors(obj, fn):
     return obj
 
 
+_WARM_POOL: set = set()
+_WARM_BLOCKS = 24
+
+
 def _pin_batch(batch):
     """Copy a batch into *fresh* pinned tensors from torch's caching host allocator.
 
@@ -78,6 +92,15 @@ def _pin_batch(batch):
     def pin(t: torch.Tensor):
         if t.is_pinned():
             return t
+        sig = (tuple(t.shape), t.dtype)
+        if sig not in _WARM_POOL:
+            # Pre-warm the allocator's free list for this batch signature: a pool miss later means cudaHostAlloc, which
+            # was measured stalling the loader for 40-80 ms in the middle of a run (profiles/r2/e2e_stalls.md).  A block
+            # is recycled only after the H2D copy out of it has completed, so a consumer that runs several steps ahead of
+            # the GPU keeps a dozen blocks of each kind in flight.
+            _WARM_POOL.add(sig)
+            warm = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for _ in range(_WARM_BLOCKS)]
+            del warm
         buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         buf.copy_(t)
         return buf
@@ -89,7 +112,7 @@ class DataLoader:
     def __init__(self, dataset, batch_size: Optional[int] = 1, shuffle: bool = False, sampler=None,
                  batch_sampler=None, num_workers: int = 0, collate_fn: Optional[Callable] = None,
                  pin_memory: bool = False, drop_last: bool = False, prefetch: int = 0,
-                 generator: Optional[torch.Generator] = None):
+                 generator: Optional[torch.Generator] = None, native: Optional[bool] = None):
         if num_workers != 0:
             # worker *processes* are not needed for tensor-backed datasets; a thread prefetcher is
             # what keeps up with a graph-replayed step. Map the knob instead of failing.
@@ -98,6 +121,7 @@ class DataLoader:
             raise ValueError("sampler option is mutually exclusive with shuffle")
         if batch_sampler is not None and (batch_size not in (1, None) or shuffle or sampler is not None or drop_last):
             raise ValueError("batch_sampler option is mutually exclusive with batch_size, shuffle, sampler, and drop_last")
+        own_batching = batch_sampler is None   # the loader batches the sampler itself (a user batch_sampler owns the grouping)
         self.dataset = dataset
         self.batch_size = batch_size
         self.drop_last = drop_last
@@ -111,6 +135,16 @@ class DataLoader:
         self.sampler = sampler
         self.batch_sampler = batch_sampler
         self._can_gather = collate_fn is None and hasattr(dataset, "gather")
+        # native path: a C++ worker thread stages batches into a pinned ring (no GIL, no intra-op thread pool, no
+        # allocator traffic in steady state); needs a tensor-backed dataset and the default collation
+        self._native = None
+        self._native_src = None
+        if collate_fn is None and own_batching and self.batch_size is not None and hasattr(dataset, "native_source") and native is not False:
+            src = dataset.native_source()
+            if src is not None and hasattr(_native_mod(), "BatchStager"):
+                self._native_src = src
+        if native is True and self._native_src is None:
+            raise ValueError("DataLoader(native=True) needs a dataset with native_source() and the default collate_fn / batch sampler")
 
     def __len__(self) -> int:
         return len(self.batch_sampler) if self.batch_sampler is not None else len(self.sampler)
@@ -166,7 +200,24 @@ class DataLoader:
                 except queue.Empty:
                     th.join(0.01)
 
+    def _iter_native(self) -> Iterator:
+        src = self._native_src
+        if self._native is None:
+            pin = bool(self.pin_memory and torch.cuda.is_available())
+            dev = torch.cuda.current_device() if pin else -1
+            self._native = _native_mod().BatchStager(src["data"], src["targets"], list(src["sample_shape"]), int(self.batch_size),
+                                                     bool(self.drop_last), float(src["scale"]), max(8, self.prefetch + 4), pin, dev)
+        order = torch.as_tensor(list(iter(self.sampler)), dtype=torch.int64)   # the sampler decides the epoch's order, once
+        self._native.start(order)
+        while True:
+            item = self._native.next()
+            if item is None:
+                return
+            yield item
+
     def __iter__(self) -> Iterator:
+        if self._native_src is not None:
+            return self._iter_native()
         if self.prefetch > 0 and self.batch_sampler is not None:
             return self._iter_prefetch()
         return self._iter_sync()

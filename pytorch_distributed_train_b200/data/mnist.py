@@ -10,10 +10,11 @@ idx-ubyte archives and converts every sample through PIL on the training thread
 * samples stay a uint8 tensor; ``__getitem__`` yields what ``ToTensor`` would
   (float32 ``[1,28,28]`` in ``[0,1]``, int label) and ``gather(indices)`` builds a whole batch
   with one ``index_select`` + one cast;
-* ``download=True`` cannot reach the network on the GPU boxes, so when the files are missing it
-  raises with instructions — or, with ``synthetic_fallback=True``, writes deterministic
-  synthetic idx files of the real shape (60000/10000 × 28×28) so the full file-parsing path
-  still runs.
+* ``download=True`` fetches the four archives from the mirrors torchvision uses and verifies their md5 sums
+  (tv datasets/mnist.py:37-47,174-197) — when a network is reachable.  The GPU boxes of this project have none, so a
+  short connectivity probe decides: unreachable + ``synthetic_fallback=True`` writes deterministic synthetic idx files
+  of the real shape (60000/10000 × 28×28) so the full file-parsing path still runs; unreachable without the fallback
+  raises with instructions.
 """
 from __future__ import annotations
 
@@ -28,6 +29,76 @@ _FILES = {
     True: ("train-images-idx3-ubyte", "train-labels-idx1-ubyte", 60000),
     False: ("t10k-images-idx3-ubyte", "t10k-labels-idx1-ubyte", 10000),
 }
+
+
+# mirrors and checksums of the reference's dataset (torchvision.datasets.MNIST)
+_MIRRORS = ("https://ossci-datasets.s3.amazonaws.com/mnist/", "http://yann.lecun.com/exdb/mnist/")
+_MD5 = {
+    "train-images-idx3-ubyte.gz": "f68b3c2dcbeaaa9fbdd348bbdeb94873",
+    "train-labels-idx1-ubyte.gz": "d53e105ee54ea40749a09fcbcd1e9432",
+    "t10k-images-idx3-ubyte.gz": "9fb629c4189551a2d022fa330f9573f3",
+    "t10k-labels-idx1-ubyte.gz": "ec29112dd5afa0611ce80d1b7f02629c",
+}
+
+
+def _md5(path: str) -> str:
+    import hashlib
+
+    h = hashlib.md5()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 20), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
+def network_reachable(timeout: float = 2.0) -> bool:
+    """Cheap probe (one TCP connect) so an offline box fails in seconds, not after urllib's retries."""
+    import socket
+
+    for host, port in (("ossci-datasets.s3.amazonaws.com", 443), ("yann.lecun.com", 80)):
+        try:
+            with socket.create_connection((host, port), timeout=timeout):
+                return True
+        except OSError:
+            continue
+    return False
+
+
+def download_mnist(root: str, timeout: float = 30.0) -> bool:
+    """Fetch + verify the four MNIST archives into ``root/MNIST/raw`` (ref: ddp_example.py:66-69 ``download=True``).
+    Returns False when no network is reachable; raises if a download is corrupt."""
+    import urllib.request
+
+    raw = os.path.join(root, "MNIST", "raw")
+    missing = [n for n in _MD5 if not (os.path.exists(os.path.join(raw, n)) and _md5(os.path.join(raw, n)) == _MD5[n])
+               and not os.path.exists(os.path.join(raw, n[:-3]))]
+    if not missing:
+        return True
+    if not network_reachable():
+        return False
+    os.makedirs(raw, exist_ok=True)
+    for name in missing:
+        dst, err = os.path.join(raw, name), None
+        for mirror in _MIRRORS:
+            try:
+                tmp = dst + f".part{os.getpid()}"
+                with urllib.request.urlopen(mirror + name, timeout=timeout) as r, open(tmp, "wb") as f:
+                    while True:
+                        chunk = r.read(1 << 16)
+                        if not chunk:
+                            break
+                        f.write(chunk)
+                if _md5(tmp) != _MD5[name]:
+                    os.remove(tmp)
+                    raise RuntimeError(f"md5 mismatch for {name} from {mirror}")
+                os.replace(tmp, dst)
+                err = None
+                break
+            except Exception as e:  # noqa: BLE001 - try the next mirror
+                err = e
+        if err is not None:
+            raise RuntimeError(f"MNIST download failed for {name}: {err}")
+    return True
 
 
 def _open(path: str):
@@ -96,6 +167,8 @@ class MNIST:
         img_name, lbl_name, _ = _FILES[train]
         raw = os.path.join(root, "MNIST", "raw")
         img_path, lbl_path = os.path.join(raw, img_name), os.path.join(raw, lbl_name)
+        have = all(os.path.exists(p) or os.path.exists(p + ".gz") for p in (img_path, lbl_path))
+        downloaded = download_mnist(root) if (download and not have) else False
         try:
             self.data = read_idx(img_path)
             self.targets = read_idx(lbl_path).to(torch.int64)
@@ -105,7 +178,7 @@ class MNIST:
                 self.data = read_idx(img_path)
                 self.targets = read_idx(lbl_path).to(torch.int64)
             else:
-                hint = ("download=True was requested but this build never touches the network; " if download else "")
+                hint = ("download=True was requested but no network is reachable from this machine; " if download and not downloaded else "")
                 raise RuntimeError(
                     f"MNIST idx files not found under {raw}. {hint}Place the four *-ubyte[.gz] files there, "
                     "or pass synthetic_fallback=True / use data.SyntheticMNIST for shape-faithful synthetic data.")
@@ -123,6 +196,13 @@ class MNIST:
         if self.target_transform is not None:
             target = self.target_transform(target)
         return img, target
+
+    def native_source(self):
+        """Raw tensors for the C++ batch stager (``_C.BatchStager``): it gathers, applies ToTensor's 1/255 and pins
+        without touching Python.  Only when no per-sample Python transform is in the way."""
+        if self.transform is not None or self.target_transform is not None:
+            return None
+        return {"data": self.data, "targets": self.targets, "scale": 1.0 / 255.0, "sample_shape": (1,) + tuple(self.data.shape[1:])}
 
     def gather(self, indices: Sequence[int]):
         idx = torch.as_tensor(indices, dtype=torch.int64)
@@ -150,6 +230,11 @@ class SyntheticMNIST:
 
     def __getitem__(self, i):
         return self.data[i], int(self.targets[i])
+
+    def native_source(self):
+        if self.data.dtype != torch.float32:
+            return None
+        return {"data": self.data, "targets": self.targets, "scale": 1.0, "sample_shape": tuple(self.data.shape[1:])}
 
     def gather(self, indices):
         idx = torch.as_tensor(indices, dtype=torch.int64)

@@ -58,6 +58,7 @@ class GraphedTrainStep:
         self.optimizer.zero_grad(set_to_none=self.set_to_none)
         if self._seed is None or self._seed.shape != loss.shape or self._seed.dtype != loss.dtype:
             self._seed = torch.ones_like(loss)
+            self._seed._pdt_unit_seed = True   # lets ops that pre-compute their unit-gradient backward skip the scaling kernel
         loss.backward(self._seed)
         self.optimizer.step()
         return loss

@@ -142,7 +142,7 @@ class _FusedLayer1(torch.autograd.Function):
         out, y, saved = _C.convnet_l1_fwd(x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps)
         ctx.save_for_backward(x, y, saved, gamma, beta)
         ctx.params = (w, b, gamma, beta)
-        return out  # [B,14,14,16] NHWC
+        return out  # [B,18,18,16]: zero-haloed NHWC frame
 
     @staticmethod
     def backward(ctx, dp):
@@ -175,10 +175,14 @@ class _FusedLayer2(torch.autograd.Function):
         w_p, b_p, g_p, be_p = ctx.params
         dg = _grad_dst(g_p, gamma)
         dbe = _grad_dst(be_p, beta)
-        dy, dp1 = _C.convnet_l2_bwd(dout.contiguous(), y, saved, gamma, beta, w, dg, dbe)
+        dy, dp1, dysum = _C.convnet_l2_bwd(dout.contiguous(), y, saved, gamma, beta, w, dg, dbe)
         dw = _grad_dst(w_p, w)
         db = _grad_dst(b_p, b_p) if b_p is not None else None
-        _C.conv5x5_wgrad(dy, p1, dw, db, "auto")
+        if os.environ.get("PDT_WGRAD_WIN", "1") != "0":
+            # dy and p1 are zero-haloed frames: every operand of the tensor-core weight gradient arrives by TMA
+            _C.conv5x5_wgrad_win(dy, p1, dysum, dw, db)
+        else:  # im2col-gather kernel on the frames' interiors
+            _C.conv5x5_wgrad(dy[:, 2:16, 2:16, :].contiguous(), p1[:, 2:16, 2:16, :].contiguous(), dw, db, "auto")
         return dp1, dw, db, dg, dbe, None, None, None, None, None, None, None
 
 
@@ -289,16 +293,22 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
 
 
 class _CrossEntropy(torch.autograd.Function):
+    """Mean cross-entropy whose forward launch also produces the gradient w.r.t. the logits for a unit incoming
+    gradient, (softmax − onehot)/B.  Backward is then free when the incoming gradient is known to be one
+    (``engine.GraphedTrainStep`` seeds backward with a tensor tagged ``_pdt_unit_seed``) and one scaling kernel otherwise."""
+
     @staticmethod
     def forward(ctx, logits, target):
-        loss, probs = _C.cross_entropy_fwd(logits.contiguous(), target.contiguous())
-        ctx.save_for_backward(probs, target)
+        loss, grad0 = _C.cross_entropy_fwd(logits.contiguous(), target.contiguous(), True)
+        ctx.save_for_backward(grad0)
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        probs, target = ctx.saved_tensors
-        return _C.cross_entropy_bwd(probs, target, dloss.contiguous()), None
+        (grad0,) = ctx.saved_tensors
+        if getattr(dloss, "_pdt_unit_seed", False):
+            return grad0, None
+        return grad0 * dloss, None
 
 
 def cross_entropy(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:

@@ -252,7 +252,8 @@ def test_cooperative_fused_layers_match_per_op_kernels(B, monkeypatch):
     assert abs(la.item() - lb.item()) < 1e-4, (la.item(), lb.item())
     for (n1, p1), (_, p2) in zip(a.named_parameters(), b.named_parameters()):
         scale = p2.grad.abs().max().item() + 1e-6
-        assert (p1.grad - p2.grad).abs().max().item() <= 2e-2 * scale + 1e-6, (n1, (p1.grad - p2.grad).abs().max().item(), scale)  # TF32 operand rounding of slightly different dy
+        # TF32 operand rounding of slightly different dy; conv biases in front of a BatchNorm have a true gradient of zero (noise level)
+        assert (p1.grad - p2.grad).abs().max().item() <= 2e-2 * scale + 5e-4, (n1, (p1.grad - p2.grad).abs().max().item(), scale)
     for (n1, b1), (_, b2) in zip(a.named_buffers(), b.named_buffers()):
         assert torch.allclose(b1.float(), b2.float(), atol=1e-5, rtol=1e-5), n1
 
@@ -261,22 +262,37 @@ def test_cooperative_layer2_exact_on_small_integers():
     """Integer-valued inputs/weights are exact in TF32 and in fp32 accumulation: the fused conv2 forward (window
     descriptors over the haloed image) and data gradient must reproduce a float64 convolution bit for bit."""
     B = 5
-    p1 = torch.randint(-3, 4, (B, 14, 14, 16), device=dev()).float()
+    p1 = torch.zeros(B, 18, 18, 16, device=dev())   # zero-haloed frame
+    p1[:, 2:16, 2:16, :] = torch.randint(-3, 4, (B, 14, 14, 16), device=dev()).float()
     w = torch.randint(-2, 3, (32, 16, 5, 5), device=dev()).float()
     bias = torch.randint(-2, 3, (32,), device=dev()).float()
     gamma, beta = torch.ones(32, device=dev()), torch.zeros(32, device=dev())
     out, y, saved, logits = _C.convnet_l2_fwd(p1, w, bias, gamma, beta, None, None, None, 0.1, 1e-5, None, None)
-    ref = F.conv2d(p1.permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=2)
+    ref = F.conv2d(p1[:, 2:16, 2:16, :].permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=2)
     assert torch.equal(y.permute(0, 3, 1, 2).double(), ref)
     mean = ref.mean((0, 2, 3))
     assert torch.allclose(saved[:32].double(), mean, atol=1e-4, rtol=1e-5)
     # data gradient: feed a gradient that passes the pool/ReLU/BN backward, compare the conv part through dy
     dout = torch.randn(B, 32, 7, 7, device=dev())
     dg, db = torch.empty(32, device=dev()), torch.empty(32, device=dev())
-    dy, dx = _C.convnet_l2_bwd(dout, y, saved, gamma, beta, w, dg, db)
-    ref_dx = torch.nn.grad.conv2d_input((B, 16, 14, 14), w.double(), dy.permute(0, 3, 1, 2).double(), padding=2)
-    err = (dx.permute(0, 3, 1, 2).double() - ref_dx).abs().max().item()
+    dy, dx, dysum = _C.convnet_l2_bwd(dout, y, saved, gamma, beta, w, dg, db)
+    dyi = dy[:, 2:16, 2:16, :]
+    halo = dy.clone()
+    halo[:, 2:16, 2:16, :] = 0
+    assert halo.abs().max().item() == 0.0, "halo of the dy frame must be zero"
+    ref_dx = torch.nn.grad.conv2d_input((B, 16, 14, 14), w.double(), dyi.permute(0, 3, 1, 2).double(), padding=2)
+    err = (dx[:, 2:16, 2:16, :].permute(0, 3, 1, 2).double() - ref_dx).abs().max().item()
     assert err <= 2e-3 * ref_dx.abs().max().item() + 1e-5, err   # dy is not integer valued: TF32 operand rounding
+    assert torch.allclose(dysum.sum(0).double(), dyi.double().sum((0, 1, 2)), atol=1e-4)
+    # weight gradient, window formulation (all operands by TMA): exact on integer-valued frames
+    dyq = torch.zeros(B, 18, 18, 32, device=dev())
+    dyq[:, 2:16, 2:16, :] = torch.randint(-2, 3, (B, 14, 14, 32), device=dev()).float()
+    dw, dbias = torch.empty(32, 16, 5, 5, device=dev()), torch.empty(32, device=dev())
+    _C.conv5x5_wgrad_win(dyq, p1, dyq[:, 2:16, 2:16, :].sum((1, 2)).contiguous(), dw, dbias)
+    ref_dw = torch.nn.grad.conv2d_weight(p1[:, 2:16, 2:16, :].permute(0, 3, 1, 2).double(), (32, 16, 5, 5),
+                                         dyq[:, 2:16, 2:16, :].permute(0, 3, 1, 2).double(), padding=2)
+    assert torch.equal(dw.double(), ref_dw), (dw.double() - ref_dw).abs().max()
+    assert torch.equal(dbias.double(), dyq.double().sum((0, 1, 2)))
 
 
 def test_generic_bn_kernels_match_torch():
