@@ -61,10 +61,9 @@ class SymmComm : public CudaCommBase {
   std::shared_ptr<CommWork> gather(at::Tensor out, at::Tensor in, int root) override;
   std::shared_ptr<CommWork> scatter(at::Tensor out, at::Tensor in, int root) override;
   std::shared_ptr<CommWork> alltoall(at::Tensor out, at::Tensor in) override;
-  // Point-to-point over the symmetric heap (API parity; the training path never uses it): the sender parks the
-  // message in its own staging area (channel 3), posts a store key, and the receiver copies it out of the sender's
-  // mapped heap.  Eager for messages up to one staging half (16 MB); larger ones advance chunk by chunk as the
-  // receiver acknowledges.  Host-synchronous on both sides.
+  // Point-to-point over the symmetric heap, device-signalled: the sender stores chunks into its slot of the receiver's
+  // heap and raises a flag there, the receiver copies out and acknowledges — two plain kernels, no host synchronisation.
+  // Eager up to one slot (32 MiB / world); longer messages need the matching recv posted.
   std::shared_ptr<CommWork> send(at::Tensor t, int dst) override;
   std::shared_ptr<CommWork> recv(at::Tensor t, int src) override;
   std::shared_ptr<CommWork> barrier() override;
@@ -108,7 +107,6 @@ class SymmComm : public CudaCommBase {
   std::shared_ptr<Store> store_;         // control plane of send/recv
   uint64_t send_seq_[kSymmMaxWorld] = {}, recv_seq_[kSymmMaxWorld] = {};
   uint64_t alloc_seq_ = 0;               // alloc_flat is collective: sequence number of the store exchange
-  std::string pending_ack_;              // ack key of the message still parked in our staging area ("" = none)
   std::string algo_ = "auto";   // auto | oneshot | oneshot_mc | twoshot | nvls
   size_t oneshot_max_ = 512 * 1024;
   SymmLaunchCfg cfg_;

@@ -342,9 +342,12 @@ void SymmComm::broadcast_inline(at::Tensor t, int root) {
 }
 
 // ---- point-to-point ------------------------------------------------------------------------------------
+// Device-signalled (p2p_send_kernel / p2p_recv_kernel): the sender stores the chunk into the slot the receiver's heap
+// reserves for it and raises a flag in the receiver's signal pad; the receiver copies the chunk out and raises the
+// acknowledgement in the sender's pad.  No store traffic, no stream synchronisation, plain kernels on the caller's stream.
+// Messages up to one slot (32 MiB / world) are eager; longer ones advance chunk by chunk as the receiver acknowledges.
 namespace {
 constexpr int kChanP2P = 3;
-std::string p2p_key(int src, int dst, uint64_t seq) { return "p2p/" + std::to_string(src) + ">" + std::to_string(dst) + "/" + std::to_string(seq); }
 }  // namespace
 
 std::shared_ptr<CommWork> SymmComm::send(at::Tensor t, int dst) {
@@ -352,25 +355,20 @@ std::shared_ptr<CommWork> SymmComm::send(at::Tensor t, int dst) {
   TORCH_CHECK(dst >= 0 && dst < size_ && dst != rank_, "send: invalid destination rank ", dst);
   record("send", &t);
   c10::cuda::CUDAGuard guard(device_);
-  cudaStream_t s = c10::cuda::getCurrentCUDAStream(device_).stream();
-  const size_t half = heap_->staging_half_bytes(kChanP2P), nbytes = t.nbytes();
-  char* stage = heap_->local_base() + heap_->staging_off(kChanP2P, 0);
+  auto cur = c10::cuda::getCurrentCUDAStream(device_);
+  const size_t slot = (2 * heap_->staging_half_bytes(kChanP2P) / static_cast<size_t>(size_)) / 256 * 256;
+  const size_t slot_off = heap_->staging_off(kChanP2P, 0) + static_cast<size_t>(rank_) * slot;   // my slot in the receiver's heap
+  const size_t nbytes = t.nbytes();
   const char* p = static_cast<const char*>(t.data_ptr());
-  for (size_t done = 0; done < nbytes || (nbytes == 0 && done == 0); done += half) {
-    const size_t n = std::min(half, nbytes - done);
-    if (!pending_ack_.empty()) {  // the previous message must have left the staging area before it is overwritten
-      store_->get(pending_ack_);
-      store_->delete_key(pending_ack_);
-      pending_ack_.clear();
-    }
-    if (n) PDT_CUDA_CHECK(cudaMemcpyAsync(stage, p + done, n, cudaMemcpyDeviceToDevice, s));
-    PDT_CUDA_CHECK(cudaStreamSynchronize(s));
-    const std::string key = p2p_key(rank_, dst, send_seq_[dst]++);
-    store_->set(key + "/d", std::to_string(n));
-    pending_ack_ = key + "/a";
-    if (nbytes == 0) break;
-  }
-  return std::make_shared<CudaWork>(device_, std::vector<at::Tensor>{});
+  size_t done = 0;
+  do {
+    const size_t n = std::min(slot, nbytes - done);
+    launch_p2p_send(heap_->dev(kChanP2P), p + done, n, dst, slot_off, static_cast<unsigned int>(++send_seq_[dst]), cur.stream());
+    done += n;
+  } while (done < nbytes);
+  auto work = std::make_shared<CudaWork>(device_, std::vector<at::Tensor>{t});
+  work->done().record(cur);
+  return work;
 }
 
 std::shared_ptr<CommWork> SymmComm::recv(at::Tensor t, int src) {
@@ -378,23 +376,20 @@ std::shared_ptr<CommWork> SymmComm::recv(at::Tensor t, int src) {
   TORCH_CHECK(src >= 0 && src < size_ && src != rank_, "recv: invalid source rank ", src);
   record("recv", &t);
   c10::cuda::CUDAGuard guard(device_);
-  cudaStream_t s = c10::cuda::getCurrentCUDAStream(device_).stream();
-  const size_t half = heap_->staging_half_bytes(kChanP2P), nbytes = t.nbytes();
-  const char* stage = heap_->base(src) + heap_->staging_off(kChanP2P, 0);   // the sender's staging area, mapped here
+  auto cur = c10::cuda::getCurrentCUDAStream(device_);
+  const size_t slot = (2 * heap_->staging_half_bytes(kChanP2P) / static_cast<size_t>(size_)) / 256 * 256;
+  const size_t slot_off = heap_->staging_off(kChanP2P, 0) + static_cast<size_t>(src) * slot;     // the sender's slot in my heap
+  const size_t nbytes = t.nbytes();
   char* p = static_cast<char*>(t.data_ptr());
-  for (size_t done = 0; done < nbytes || (nbytes == 0 && done == 0); done += half) {
-    const size_t n = std::min(half, nbytes - done);
-    const std::string key = p2p_key(src, rank_, recv_seq_[src]++);
-    const std::string posted = store_->get(key + "/d");  // blocks until the sender has parked this chunk
-    TORCH_CHECK(static_cast<size_t>(std::stoull(posted)) == n, "recv: rank ", src, " sent ", posted, " bytes where ", n,
-                " were expected (mismatched send/recv sizes)");
-    if (n) PDT_CUDA_CHECK(cudaMemcpyAsync(p + done, stage, n, cudaMemcpyDeviceToDevice, s));
-    PDT_CUDA_CHECK(cudaStreamSynchronize(s));
-    store_->delete_key(key + "/d");
-    store_->set(key + "/a", "1");
-    if (nbytes == 0) break;
-  }
-  return std::make_shared<CudaWork>(device_, std::vector<at::Tensor>{});
+  size_t done = 0;
+  do {
+    const size_t n = std::min(slot, nbytes - done);
+    launch_p2p_recv(heap_->dev(kChanP2P), p + done, n, src, slot_off, static_cast<unsigned int>(++recv_seq_[src]), cur.stream());
+    done += n;
+  } while (done < nbytes);
+  auto work = std::make_shared<CudaWork>(device_, std::vector<at::Tensor>{t});
+  work->done().record(cur);
+  return work;
 }
 
 std::shared_ptr<CommWork> SymmComm::allgather(at::Tensor out, at::Tensor in) {
@@ -442,41 +437,132 @@ std::shared_ptr<CommWork> SymmComm::alltoall(at::Tensor out, at::Tensor in) {
   });
 }
 
-// The remaining collectives are compositions; they are off the training hot path.
+// ---- rooted / scattered collectives: one barrier-synchronised kernel over the staging area each, no clone + allreduce ------
 std::shared_ptr<CommWork> SymmComm::reduce(at::Tensor t, ReduceOp op, int root) {
   check(t, "reduce");
-  at::Tensor tmp = t.clone();
-  auto w = allreduce(tmp, op, 1.0);
-  w->wait();
-  if (rank_ == root) t.copy_(tmp);
-  return w;
+  TORCH_CHECK(root >= 0 && root < size_, "reduce: invalid root");
+  record("reduce", &t);
+  return enqueue({t}, [&](cudaStream_t s) {
+    const size_t nbytes = t.nbytes();
+    if (nbytes == 0 || size_ == 1) return;
+    double scale = 1.0;
+    ReduceOp rop = op;
+    if (op == ReduceOp::AVG) { scale = 1.0 / size_; rop = ReduceOp::SUM; }
+    const size_t half = heap_->staging_half_bytes(kChanComm) / 16 * 16;
+    char* p = static_cast<char*>(t.data_ptr());
+    for (size_t done = 0; done < nbytes; done += half) {
+      const size_t n = std::min(half, nbytes - done), n_pad = (n + 15) / 16 * 16;
+      const size_t stage = heap_->staging_off(kChanComm, heap_->next_parity(kChanComm));
+      char* stg = heap_->local_base() + stage;
+      if (n_pad != n) PDT_CUDA_CHECK(cudaMemsetAsync(stg + n, 0, n_pad - n, s));
+      PDT_CUDA_CHECK(cudaMemcpyAsync(stg, p + done, n, cudaMemcpyDeviceToDevice, s));
+      // the root reduces every rank's parked chunk back into its own staging copy (an exact 16-byte multiple), then takes it
+      launch_reduce_pull(heap_->dev(kChanComm), stage, 0, rank_ == root ? n_pad / 16 : 0, n_pad / 16, stg, to_symm_dtype(t.scalar_type()),
+                         static_cast<int>(rop), scale, cfg_, s);
+      if (rank_ == root) PDT_CUDA_CHECK(cudaMemcpyAsync(p + done, stg, n, cudaMemcpyDeviceToDevice, s));
+    }
+  });
 }
+
 std::shared_ptr<CommWork> SymmComm::reduce_scatter(at::Tensor out, at::Tensor in, ReduceOp op) {
   check(out, "reduce_scatter output");
   check(in, "reduce_scatter input");
-  TORCH_CHECK(in.numel() == out.numel() * size_, "reduce_scatter: input must hold world_size × output elements");
-  at::Tensor tmp = in.clone();
-  auto w = allreduce(tmp, op, 1.0);
-  w->wait();
-  out.copy_(tmp.view(-1).narrow(0, static_cast<int64_t>(rank_) * out.numel(), out.numel()).view_as(out));
-  return w;
+  TORCH_CHECK(in.numel() == out.numel() * size_ && in.scalar_type() == out.scalar_type(), "reduce_scatter: input must hold world_size × output elements");
+  record("reduce_scatter", &in);
+  return enqueue({out, in}, [&](cudaStream_t s) {
+    const size_t slice = out.nbytes();
+    if (slice == 0) return;
+    if (size_ == 1) {
+      PDT_CUDA_CHECK(cudaMemcpyAsync(out.data_ptr(), in.data_ptr(), slice, cudaMemcpyDeviceToDevice, s));
+      return;
+    }
+    double scale = 1.0;
+    ReduceOp rop = op;
+    if (op == ReduceOp::AVG) { scale = 1.0 / size_; rop = ReduceOp::SUM; }
+    // a chunk = the same piece of every rank's slice, parked slice-major with 16-byte padded pieces
+    const size_t half = heap_->staging_half_bytes(kChanComm);
+    const size_t piece_max = (half / size_) / 16 * 16;
+    const char* src = static_cast<const char*>(in.data_ptr());
+    char* dst = static_cast<char*>(out.data_ptr());
+    for (size_t done = 0; done < slice; done += piece_max) {
+      const size_t n = std::min(piece_max, slice - done), n_pad = (n + 15) / 16 * 16;
+      const size_t stage = heap_->staging_off(kChanComm, heap_->next_parity(kChanComm));
+      char* stg = heap_->local_base() + stage;
+      for (int r = 0; r < size_; ++r) {
+        if (n_pad != n) PDT_CUDA_CHECK(cudaMemsetAsync(stg + r * n_pad + n, 0, n_pad - n, s));
+        PDT_CUDA_CHECK(cudaMemcpyAsync(stg + r * n_pad, src + r * slice + done, n, cudaMemcpyDeviceToDevice, s));
+      }
+      if (n_pad == n) {
+        launch_reduce_pull(heap_->dev(kChanComm), stage, static_cast<size_t>(rank_) * (n_pad / 16), n_pad / 16, size_ * (n_pad / 16), dst + done,
+                           to_symm_dtype(out.scalar_type()), static_cast<int>(rop), scale, cfg_, s);
+      } else {  // ragged tail: reduce into the (now free) own piece of the staging copy, then copy the exact bytes out
+        char* tmp = stg + static_cast<size_t>(rank_) * n_pad;
+        launch_reduce_pull(heap_->dev(kChanComm), stage, static_cast<size_t>(rank_) * (n_pad / 16), n_pad / 16, size_ * (n_pad / 16), tmp,
+                           to_symm_dtype(out.scalar_type()), static_cast<int>(rop), scale, cfg_, s);
+        PDT_CUDA_CHECK(cudaMemcpyAsync(dst + done, tmp, n, cudaMemcpyDeviceToDevice, s));
+      }
+    }
+  });
 }
+
 std::shared_ptr<CommWork> SymmComm::gather(at::Tensor out, at::Tensor in, int root) {
   check(in, "gather input");
-  at::Tensor all = at::empty({static_cast<int64_t>(size_) * in.numel()}, in.options());
-  auto w = allgather(all, in.view(-1));
-  w->wait();
-  if (rank_ == root) out.view(-1).copy_(all);
-  return w;
+  TORCH_CHECK(root >= 0 && root < size_, "gather: invalid root");
+  if (rank_ == root) {
+    check(out, "gather output");
+    TORCH_CHECK(out.numel() == in.numel() * size_ && out.scalar_type() == in.scalar_type(), "gather: output must hold world_size × input elements");
+  }
+  record("gather", &in);
+  return enqueue({out, in}, [&](cudaStream_t s) {
+    const size_t nbytes = in.nbytes();
+    if (nbytes == 0) return;
+    if (size_ == 1) {
+      PDT_CUDA_CHECK(cudaMemcpyAsync(out.data_ptr(), in.data_ptr(), nbytes, cudaMemcpyDeviceToDevice, s));
+      return;
+    }
+    const size_t half = heap_->staging_half_bytes(kChanComm);
+    const char* src = static_cast<const char*>(in.data_ptr());
+    char* dst = rank_ == root ? static_cast<char*>(out.data_ptr()) : nullptr;
+    for (size_t done = 0; done < nbytes; done += half) {
+      const size_t n = std::min(half, nbytes - done);
+      const size_t stage = heap_->staging_off(kChanComm, heap_->next_parity(kChanComm));
+      PDT_CUDA_CHECK(cudaMemcpyAsync(heap_->local_base() + stage, src + done, n, cudaMemcpyDeviceToDevice, s));
+      // only the root pulls; everybody else just attends the barrier (dst == nullptr)
+      launch_allgather_pull(heap_->dev(kChanComm), stage, dst ? dst + done : nullptr, n, nbytes, /*exit_barrier=*/false, cfg_, s);
+    }
+  });
 }
+
 std::shared_ptr<CommWork> SymmComm::scatter(at::Tensor out, at::Tensor in, int root) {
   check(out, "scatter output");
-  at::Tensor all = at::empty({static_cast<int64_t>(size_) * out.numel()}, out.options());
-  if (rank_ == root) all.copy_(in.view(-1));
-  auto w = broadcast(all, root);
-  w->wait();
-  out.view(-1).copy_(all.narrow(0, static_cast<int64_t>(rank_) * out.numel(), out.numel()));
-  return w;
+  TORCH_CHECK(root >= 0 && root < size_, "scatter: invalid root");
+  if (rank_ == root) {
+    check(in, "scatter input");
+    TORCH_CHECK(in.numel() == out.numel() * size_ && in.scalar_type() == out.scalar_type(), "scatter: input must hold world_size × output elements");
+  }
+  record("scatter", &out);
+  return enqueue({out, in}, [&](cudaStream_t s) {
+    const size_t blk = out.nbytes();
+    if (blk == 0) return;
+    if (size_ == 1) {
+      PDT_CUDA_CHECK(cudaMemcpyAsync(out.data_ptr(), in.data_ptr(), blk, cudaMemcpyDeviceToDevice, s));
+      return;
+    }
+    const size_t half = heap_->staging_half_bytes(kChanComm);
+    const size_t piece_max = (half / size_) / 16 * 16;
+    char* dst = static_cast<char*>(out.data_ptr());
+    for (size_t done = 0; done < blk; done += piece_max) {
+      const size_t n = std::min(piece_max, blk - done), n_pad = (n + 15) / 16 * 16;
+      const size_t stage = heap_->staging_off(kChanComm, heap_->next_parity(kChanComm));
+      if (rank_ == root) {
+        const char* src = static_cast<const char*>(in.data_ptr());
+        for (int r = 0; r < size_; ++r)
+          PDT_CUDA_CHECK(cudaMemcpyAsync(heap_->local_base() + stage + r * n_pad, src + r * blk + done, n, cudaMemcpyDeviceToDevice, s));
+      }
+      // every rank pulls its own piece out of the root's staging area
+      launch_broadcast_pull(heap_->dev(kChanComm), stage + static_cast<size_t>(rank_) * n_pad, dst + done, n, root, /*exit_barrier=*/false, cfg_, s);
+    }
+  });
 }
 
 std::shared_ptr<CommWork> SymmComm::barrier() {

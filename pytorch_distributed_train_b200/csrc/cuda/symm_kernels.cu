@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <stdexcept>
 #include <string>
 
@@ -247,12 +248,38 @@ __global__ void __launch_bounds__(512) allreduce_twoshot_kernel(const __grid_con
   ep.commit(d, blockIdx.x);
 }
 
+// ---- reduce-scatter / rooted reduce: the first half of a two-shot ------------------------------------------------
+// Every rank has parked its whole contribution (nvec 16-byte vectors) at `stage_off` of its own heap.  After one
+// barrier a rank reduces vectors [begin, begin + count) over all ranks, in rank order, straight out of the peers'
+// memory, into `out` — reduce_scatter: everybody takes its slice (inbound (N−1)/N·S per GPU, the minimum);
+// reduce(root): the root takes everything, the others only attend the barrier.
+template <typename T, int OP>
+__global__ void __launch_bounds__(512) reduce_pull_kernel(const __grid_constant__ SymmDev d, size_t stage_off, size_t begin, size_t count, uint4* out,
+                                                          float scale) {
+  SymmEpoch ep(d, blockIdx.x);
+  symm_barrier_block(d, blockIdx.x, ep.next());
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const size_t off = stage_off + (begin + i) * 16;
+    typename Acc<T>::type a[VecOf<T>::N];
+    acc_init<T, OP>(a, ld_vec_nc(d.peer[0] + off));
+    for (int r = 1; r < d.world; ++r) acc_add<T, OP>(a, ld_vec_nc(d.peer[r] + off));
+    st_vec(out + i, acc_pack<T>(a, scale));
+  }
+  ep.commit(d, blockIdx.x);
+}
+
 // ---- pull-style data movement -------------------------------------------------------------------------
 // mode 0: broadcast (root → dst), 1: allgather, 2: alltoall
 __global__ void __launch_bounds__(512) pull_kernel(const __grid_constant__ SymmDev d, size_t src_off, char* dst, size_t nbytes, size_t dst_stride,
                                                    int root, int mode, int exit_barrier) {
   SymmEpoch ep(d, blockIdx.x);
   symm_barrier_block(d, blockIdx.x, ep.next());
+  if (dst == nullptr) {   // a rank that only attends (gather on a non-root rank): barriers, no copies
+    if (exit_barrier) symm_barrier_block(d, blockIdx.x, ep.next());
+    ep.commit(d, blockIdx.x);
+    return;
+  }
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nvec = nbytes / 16, tail = nbytes % 16;
@@ -278,6 +305,70 @@ __global__ void __launch_bounds__(512) pull_kernel(const __grid_constant__ SymmD
   ep.commit(d, blockIdx.x);
 }
 
+// ---- point-to-point: device-signalled, no host round trip ---------------------------------------------------------------
+// A message travels in chunks through a slot of the RECEIVER's heap reserved for this sender.  Per (pair, block) there
+// are two monotonically increasing flags: `ready` in the receiver's signal pad (written by the sender after its
+// stores, release.sys) and `ack` in the sender's pad (written by the receiver once the chunk has been copied out).
+// Chunk k of the pair carries sequence number k (host-side counters on both ends, identical chunking), so nothing is
+// ever reset: send(k) waits for ack ≥ k−1, writes, publishes ready = k; recv(k) waits for ready ≥ k, copies, acks k.
+// Both are ordinary kernels on the caller's stream.  Rows [0, kP2PBlocks) of the channel hold `ready`, rows
+// [kP2PAckRow, …) hold `ack`.
+constexpr int kP2PAckRow = 80;
+
+__device__ __forceinline__ void p2p_wait(const SymmDev& d, const uint32_t* flag, uint32_t want, int peer) {
+  uint32_t v = ld_acquire_sys(flag);
+  if (static_cast<int32_t>(v - want) < 0) {
+    const unsigned long long t0 = globaltimer_ns();
+    int spins = 0;
+    while (static_cast<int32_t>((v = ld_acquire_sys(flag)) - want) < 0) {
+      if (++spins > 64) {
+        __nanosleep(40);
+        if ((spins & 1023) == 0 && globaltimer_ns() - t0 > d.timeout_ns) symm_trap_timeout(d, peer, want, v);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) p2p_send_kernel(const __grid_constant__ SymmDev d, const char* __restrict__ src, size_t nbytes, int dst_rank,
+                                                       size_t slot_off, uint32_t seq) {
+  if (threadIdx.x == 0) p2p_wait(d, symm_flag_row(d, d.rank, kP2PAckRow + blockIdx.x) + dst_rank, seq - 1, dst_rank);   // previous chunk consumed
+  __syncthreads();
+  char* out = d.peer[dst_rank] + slot_off;
+  const size_t nvec = nbytes / 16, tail = nbytes % 16;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x, first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    for (size_t i = first; i < nvec; i += stride) st_vec_sys(out + i * 16, ld_vec(src + i * 16));
+    if (blockIdx.x == 0 && threadIdx.x < tail) out[nvec * 16 + threadIdx.x] = src[nvec * 16 + threadIdx.x];
+  } else {
+    for (size_t i = first; i < nbytes; i += stride) out[i] = src[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(symm_flag_row(d, dst_rank, blockIdx.x) + d.rank, seq);
+  }
+}
+
+__global__ void __launch_bounds__(512) p2p_recv_kernel(const __grid_constant__ SymmDev d, char* __restrict__ dst, size_t nbytes, int src_rank,
+                                                       size_t slot_off, uint32_t seq) {
+  if (threadIdx.x == 0) p2p_wait(d, symm_flag_row(d, d.rank, blockIdx.x) + src_rank, seq, src_rank);
+  __syncthreads();
+  const char* in = d.peer[d.rank] + slot_off;
+  const size_t nvec = nbytes / 16, tail = nbytes % 16;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x, first = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    for (size_t i = first; i < nvec; i += stride) st_vec(dst + i * 16, ld_vec_nc(in + i * 16));
+    if (blockIdx.x == 0 && threadIdx.x < tail) dst[nvec * 16 + threadIdx.x] = *reinterpret_cast<const volatile char*>(in + nvec * 16 + threadIdx.x);
+  } else {
+    for (size_t i = first; i < nbytes; i += stride) dst[i] = *reinterpret_cast<const volatile char*>(in + i);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(symm_flag_row(d, src_rank, kP2PAckRow + blockIdx.x) + d.rank, seq);
+  }
+}
+
 __global__ void barrier_kernel(const __grid_constant__ SymmDev d) {
   SymmEpoch ep(d, 0);
   symm_barrier_block(d, 0, ep.next());
@@ -296,15 +387,33 @@ void check_launch(const char* what) {
   count_kernel_launch();
 }
 
+// Which (dtype, op) pairs get a kernel.  SUM exists for every dtype (it is what DDP, SyncBatchNorm and the object
+// collectives use); MIN / MAX / PROD for the 32/64-bit types; the bitwise ops for the integer types they are defined on.
+// Everything else is rejected at dispatch instead of being instantiated (the full cross product was 210 kernels and a
+// 9.7 MB object for combinations nothing ever calls).
+template <typename T, int OP> constexpr bool op_supported() {
+  if (OP == SO_SUM) return true;
+  if (OP == SO_PROD || OP == SO_MIN || OP == SO_MAX)
+    return std::is_same<T, float>::value || std::is_same<T, double>::value || std::is_same<T, int>::value || std::is_same<T, long long>::value;
+  return std::is_same<T, int>::value || std::is_same<T, long long>::value || std::is_same<T, unsigned char>::value;
+}
+
+#define PDT_OP_CASE(T, OPC, ...)                                                                                      \
+  {                                                                                                                   \
+    constexpr int OP = OPC;                                                                                           \
+    if constexpr (op_supported<T, OPC>()) { __VA_ARGS__; }                                                           \
+    else throw std::invalid_argument("this reduce op is not implemented for this dtype on the NVLink backend");     \
+    break;                                                                                                            \
+  }
 #define PDT_DISPATCH_OP(T, OPV, ...)                                  \
   switch (OPV) {                                                      \
-    case SO_SUM: case SO_AVG: { constexpr int OP = SO_SUM; __VA_ARGS__; break; } \
-    case SO_PROD: { constexpr int OP = SO_PROD; __VA_ARGS__; break; } \
-    case SO_MIN: { constexpr int OP = SO_MIN; __VA_ARGS__; break; }   \
-    case SO_MAX: { constexpr int OP = SO_MAX; __VA_ARGS__; break; }   \
-    case SO_BAND: { constexpr int OP = SO_BAND; __VA_ARGS__; break; } \
-    case SO_BOR: { constexpr int OP = SO_BOR; __VA_ARGS__; break; }   \
-    case SO_BXOR: { constexpr int OP = SO_BXOR; __VA_ARGS__; break; } \
+    case SO_SUM: case SO_AVG: PDT_OP_CASE(T, SO_SUM, __VA_ARGS__)     \
+    case SO_PROD: PDT_OP_CASE(T, SO_PROD, __VA_ARGS__)                \
+    case SO_MIN: PDT_OP_CASE(T, SO_MIN, __VA_ARGS__)                  \
+    case SO_MAX: PDT_OP_CASE(T, SO_MAX, __VA_ARGS__)                  \
+    case SO_BAND: PDT_OP_CASE(T, SO_BAND, __VA_ARGS__)                \
+    case SO_BOR: PDT_OP_CASE(T, SO_BOR, __VA_ARGS__)                  \
+    case SO_BXOR: PDT_OP_CASE(T, SO_BXOR, __VA_ARGS__)                \
     default: throw std::invalid_argument("unsupported reduce op");    \
   }
 
@@ -417,6 +526,26 @@ void launch_alltoall_pull(const SymmDev& d, size_t src_off, void* dst, size_t nb
                           SymmLaunchCfg cfg, cudaStream_t s) {
   launch_pull(d, src_off, dst, nbytes, stride, 0, 2, exit_barrier, cfg, s);
 }
+void launch_reduce_pull(const SymmDev& d, size_t stage_off, size_t begin_vec, size_t count_vec, size_t total_vec, void* out, int dtype, int op,
+                        double scale, SymmLaunchCfg cfg, cudaStream_t s) {
+  if (stage_off % 16 != 0) throw std::invalid_argument("reduce_pull: staging offset must be 16-byte aligned");
+  const int threads = cfg.threads ? cfg.threads : 512;
+  // every rank must launch the same grid (the barrier is per block): size it by the whole vector, not by this rank's share
+  const int blocks = std::min(cfg.blocks ? cfg.blocks : auto_blocks(total_vec / std::max(1, d.world) + 1, threads, 64), kSymmMaxBlocks);
+  const float sc = static_cast<float>(scale);
+  PDT_DISPATCH_TYPE(dtype, PDT_DISPATCH_OP(T, op, { reduce_pull_kernel<T, OP><<<blocks, threads, 0, s>>>(d, stage_off, begin_vec, count_vec, static_cast<uint4*>(out), sc); }));
+  check_launch("reduce_pull");
+}
+
+void launch_p2p_send(const SymmDev& d, const void* src, size_t nbytes, int dst_rank, size_t slot_off, unsigned int seq, cudaStream_t s) {
+  p2p_send_kernel<<<kSymmP2PBlocks, 512, 0, s>>>(d, static_cast<const char*>(src), nbytes, dst_rank, slot_off, seq);
+  check_launch("p2p_send");
+}
+void launch_p2p_recv(const SymmDev& d, void* dst, size_t nbytes, int src_rank, size_t slot_off, unsigned int seq, cudaStream_t s) {
+  p2p_recv_kernel<<<kSymmP2PBlocks, 512, 0, s>>>(d, static_cast<char*>(dst), nbytes, src_rank, slot_off, seq);
+  check_launch("p2p_recv");
+}
+
 void launch_barrier(const SymmDev& d, cudaStream_t s) {
   barrier_kernel<<<1, 32, 0, s>>>(d);
   check_launch("barrier_kernel");

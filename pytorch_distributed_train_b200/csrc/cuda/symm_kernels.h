@@ -43,6 +43,15 @@ void launch_allgather_pull(const SymmDev& d, size_t src_off, void* dst, size_t n
 // dst[r*stride ...] <- nbytes of rank r's block [my_rank] (sources hold world blocks, `stride` apart).
 void launch_alltoall_pull(const SymmDev& d, size_t src_off, void* dst, size_t nbytes, size_t stride, bool exit_barrier,
                           SymmLaunchCfg cfg, cudaStream_t s);
+// Every rank has parked total_vec 16-byte vectors at heap offset `stage_off`; after one barrier this rank reduces
+// vectors [begin_vec, begin_vec + count_vec) over all ranks (rank order) into `out` (local pointer; count_vec may be 0).
+void launch_reduce_pull(const SymmDev& d, size_t stage_off, size_t begin_vec, size_t count_vec, size_t total_vec, void* out, int dtype, int op,
+                        double scale, SymmLaunchCfg cfg, cudaStream_t s);
+// Device-signalled point-to-point chunk (see p2p_send_kernel): `slot_off` is the heap offset of the (sender → receiver)
+// slot inside the RECEIVER's heap, `seq` the pair's chunk sequence number (1, 2, …; same on both ends).
+constexpr int kSymmP2PBlocks = 16;
+void launch_p2p_send(const SymmDev& d, const void* src, size_t nbytes, int dst_rank, size_t slot_off, unsigned int seq, cudaStream_t s);
+void launch_p2p_recv(const SymmDev& d, void* dst, size_t nbytes, int src_rank, size_t slot_off, unsigned int seq, cudaStream_t s);
 void launch_barrier(const SymmDev& d, cudaStream_t s);
 
 // Fused: mean-allreduce of a flat fp32 gradient vector (one-shot push) + SGD update of the flat

@@ -12,10 +12,6 @@ from mp_helpers import free_port, run_ranks
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 dist = pdt.distributed
 
-# Tests written after the round's GPU budget was spent have never executed on hardware; they stay out of the default
-# `-m gpu` run until they have passed once (tools/trip_first_2gpu.sh sets PDT_TEST_EXPERIMENTAL=1).
-not_yet_run_on_hardware = pytest.mark.skipif(os.environ.get("PDT_TEST_EXPERIMENTAL") != "1",
-                                             reason="written without GPU access; set PDT_TEST_EXPERIMENTAL=1 to run")
 
 
 def _world():
@@ -321,6 +317,40 @@ def test_fused_allreduce_sgd(momentum):
     assert torch.equal(res[0][1], res[-1][1]) and torch.equal(res[0][2], res[-1][2])  # ranks bit-identical
 
 
+def _rooted(rank, world):
+    """reduce / reduce_scatter / gather / scatter: one barrier-synchronised kernel over the staging area each."""
+    dev = torch.device("cuda", rank)
+    total = sum(range(1, world + 1))
+    for n in (5, 1000, 262147):
+        for root in (0, world - 1):
+            t = torch.arange(n, device=dev, dtype=torch.float32) % 13 * (rank + 1)
+            dist.reduce(t, root)
+            if rank == root:
+                assert torch.equal(t, torch.arange(n, device=dev, dtype=torch.float32) % 13 * total), ("reduce", n, root)
+            g = torch.full((n,), float(rank), device=dev)
+            outs = [torch.empty(n, device=dev) for _ in range(world)] if rank == root else None
+            dist.gather(g, outs, dst=root)
+            if rank == root:
+                assert all(torch.equal(o, torch.full((n,), float(r), device=dev)) for r, o in enumerate(outs)), ("gather", n, root)
+            sc = torch.empty(n, device=dev)
+            dist.scatter(sc, [torch.full((n,), float(10 * r + root), device=dev) for r in range(world)] if rank == root else None, src=root)
+            assert torch.equal(sc, torch.full((n,), float(10 * rank + root), device=dev)), ("scatter", n, root)
+        inp = (torch.arange(world * n, device=dev, dtype=torch.float32) % 7 + rank).contiguous()
+        out = torch.empty(n, device=dev)
+        dist.reduce_scatter_tensor(out, inp)
+        exp = (torch.arange(world * n, device=dev, dtype=torch.float32) % 7)[rank * n:(rank + 1) * n] * world + sum(range(world))
+        assert torch.equal(out, exp), ("reduce_scatter", n)
+    mx = torch.tensor([float(rank)], device=dev)
+    dist.reduce(mx, 0, dist.ReduceOp.MAX)
+    assert rank != 0 or mx.item() == world - 1
+    torch.cuda.synchronize()
+    return True
+
+
+def test_rooted_collectives_over_the_symmetric_heap():
+    assert all(run_ranks(_rooted, _world(), backend="nccl"))
+
+
 def _absent_rank(rank, world, init, outdir):
     import json
     import time
@@ -389,7 +419,6 @@ def _stress(rank, world):
     return comm.status()
 
 
-@not_yet_run_on_hardware
 def test_ten_thousand_back_to_back_collectives():
     assert run_ranks(_stress, _world(), backend="nccl") == [0] * _world()
 
@@ -417,6 +446,5 @@ def _p2p(rank, world):
     return ok
 
 
-@not_yet_run_on_hardware
 def test_send_recv_over_the_symmetric_heap():
     assert all(run_ranks(_p2p, _world(), backend="nccl"))

@@ -1,11 +1,21 @@
 #!/usr/bin/env python
-"""Per-kernel device times of the ConvNet step (CUDA events on the launching stream, after warm-up,
-L2 flushed between iterations by overwriting a 256 MB buffer).  Writes gpurun_out/op_bench.json."""
+"""Per-kernel device times of the ConvNet step, ours next to the library kernels the reference stack runs for the
+same work (cuDNN convolution fwd/dgrad/wgrad, ATen batch-norm / ReLU / max-pool and their backward ops, cuBLAS addmm,
+log-softmax + NLL, foreach SGD) — same box, same shapes (batch 100), same method:
+
+* every row is timed as a CUDA graph of REPS back-to-back launches (CUDA events around the replay, ÷ REPS), i.e. what
+  the op costs inside a captured step, launch gap included, host overhead excluded — for both arms;
+* "cold" rows additionally overwrite a 256 MB buffer (> 126 MB L2) before a single eager launch.
+
+Writes gpurun_out/op_bench.json and prints a table; tools/roofline_report.py turns it into profiles/*.md.
+"""
 import json
 import os
 import sys
 
 import torch
+import torch.nn as nn
+import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -14,16 +24,44 @@ from pytorch_distributed_train_b200.utils import l2_flush  # noqa: E402
 
 dev = torch.device("cuda", 0)
 B = 100
+REPS = 20
 
 
-def bench(name, fn, iters=30, flush=True):
-    for _ in range(5):
+def graph_time(fn, reps=REPS, iters=20):
+    """µs per launch of `fn` inside a CUDA graph holding `reps` copies of it."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        for _ in range(reps):
+            fn()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3 / reps)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def cold_time(fn, iters=15):
+    for _ in range(3):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
-        if flush:
-            l2_flush(dev)
+        l2_flush(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
@@ -31,72 +69,103 @@ def bench(name, fn, iters=30, flush=True):
         b.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)
     ts.sort()
-    return {"op": name, "us_median": ts[len(ts) // 2], "us_min": ts[0], "flush": flush}
+    return ts[len(ts) // 2]
 
 
 def main():
     torch.manual_seed(0)
-    x1 = torch.rand(B, 28, 28, 1, device=dev)
-    w1, b1 = torch.randn(16, 1, 5, 5, device=dev) * 0.1, torch.zeros(16, device=dev)
-    w2, b2 = torch.randn(32, 16, 5, 5, device=dev) * 0.05, torch.zeros(32, device=dev)
-    y1, st1 = _C.conv5x5_fwd(x1, w1, b1, True, "simt")
-    g1, be1 = torch.ones(16, device=dev), torch.zeros(16, device=dev)
-    g2, be2 = torch.ones(32, device=dev), torch.zeros(32, device=dev)
-    a1, sv1 = _C.bn_relu_pool_fwd(y1, st1, g1, be1, None, None, None, 0.1, 1e-5, False)
-    y2, st2 = _C.conv5x5_fwd(a1, w2, b2, True, "tcgen05")
-    a2, sv2 = _C.bn_relu_pool_fwd(y2, st2, g2, be2, None, None, None, 0.1, 1e-5, True)
-    flat = a2.reshape(B, -1)
-    wf, bf = torch.randn(10, 1568, device=dev) * 0.01, torch.zeros(10, device=dev)
-    logits = _C.linear_fwd(flat, wf, bf)
+    torch.backends.cudnn.allow_tf32 = True          # the reference's default: TF32 allowed in cuDNN convolutions
+    torch.backends.cudnn.benchmark = True            # let cuDNN pick its fastest engine for these shapes
+    x = torch.rand(B, 1, 28, 28, device=dev)
     tgt = torch.randint(0, 10, (B,), device=dev)
-    loss, probs = _C.cross_entropy_fwd(logits, tgt)
-    one = torch.ones((), device=dev)
-    dlog = _C.cross_entropy_bwd(probs, tgt, one)
+    c1, bn1 = nn.Conv2d(1, 16, 5, 1, 2).to(dev), nn.BatchNorm2d(16).to(dev)
+    c2, bn2 = nn.Conv2d(16, 32, 5, 1, 2).to(dev), nn.BatchNorm2d(32).to(dev)
+    fc = nn.Linear(1568, 10).to(dev)
+    w1, b1, g1, be1 = c1.weight.detach(), c1.bias.detach(), bn1.weight.detach(), bn1.bias.detach()
+    w2, b2, g2, be2 = c2.weight.detach(), c2.bias.detach(), bn2.weight.detach(), bn2.bias.detach()
+    wf, bf = fc.weight.detach(), fc.bias.detach()
+
+    # ---- ours: the cooperative fused layers (what a captured step launches) -------------------------------------------
+    p1, y1, sv1 = _C.convnet_l1_fwd(x, w1, b1, g1, be1, None, None, None, 0.1, 1e-5)
+    p2, y2, sv2, logits = _C.convnet_l2_fwd(p1, w2, b2, g2, be2, None, None, None, 0.1, 1e-5, wf, bf)
+    loss, dlog = _C.cross_entropy_fwd(logits, tgt, True)
     dwf, dbf = torch.empty_like(wf), torch.empty_like(bf)
-    dflat = _C.linear_bwd(dlog, flat, wf, True, dwf, dbf)
-    d2 = dflat.view(B, 32, 7, 7)
-    sums2, dg2, db2 = _C.bn_relu_pool_bwd_reduce(d2, y2, sv2, g2, be2, True)
-    dy2 = _C.bn_relu_pool_bwd_apply(d2, y2, sv2, g2, be2, sums2, st2[64:], True)
-    dw2, dbb2 = torch.empty_like(w2), torch.empty_like(b2)
-    da1 = _C.conv5x5_dgrad(dy2, w2, "tcgen05")
-    sums1, dg1, db1 = _C.bn_relu_pool_bwd_reduce(da1, y1, sv1, g1, be1, False)
-    dy1 = _C.bn_relu_pool_bwd_apply(da1, y1, sv1, g1, be1, sums1, st1[32:], False)
-    dw1, dbb1 = torch.empty_like(w1), torch.empty_like(b1)
+    dflat = _C.linear_bwd(dlog, p2.reshape(B, -1), wf, True, dwf, dbf)
+    dg2, dbe2 = torch.empty(32, device=dev), torch.empty(32, device=dev)
+    dy2, dp1, dysum = _C.convnet_l2_bwd(dflat.view(B, 32, 7, 7), y2, sv2, g2, be2, w2, dg2, dbe2)
+    dw2, db2 = torch.empty_like(w2), torch.empty_like(b2)
+    dg1, dbe1, dw1, db1 = torch.empty(16, device=dev), torch.empty(16, device=dev), torch.empty_like(w1), torch.empty_like(b1)
     params = [w1, b1, g1, be1, w2, b2, g2, be2, wf, bf]
     grads = [torch.randn_like(p) for p in params]
-    ops = [
-        ("conv1_fwd_simt", lambda: _C.conv5x5_fwd(x1, w1, b1, True, "simt")),
-        ("bn_relu_pool1_fwd", lambda: _C.bn_relu_pool_fwd(y1, st1, g1, be1, None, None, None, 0.1, 1e-5, False)),
-        ("conv2_fwd_tcgen05(+repack)", lambda: _C.conv5x5_fwd(a1, w2, b2, True, "tcgen05")),
-        ("conv2_fwd_tma_im2col(+repack)", lambda: _C.conv5x5_fwd(a1, w2, b2, True, "tma")),
-        ("conv2_dgrad_tma_im2col(+repack)", lambda: _C.conv5x5_dgrad(dy2, w2, "tma")),
-        ("conv2_wgrad_tcgen05(+fold)", lambda: _C.conv5x5_wgrad(dy2, a1, dw2, dbb2, "tcgen05")),
-        ("conv2_wgrad_simt(+fold)", lambda: _C.conv5x5_wgrad(dy2, a1, dw2, dbb2, "simt")),
-        ("conv2_fwd_simt", lambda: _C.conv5x5_fwd(a1, w2, b2, True, "simt")),
-        ("bn_relu_pool2_fwd", lambda: _C.bn_relu_pool_fwd(y2, st2, g2, be2, None, None, None, 0.1, 1e-5, True)),
-        ("linear_fwd", lambda: _C.linear_fwd(flat, wf, bf)),
-        ("cross_entropy_fwd", lambda: _C.cross_entropy_fwd(logits, tgt)),
-        ("cross_entropy_bwd", lambda: _C.cross_entropy_bwd(probs, tgt, one)),
-        ("linear_bwd", lambda: _C.linear_bwd(dlog, flat, wf, True, dwf, dbf)),
-        ("bn_relu_pool2_bwd_reduce", lambda: _C.bn_relu_pool_bwd_reduce(d2, y2, sv2, g2, be2, True)),
-        ("bn_relu_pool2_bwd_apply", lambda: _C.bn_relu_pool_bwd_apply(d2, y2, sv2, g2, be2, sums2, st2[64:], True)),
-        ("conv2_dgrad_tcgen05(+repack)", lambda: _C.conv5x5_dgrad(dy2, w2, "tcgen05")),
-        ("conv2_dgrad_simt", lambda: _C.conv5x5_dgrad(dy2, w2, "simt")),
-        ("conv2_wgrad(+fold)", lambda: _C.conv5x5_wgrad(dy2, a1, dw2, dbb2, "auto")),
-        ("bn_relu_pool1_bwd_reduce", lambda: _C.bn_relu_pool_bwd_reduce(da1, y1, sv1, g1, be1, False)),
-        ("bn_relu_pool1_bwd_apply", lambda: _C.bn_relu_pool_bwd_apply(da1, y1, sv1, g1, be1, sums1, st1[32:], False)),
-        ("conv1_wgrad(+fold)", lambda: _C.conv5x5_wgrad(dy1, x1, dw1, dbb1, "auto")),
-        ("sgd_multi(10 tensors)", lambda: _C.sgd_multi(params, grads, [], 1e-4, None, 0.0, 0.0, 0.0, False, False, False)),
-        ("empty_launch_floor(torch.zero_ 1 elem)", lambda: one.zero_()),
+    ours = [
+        ("layer1 fwd: conv1+BN+ReLU+pool (1 kernel)", lambda: _C.convnet_l1_fwd(x, w1, b1, g1, be1, None, None, None, 0.1, 1e-5)),
+        ("layer2 fwd: conv2(tcgen05)+BN+ReLU+pool+fc (1 kernel)", lambda: _C.convnet_l2_fwd(p1, w2, b2, g2, be2, None, None, None, 0.1, 1e-5, wf, bf)),
+        ("cross-entropy fwd (+dlogits) (1 kernel)", lambda: _C.cross_entropy_fwd(logits, tgt, True)),
+        ("fc bwd: dX, dW, db (1 kernel)", lambda: _C.linear_bwd(dlog, p2.reshape(B, -1), wf, True, dwf, dbf)),
+        ("layer2 bwd: pool/ReLU/BN bwd + conv2 dgrad(tcgen05) (1 kernel)", lambda: _C.convnet_l2_bwd(dflat.view(B, 32, 7, 7), y2, sv2, g2, be2, w2, dg2, dbe2)),
+        ("conv2 wgrad, TMA window (tcgen05) + fold (2 kernels)", lambda: _C.conv5x5_wgrad_win(dy2, p1, dysum, dw2, db2)),
+        ("layer1 bwd: pool/ReLU/BN bwd + conv1 wgrad (1 kernel)", lambda: _C.convnet_l1_bwd(dp1, y1, x, sv1, g1, be1, dg1, dbe1, dw1, db1)),
+        ("SGD, 10 tensors (1 kernel)", lambda: _C.sgd_multi(params, grads, [], 1e-4, None, 0.0, 0.0, 0.0, False, False, False)),
     ]
+
+    # ---- library: the ATen / cuDNN / cuBLAS ops the reference's modules dispatch to, same shapes -----------------------
+    def lib_l1_fwd():
+        return F.max_pool2d(F.relu(F.batch_norm(F.conv2d(x, w1, b1, padding=2), None, None, g1, be1, True, 0.1, 1e-5)), 2, 2)
+
+    a1 = lib_l1_fwd()
+
+    def lib_l2_fwd():
+        return F.max_pool2d(F.relu(F.batch_norm(F.conv2d(a1, w2, b2, padding=2), None, None, g2, be2, True, 0.1, 1e-5)), 2, 2)
+
+    a2 = lib_l2_fwd()
+    flat = a2.reshape(B, -1)
+    lg = torch.addmm(bf, flat, wf.t())
+
+    def lib_fwd_bwd(make_out, inputs, grad_out):
+        ins = [t.detach().requires_grad_(True) for t in inputs]
+        out = make_out(*ins)
+        return torch.autograd.grad(out, ins, grad_out)
+
+    go1, go2 = torch.randn_like(a1), torch.randn_like(a2)
+    lib = [
+        ("layer1 fwd: cudnn conv + batch_norm + relu + max_pool2d", lib_l1_fwd),
+        ("layer2 fwd: cudnn conv + batch_norm + relu + max_pool2d", lib_l2_fwd),
+        ("fc fwd: addmm", lambda: torch.addmm(bf, flat, wf.t())),
+        ("cross-entropy fwd: log_softmax + nll_loss", lambda: F.cross_entropy(lg, tgt)),
+        ("cross-entropy fwd+bwd", lambda: lib_fwd_bwd(lambda l: F.cross_entropy(l, tgt), [lg], torch.ones((), device=dev))),
+        ("fc fwd+bwd: addmm, mm, mm, sum", lambda: lib_fwd_bwd(lambda f_, w_, b_: torch.addmm(b_, f_, w_.t()), [flat, wf, bf], torch.randn(B, 10, device=dev))),
+        ("layer2 fwd+bwd: + pool/relu/bn backward + cudnn dgrad + wgrad",
+         lambda: lib_fwd_bwd(lambda a_, w_, b_, g_, e_: F.max_pool2d(F.relu(F.batch_norm(F.conv2d(a_, w_, b_, padding=2), None, None, g_, e_, True, 0.1, 1e-5)), 2, 2),
+                             [a1, w2, b2, g2, be2], go2)),
+        ("layer1 fwd+bwd: + pool/relu/bn backward + cudnn wgrad",
+         lambda: lib_fwd_bwd(lambda w_, b_, g_, e_: F.max_pool2d(F.relu(F.batch_norm(F.conv2d(x, w_, b_, padding=2), None, None, g_, e_, True, 0.1, 1e-5)), 2, 2),
+                             [w1, b1, g1, be1], go1)),
+        ("conv2 cudnn fwd only", lambda: F.conv2d(a1, w2, b2, padding=2)),
+        ("conv2 cudnn dgrad only", lambda: torch.ops.aten.convolution_backward(go_c2, a1, w2, [32], [1, 1], [2, 2], [1, 1], False, [0, 0], 1, [True, False, False])),
+        ("conv2 cudnn wgrad(+bias) only", lambda: torch.ops.aten.convolution_backward(go_c2, a1, w2, [32], [1, 1], [2, 2], [1, 1], False, [0, 0], 1, [False, True, True])),
+        ("conv1 cudnn fwd only", lambda: F.conv2d(x, w1, b1, padding=2)),
+        ("conv1 cudnn wgrad(+bias) only", lambda: torch.ops.aten.convolution_backward(go_c1, x, w1, [16], [1, 1], [2, 2], [1, 1], False, [0, 0], 1, [False, True, True])),
+        ("SGD: _foreach_add_ over 10 tensors", lambda: torch._foreach_add_(params, grads, alpha=-1e-4)),
+    ]
+    go_c2 = torch.randn(B, 32, 14, 14, device=dev)
+    go_c1 = torch.randn(B, 16, 28, 28, device=dev)
+
     rows = []
-    for name, fn in ops:
-        r = bench(name, fn)
-        r["us_warm_min"] = bench(name, fn, flush=False)["us_min"]
-        rows.append(r)
-        print(f"{r['us_median']:9.2f} us (cold L2)  {r['us_warm_min']:9.2f} us (warm)  {name}", flush=True)
-    tot = sum(r["us_median"] for r in rows if "simt" not in r["op"] or "conv1" in r["op"])
-    print("sum of the step's kernels (cold):", round(tot, 1), "us")
+    for arm, ops in (("ours", ours), ("library", lib)):
+        for name, fn in ops:
+            try:
+                r = {"arm": arm, "op": name, "us_in_graph": graph_time(fn), "us_cold_eager": cold_time(fn)}
+            except Exception as e:  # noqa: BLE001 - an op that cannot be captured still gets its eager number
+                r = {"arm": arm, "op": name, "us_in_graph": None, "us_cold_eager": cold_time(fn), "note": f"{type(e).__name__}: {e}"[:120]}
+            rows.append(r)
+            g = f"{r['us_in_graph']:8.2f}" if r["us_in_graph"] is not None else "     n/a"
+            print(f"{arm:8s} {g} us in-graph   {r['us_cold_eager']:8.2f} us cold eager   {name}", flush=True)
+    floor = {"arm": "floor", "op": "empty launch (zero_ on 1 element)", "us_in_graph": graph_time(lambda: go_c1[0, 0, 0, :1].zero_()),
+             "us_cold_eager": cold_time(lambda: go_c1[0, 0, 0, :1].zero_())}
+    rows.append(floor)
+    print(f"floor    {floor['us_in_graph']:8.2f} us in-graph   {floor['us_cold_eager']:8.2f} us cold eager   {floor['op']}")
+    t_ours = sum(r["us_in_graph"] for r in rows if r["arm"] == "ours" and r["us_in_graph"])
+    print(f"ours, sum of the step's kernels in-graph: {t_ours:.1f} us")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "op_bench.json"), "w") as f:
         json.dump(rows, f, indent=1)
