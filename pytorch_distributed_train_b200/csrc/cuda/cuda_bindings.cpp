@@ -267,6 +267,34 @@ void register_cuda_bindings(py::module_& m) {
                           GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x));
     return py::make_tuple(out, y, saved, logits);
   });
+  m.def("convnet_fwd", [](const at::Tensor& x, const at::Tensor& w1, c10::optional<at::Tensor> b1, c10::optional<at::Tensor> g1,
+                          c10::optional<at::Tensor> be1, c10::optional<at::Tensor> rm1, c10::optional<at::Tensor> rv1, c10::optional<at::Tensor> nbt1,
+                          double mom1, double eps1, const at::Tensor& w2, c10::optional<at::Tensor> b2, c10::optional<at::Tensor> g2,
+                          c10::optional<at::Tensor> be2, c10::optional<at::Tensor> rm2, c10::optional<at::Tensor> rv2, c10::optional<at::Tensor> nbt2,
+                          double mom2, double eps2, const at::Tensor& fcw, c10::optional<at::Tensor> fcb) {
+    chk(x, "x"); chk(w1, "w1"); chk(w2, "w2"); chk(fcw, "fc weight");
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.numel() % 784 == 0 && w1.numel() == 400 && w2.numel() == 12800 && fcw.dim() == 2 && fcw.size(1) == 1568 && fcw.size(0) <= 16,
+                "convnet_fwd: x [B,1,28,28], w1 [16,1,5,5], w2 [32,16,5,5], fc weight [<=16, 1568] expected");
+    const int B = static_cast<int>(x.numel() / 784), ncls = static_cast<int>(fcw.size(0));
+    TORCH_CHECK(fused_convnet_supported(B), "convnet_fwd: batch ", B, " exceeds one CTA per SM");
+    at::Tensor y1 = at::empty({B, 28, 28, 16}, x.options()), p1 = at::empty({B, 18, 18, 16}, x.options()), saved1 = at::empty({32}, x.options());
+    at::Tensor y2 = at::empty({B, 14, 14, 32}, x.options()), out = at::empty({B, 32, 7, 7}, x.options()), saved2 = at::empty({64}, x.options());
+    at::Tensor logits = at::empty({B, ncls}, x.options());
+    auto nbt_ptr = [](c10::optional<at::Tensor>& t) -> long long* {
+      if (!t.has_value() || !t->defined()) return nullptr;
+      chk(*t, "num_batches_tracked", at::kLong);
+      return reinterpret_cast<long long*>(t->data_ptr<int64_t>());
+    };
+    ReduceScratch scr = scratch(x);
+    launch_convnet_fwd(x.data_ptr<float>(), w1.data_ptr<float>(), opt_ptr(b1, "b1"), opt_ptr(g1, "g1"), opt_ptr(be1, "be1"), y1.data_ptr<float>(),
+                       p1.data_ptr<float>(), saved1.data_ptr<float>(), opt_mut(rm1, "rm1"), opt_mut(rv1, "rv1"), nbt_ptr(nbt1), static_cast<float>(mom1),
+                       static_cast<float>(eps1), w2.data_ptr<float>(), opt_ptr(b2, "b2"), opt_ptr(g2, "g2"), opt_ptr(be2, "be2"), y2.data_ptr<float>(),
+                       out.data_ptr<float>(), saved2.data_ptr<float>(), opt_mut(rm2, "rm2"), opt_mut(rv2, "rv2"), nbt_ptr(nbt2), static_cast<float>(mom2),
+                       static_cast<float>(eps2), fcw.data_ptr<float>(), opt_ptr(fcb, "fc bias"), logits.data_ptr<float>(), ncls, B, scr.partials,
+                       GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x));
+    return py::make_tuple(p1, y1, saved1, out, y2, saved2, logits);
+  });
   m.def("convnet_l2_bwd", [](const at::Tensor& dout, const at::Tensor& y, const at::Tensor& saved, c10::optional<at::Tensor> gamma,
                              c10::optional<at::Tensor> beta, const at::Tensor& w, at::Tensor dgamma, at::Tensor dbeta) {
     chk(dout, "dout"); chk(y, "y"); chk(saved, "saved"); chk(w, "w"); chk(dgamma, "dgamma"); chk(dbeta, "dbeta");

@@ -739,6 +739,304 @@ convnet_l2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
   if (warp == 1) tmem_dealloc<64>(tmem_base);
 }
 
+// =====================================================================================================================
+// Whole forward pass in ONE kernel: layer 1 and layer 2 (+ classifier) of an image run in the same CTA, so the pooled
+// layer-1 activations never leave the SM on their way into conv2 — they are written straight into the swizzled,
+// zero-haloed shared-memory patch the tcgen05 descriptors read (the global copy is still written: backward needs it) —
+// and the conv2 weights are staged while conv1 computes.  Two grid barriers (BN1 and BN2 batch statistics), one launch.
+// =====================================================================================================================
+__global__ void __launch_bounds__(kL1Threads, 1)
+convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ g1,
+                   const float* __restrict__ be1, float* __restrict__ y1, float* __restrict__ p1, float* saved1, float* rm1, float* rv1,
+                   long long* nbt1, float mom1, float eps1, const float* __restrict__ w2, const float* __restrict__ b2,
+                   const float* __restrict__ g2, const float* __restrict__ be2, float* __restrict__ y2, float* __restrict__ out, float* saved2,
+                   float* rm2, float* rv2, long long* nbt2, float mom2, float eps2, const float* __restrict__ fcw,
+                   const float* __restrict__ fcb, float* __restrict__ logits, int ncls, float* partials, GridSync gs) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                                  // conv2 input patch, written by this CTA's layer-1 epilogue
+  uint8_t* sb = sa + kPatchAlloc;                      // conv2 weights
+  float* ys = reinterpret_cast<float*>(sb + L2FwdSmem::kB);
+  float* misc = ys + 196 * 32;                         // 2048 floats
+  float* s_part = misc;                                // [4][64] / [25 warps][16]
+  float* s_tmp2 = misc + 512;                          // [4][64]
+  float* s_tot2 = misc + 768;                          // [64]
+  float* s_scale2 = misc + 832;                        // [32]
+  float* s_shift2 = misc + 864;                        // [32]
+  __shared__ float xs[32 * 32];
+  __shared__ __align__(16) float ws[25 * 16];
+  __shared__ float red[kL1Warps * 32];
+  __shared__ float s_tmp[4 * 32];
+  __shared__ float s_tot[32];
+  __shared__ float s_scale[16], s_shift[16];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
+  const L1Map m(tid);
+  GridBar bar(gs);
+
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<64>(&tmem_slot);
+  for (int i = tid; i < kPatchAlloc / 16; i += kL1Threads) reinterpret_cast<float4*>(sa)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // halo = 0
+  l1_load_image(x + static_cast<size_t>(n) * 784, xs, tid);
+  if (tid < 400) {
+    const int tap = tid >> 4, co = tid & 15;
+    ws[tid] = w1[co * 25 + tap];
+  }
+  // conv2 weights: one (co, ci) pair per thread, 25 taps contiguous in global, 4 KiB apart in smem (SWIZZLE_128B K-major tiles);
+  // the loads fly while conv1 computes
+  float wv[25];
+  if (tid < 512) {
+#pragma unroll
+    for (int tap = 0; tap < 25; ++tap) wv[tap] = __ldg(w2 + tid * 25 + tap);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // ---- layer 1 ------------------------------------------------------------------------------------------------------
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = b1 ? __ldg(b1 + j) : 0.f;
+#pragma unroll 1
+  for (int kh = 0; kh < 5; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < 5; ++kw) {
+      const float xv = xs[(m.r + kh) * 32 + m.c + kw];
+      const float4* wt = reinterpret_cast<const float4*>(ws + (kh * 5 + kw) * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 wq = wt[q];
+        acc[4 * q + 0] = fmaf(xv, wq.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(xv, wq.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(xv, wq.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(xv, wq.w, acc[4 * q + 3]);
+      }
+    }
+  }
+  if (tid < 512) {
+    const int co = tid >> 4, ci = tid & 15;
+    uint8_t* dst = sb + sw128_off(co, ci >> 2) + (ci & 3) * 4;
+#pragma unroll
+    for (int tap = 0; tap < 25; ++tap) *reinterpret_cast<float*>(dst + tap * 4096) = wv[tap];
+  }
+  {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] = m.valid ? acc[j] : 0.f;
+      v[16 + j] = m.valid ? acc[j] * acc[j] : 0.f;
+    }
+    warp_transpose_reduce32(v, lane);
+    red[warp * 32 + lane] = v[0];
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.f;
+#pragma unroll 5
+    for (int wi = 0; wi < kL1Warps; ++wi) s += red[wi * 32 + tid];
+    partials[static_cast<size_t>(n) * 32 + tid] = s;
+  }
+  bar.sync(gs);
+  fold_rows<32>(partials, B, s_tmp, s_tot);
+  if (tid < 16) {
+    const float cnt = static_cast<float>(B) * 784.f;
+    const float mean = s_tot[tid] / cnt;
+    const float var = fmaxf(s_tot[16 + tid] / cnt - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps1);
+    const float g = g1 ? g1[tid] : 1.f, b = be1 ? be1[tid] : 0.f;
+    s_scale[tid] = g * invstd;
+    s_shift[tid] = b - mean * g * invstd;
+    if (n == 0) {
+      saved1[tid] = mean;
+      saved1[16 + tid] = invstd;
+      if (rm1) {
+        const float unbiased = var * (cnt / fmaxf(cnt - 1.f, 1.f));
+        rm1[tid] = (1.f - mom1) * rm1[tid] + mom1 * mean;
+        rv1[tid] = (1.f - mom1) * rv1[tid] + mom1 * unbiased;
+      }
+      if (nbt1 && tid == 0) *nbt1 += 1;
+    }
+  }
+  __syncthreads();
+  {
+    float z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float t = fmaxf(fmaf(acc[j], s_scale[j], s_shift[j]), 0.f);
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2));
+      z[j] = t;
+    }
+    if (m.valid) {  // lane d of the window owns channels 4d..4d+3 = one 16-byte chunk of the 128-byte patch row
+      float4 o;
+      if (m.d == 0) o = make_float4(z[0], z[1], z[2], z[3]);
+      else if (m.d == 1) o = make_float4(z[4], z[5], z[6], z[7]);
+      else if (m.d == 2) o = make_float4(z[8], z[9], z[10], z[11]);
+      else o = make_float4(z[12], z[13], z[14], z[15]);
+      const int P = (m.ph + 2) * kPW + m.pw + 2;
+      *reinterpret_cast<float4*>(sa + sw128_off(P, m.d)) = o;                                   // conv2 reads this one
+      reinterpret_cast<float4*>(p1 + (static_cast<size_t>(n) * 324 + P) * 16)[m.d] = o;         // backward (conv2 wgrad) reads this one
+    }
+  }
+  fence_proxy_async_smem();   // generic-proxy writes of the patch and of the weights → visible to the tensor core
+  __syncthreads();
+  // ---- layer 2: 100 MMAs, one elected thread -----------------------------------------------------------------------------
+  if (warp == 0) {
+    tc_fence_after();
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, 32);
+      const uint64_t ad0 = umma_desc_kmajor<128>(smem_u32(sa)), bd0 = umma_desc_kmajor<128>(smem_u32(sb));
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll 1
+        for (int kh = 0; kh < 5; ++kh) {
+          const uint64_t ad = ad0 + static_cast<uint64_t>(((7 * t + kh) * kPW * 128) >> 4);
+          const uint64_t bd = bd0 + static_cast<uint64_t>((kh * 5 * 4096) >> 4);
+#pragma unroll
+          for (int kw = 0; kw < 5; ++kw) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_tf32(tmem_base + t * 32, ad + ((kw * 128 + k * 32) >> 4), bd + ((kw * 4096 + k * 32) >> 4), idesc, (kh | kw | k) != 0);
+          }
+        }
+      }
+      umma_commit(&bar_mma);
+    }
+    __syncwarp();
+  }
+  // meanwhile: everything layer 1 still owes to global memory (nothing in this kernel waits for it)
+  if (m.valid) {
+    float4* yp = reinterpret_cast<float4*>(y1 + ((static_cast<size_t>(n) * 28 + m.r) * 28 + m.c) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) yp[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+  for (int i = tid; i < 324 * 4; i += kL1Threads) {
+    const int P = i >> 2, pr = P / 18, pc = P - pr * 18;
+    if (pr < 2 || pr >= 16 || pc < 2 || pc >= 16) reinterpret_cast<float4*>(p1 + (static_cast<size_t>(n) * 324 + P) * 16)[i & 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (warp >= 4 && warp < 8) {   // epilogue: TMEM lane quadrant = warp % 4
+    mbar_wait(&bar_mma, 0);
+    __syncwarp();
+    tc_fence_after();
+    const int quad = warp & 3, rr = quad * 32 + lane;
+    const int orow = rr / kPW, ow = rr - orow * kPW;
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float t16[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + t * 32 + c0, t16);
+        if (rr < 126 && ow < 14) {
+          const int pix = (7 * t + orow) * 14 + ow;
+          float4* yl = reinterpret_cast<float4*>(ys + pix * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int cq = (c0 >> 2) + q;
+            float4 o = make_float4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+            if (b2) { o.x += __ldg(b2 + 4 * cq); o.y += __ldg(b2 + 4 * cq + 1); o.z += __ldg(b2 + 4 * cq + 2); o.w += __ldg(b2 + 4 * cq + 3); }
+            yl[(cq + pix) & 7] = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (tid < 128) {
+    const int c = tid & 31, part = tid >> 5;
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = part * 49; p < part * 49 + 49; ++p) {
+      const float val = ys[p * 32 + ((((c >> 2) + p) & 7) << 2) + (c & 3)];
+      s1 += val;
+      s2 = fmaf(val, val, s2);
+    }
+    s_part[part * 64 + c] = s1;
+    s_part[part * 64 + 32 + c] = s2;
+  }
+  __syncthreads();
+  float* partials2 = partials + static_cast<size_t>(B) * 32;
+  if (tid < 64) partials2[static_cast<size_t>(n) * 64 + tid] = (s_part[tid] + s_part[64 + tid]) + (s_part[128 + tid] + s_part[192 + tid]);
+  bar.sync(gs);
+  for (int i = tid; i < 196 * 8; i += kL1Threads) {
+    const int pix = i >> 3, q = i & 7;
+    reinterpret_cast<float4*>(y2 + (static_cast<size_t>(n) * 196 + pix) * 32)[q] = reinterpret_cast<const float4*>(ys + pix * 32)[(q + pix) & 7];
+  }
+  fold_rows<64>(partials2, B, s_tmp2, s_tot2);
+  if (tid < 32) {
+    const float cnt = static_cast<float>(B) * 196.f;
+    const float mean = s_tot2[tid] / cnt;
+    const float var = fmaxf(s_tot2[32 + tid] / cnt - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps2);
+    const float g = g2 ? g2[tid] : 1.f, b = be2 ? be2[tid] : 0.f;
+    s_scale2[tid] = g * invstd;
+    s_shift2[tid] = b - mean * g * invstd;
+    if (n == 0) {
+      saved2[tid] = mean;
+      saved2[32 + tid] = invstd;
+      if (rm2) {
+        const float unbiased = var * (cnt / fmaxf(cnt - 1.f, 1.f));
+        rm2[tid] = (1.f - mom2) * rm2[tid] + mom2 * mean;
+        rv2[tid] = (1.f - mom2) * rv2[tid] + mom2 * unbiased;
+      }
+      if (nbt2 && tid == 0) *nbt2 += 1;
+    }
+  }
+  __syncthreads();
+  float* pool = reinterpret_cast<float*>(sb);   // the weights are dead after the MMAs
+  for (int i = tid; i < 1568; i += kL1Threads) {
+    const int c = i & 31, pp = i >> 5, ph = pp / 7, pw = pp - ph * 7;
+    const float sc = s_scale2[c], sh = s_shift2[c];
+    float mx = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int p = (2 * ph + (d >> 1)) * 14 + 2 * pw + (d & 1);
+      mx = fmaxf(mx, fmaf(ys[p * 32 + ((((c >> 2) + p) & 7) << 2) + (c & 3)], sc, sh));
+    }
+    pool[c * 49 + pp] = mx;
+  }
+  __syncthreads();
+  for (int i = tid; i < 1568; i += kL1Threads) out[static_cast<size_t>(n) * 1568 + i] = pool[i];
+  if (logits != nullptr) {
+    // classifier: thread t owns features t and t + 800 for every class (≤ 16): all weight loads independent
+    float accv[16];
+    const float pv0 = pool[tid], pv1 = (tid + kL1Threads < 1568) ? pool[tid + kL1Threads] : 0.f;
+#pragma unroll
+    for (int c16 = 0; c16 < 16; ++c16) {
+      float sacc = 0.f;
+      if (c16 < ncls) {
+        const float* wr = fcw + static_cast<size_t>(c16) * 1568 + tid;
+        sacc = pv0 * __ldg(wr);
+        if (tid + kL1Threads < 1568) sacc = fmaf(pv1, __ldg(wr + kL1Threads), sacc);
+      }
+      accv[c16] = sacc;
+    }
+#pragma unroll
+    for (int c16 = 0; c16 < 16; ++c16) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) accv[c16] += __shfl_xor_sync(0xffffffffu, accv[c16], off);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c16 = 0; c16 < 16; ++c16) s_part[warp * 16 + c16] = accv[c16];
+    }
+    __syncthreads();
+    if (tid < ncls) {
+      float sfin = fcb ? fcb[tid] : 0.f;
+#pragma unroll 5
+      for (int wi = 0; wi < kL1Warps; ++wi) sfin += s_part[wi * 16 + tid];
+      logits[static_cast<size_t>(n) * ncls + tid] = sfin;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<64>(tmem_base);
+}
+
 // ---- layer 2 backward: pool/ReLU/BN backward + conv2 data gradient ---------------------------------------------------------
 struct L2BwdSmem {
   static constexpr int kB = 25 * 16 * 128;       // dgrad weights: [tap][16 ci][128 B = 32 co]                  51,200
@@ -1035,6 +1333,15 @@ void launch_convnet_l2_fwd(const float* x, const float* w, const float* bias, co
   CUtensorMap tm_x = make_patch_map(x, 16, 18, 18, B);
   launch_coop(convnet_l2_fwd_kernel, B, kL2Threads, static_cast<size_t>(L2FwdSmem::kTotal), st, "convnet_l2_fwd", tm_x, w, bias, gamma, beta, y, out,
               saved, running_mean, running_var, nbt, momentum, eps, fcw, fcb, logits, ncls, partials, gs);
+}
+
+void launch_convnet_fwd(const float* x, const float* w1, const float* b1, const float* g1, const float* be1, float* y1, float* p1, float* saved1,
+                        float* rm1, float* rv1, long long* nbt1, float mom1, float eps1, const float* w2, const float* b2, const float* g2,
+                        const float* be2, float* y2, float* out, float* saved2, float* rm2, float* rv2, long long* nbt2, float mom2, float eps2,
+                        const float* fcw, const float* fcb, float* logits, int ncls, int B, float* partials, GridSync gs, cudaStream_t st) {
+  if (logits != nullptr && ncls > 16) throw std::invalid_argument("convnet_fwd: the fused classifier handles at most 16 classes");
+  launch_coop(convnet_fwd_kernel, B, kL1Threads, static_cast<size_t>(L2FwdSmem::kTotal), st, "convnet_fwd", x, w1, b1, g1, be1, y1, p1, saved1, rm1, rv1,
+              nbt1, mom1, eps1, w2, b2, g2, be2, y2, out, saved2, rm2, rv2, nbt2, mom2, eps2, fcw, fcb, logits, ncls, partials, gs);
 }
 
 void launch_convnet_l2_bwd(const float* dout, const float* y, const float* saved, const float* gamma, const float* beta, const float* w,

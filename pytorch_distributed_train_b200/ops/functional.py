@@ -138,8 +138,17 @@ class _FusedLayer1(torch.autograd.Function):
     """conv1 + BN1 + ReLU + pool1 forward, and its whole backward, as one cooperative kernel each."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps):
-        out, y, saved = _C.convnet_l1_fwd(x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps)
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, whole=None):
+        if whole is not None:
+            # ONE launch for the whole forward pass (csrc/cuda/fused_convnet.cu: convnet_fwd_kernel): layer 2 and the
+            # classifier of an image run in the same CTA; their results are handed to the next autograd nodes through `whole`
+            c2, b2, fc = whole["conv2"], whole["bn2"], whole["fc"]
+            out, y, saved, p2, y2, saved2, logits = _C.convnet_fwd(
+                x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, c2.weight, c2.bias, b2.weight, b2.bias,
+                b2.running_mean, b2.running_var, b2.num_batches_tracked, float(b2.momentum), float(b2.eps), fc.weight, fc.bias)
+            whole["layer2"] = (p2, y2, saved2, logits)
+        else:
+            out, y, saved = _C.convnet_l1_fwd(x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps)
         ctx.save_for_backward(x, y, saved, gamma, beta)
         ctx.params = (w, b, gamma, beta)
         return out  # [B,18,18,16]: zero-haloed NHWC frame
@@ -153,7 +162,7 @@ class _FusedLayer1(torch.autograd.Function):
         dg = _grad_dst(g_p, gamma)
         dbe = _grad_dst(be_p, beta)
         _C.convnet_l1_bwd(dp.contiguous(), y, x, saved, gamma, beta, dg, dbe, dw, db)
-        return None, dw, db, dg, dbe, None, None, None, None, None
+        return None, dw, db, dg, dbe, None, None, None, None, None, None
 
 
 class _FusedLayer2(torch.autograd.Function):
@@ -162,8 +171,11 @@ class _FusedLayer2(torch.autograd.Function):
     tensor-core weight gradient."""
 
     @staticmethod
-    def forward(ctx, p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb):
-        out, y, saved, logits = _C.convnet_l2_fwd(p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb)
+    def forward(ctx, p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb, whole=None):
+        if whole is not None and "layer2" in whole:
+            out, y, saved, logits = whole.pop("layer2")   # produced by the whole-forward launch of layer 1's node
+        else:
+            out, y, saved, logits = _C.convnet_l2_fwd(p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb)
         ctx.save_for_backward(p1, y, saved, gamma, beta, w)
         ctx.params = (w, b, gamma, beta)
         ctx.mark_non_differentiable(logits)
@@ -183,7 +195,7 @@ class _FusedLayer2(torch.autograd.Function):
             _C.conv5x5_wgrad_win(dy, p1, dysum, dw, db)
         else:  # im2col-gather kernel on the frames' interiors
             _C.conv5x5_wgrad(dy[:, 2:16, 2:16, :].contiguous(), p1[:, 2:16, 2:16, :].contiguous(), dw, db, "auto")
-        return dp1, dw, db, dg, dbe, None, None, None, None, None, None, None
+        return dp1, dw, db, dg, dbe, None, None, None, None, None, None, None, None
 
 
 class _FusedClassifier(torch.autograd.Function):
@@ -206,12 +218,15 @@ class _FusedClassifier(torch.autograd.Function):
 
 
 def fused_convnet_forward(x: torch.Tensor, model) -> torch.Tensor:
-    """The reference ConvNet's training forward as TWO kernels (ref: ddp_example.py:36-41)."""
+    """The reference ConvNet's training forward as ONE kernel (two with PDT_FUSED_WHOLE_FWD=0) (ref: ddp_example.py:36-41)."""
     c1, b1, c2, b2, fc = model.layer1[0], model.layer1[1], model.layer2[0], model.layer2[1], model.fc
+    whole = None
+    if os.environ.get("PDT_FUSED_WHOLE_FWD", "1") != "0" and fc.weight.shape[0] <= 16 and hasattr(_C, "convnet_fwd"):
+        whole = {"conv2": c2, "bn2": b2, "fc": fc}
     p1 = _FusedLayer1.apply(x, c1.weight, c1.bias, b1.weight, b1.bias, b1.running_mean, b1.running_var, b1.num_batches_tracked,
-                            float(b1.momentum), float(b1.eps))
+                            float(b1.momentum), float(b1.eps), whole)
     p2, logits = _FusedLayer2.apply(p1, c2.weight, c2.bias, b2.weight, b2.bias, b2.running_mean, b2.running_var, b2.num_batches_tracked,
-                                    float(b2.momentum), float(b2.eps), fc.weight, fc.bias)
+                                    float(b2.momentum), float(b2.eps), fc.weight, fc.bias, whole)
     return _FusedClassifier.apply(p2, fc.weight, fc.bias, logits)
 
 

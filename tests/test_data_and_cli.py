@@ -97,3 +97,34 @@ def test_train_script_checkpoint_and_resume(tmp_path):
     b = subprocess.run(base + ["--epochs", "2", "--resume", ck], capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert b.returncode == 0, b.stderr[-2000:]
     assert "Resumed from" in b.stdout and "Epoch [2/2], Step [5/10]" in b.stdout and "Epoch [1/2]" not in b.stdout
+
+
+def test_native_batch_stager_matches_python_loader_and_never_overwrites_a_retained_batch(tmp_path):
+    """_C.BatchStager (C++ worker thread + ring of staging buffers) must yield exactly what the Python loader yields,
+    for the uint8 (MNIST, ToTensor's 1/255) and float32 paths, ragged last batch included — and a batch the user keeps
+    (list(loader)) must never be overwritten when its ring slot comes around again (advisor finding, round 1)."""
+    import pytorch_distributed_train_b200 as pdt
+
+    pdt.data.synthesize_mnist_files(str(tmp_path), train=True, n=1030)
+    m = pdt.data.MNIST(str(tmp_path), train=True)
+    assert m.native_source() is not None
+    for ds in (m, pdt.data.SyntheticMNIST(1030, seed=3)):
+        smp = pdt.DistributedSampler(ds, num_replicas=2, rank=1, shuffle=True, seed=7)
+        fast = pdt.DataLoader(ds, batch_size=100, sampler=smp)
+        slow = pdt.DataLoader(ds, batch_size=100, sampler=smp, native=False)
+        assert fast._native_src is not None and slow._native_src is None
+        for epoch in range(2):
+            smp.set_epoch(epoch)
+            kept = list(fast)                      # 6 batches through an 8-slot ring, all retained
+            ref = list(slow)
+            assert len(kept) == len(ref) == 6 and kept[-1][0].shape[0] == 15
+            for (xa, ya), (xb, yb) in zip(kept, ref):
+                assert torch.allclose(xa, xb) and torch.equal(ya, yb)
+    # more batches than ring slots, every one retained: earlier batches must keep their contents
+    big = pdt.DataLoader(m, batch_size=10)
+    kept = list(big)
+    assert len(kept) == 103
+    ref = list(pdt.DataLoader(m, batch_size=10, native=False))
+    assert all(torch.allclose(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(kept, ref))
+    # a transform forces the Python path
+    assert pdt.data.MNIST(str(tmp_path), train=True, transform=lambda t: t).native_source() is None
