@@ -29,6 +29,7 @@
 #include "umma_ptx.cuh"
 #include "cuda_utils.h"
 #include "grid_fold.cuh"
+#include "grid_sync.cuh"
 
 namespace pdt {
 
@@ -787,15 +788,7 @@ struct WgradCfg {
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = byte stride between 32-element MN atoms, SBO = byte
 // stride between 4-row K atoms (512 B when the 8 rows of one MMA are contiguous).
 // [cf. UMMA::Layout_MN_SW128_32B_Atom and make_umma_desc<Major::MN>, cute/atom/mma_traits_sm100.hpp]
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(1) << 61;
-  return d;
-}
+// umma_desc_mn_sw128_32b: umma_ptx.cuh
 
 __global__ void __launch_bounds__(192, 1) conv5x5_wgrad_umma_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap tm_dy,
                                                                     const float* __restrict__ ones, float* __restrict__ partials, int B,
@@ -996,7 +989,8 @@ struct WgradWinCfg {
 };
 
 __global__ void __launch_bounds__(192, 1) conv5x5_wgrad_win_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
-                                                                   float* __restrict__ partials, int B) {
+                                                                   float* __restrict__ partials, int B, const float* __restrict__ dysum,
+                                                                   float* __restrict__ dw, float* __restrict__ db, GridSync gs) {
   using Cfg = WgradWinCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1012,6 +1006,7 @@ __global__ void __launch_bounds__(192, 1) conv5x5_wgrad_win_kernel(const __grid_
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int num_tiles = 2 * B;   // (image, half)
+  GridBar bar(gs);
   if (tid == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_dy);
@@ -1100,6 +1095,38 @@ __global__ void __launch_bounds__(192, 1) conv5x5_wgrad_win_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (dw == nullptr) return;   // two-launch variant: wgrad_win_fold_kernel folds
+  // ---- in-kernel fold (cooperative launch): after a grid barrier every CTA folds a share of the 400 × 32 outputs over the
+  //      per-CTA partials in a fixed order — thread = (co, one of six partial classes), classes combined through smem ----------
+  bar.sync(gs);
+  float* s_f = reinterpret_cast<float*>(smem);   // [6][32]
+  const int co = tid & 31, part = tid >> 5, nparts = gridDim.x;
+  for (int i = blockIdx.x; i < 401; i += gridDim.x) {
+    float acc = 0.f;
+    if (i < 400) {
+      const int tap = i >> 4, ci = i & 15, kh = tap / 5, kw = tap - kh * 5;
+      const int m = (3 * kh + (kw >> 1)) * 32 + (kw & 1) * 16 + ci;
+      const float* p = partials + static_cast<size_t>(m) * 32 + co;
+      const size_t stride = static_cast<size_t>(Cfg::kMRows) * 32;
+      for (int c = part; c < nparts; c += 48) {   // eight independent L2 loads in flight
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = (c + 6 * j < nparts) ? __ldcg(p + static_cast<size_t>(c + 6 * j) * stride) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += t[j];
+      }
+    } else {
+      for (int n = part; n < B; n += 6) acc += __ldcg(dysum + static_cast<size_t>(n) * 32 + co);
+    }
+    __syncthreads();
+    s_f[part * 32 + co] = acc;
+    __syncthreads();
+    if (part == 0) {
+      const float tot = ((s_f[co] + s_f[32 + co]) + (s_f[64 + co] + s_f[96 + co])) + (s_f[128 + co] + s_f[160 + co]);
+      if (i < 400) dw[(co * 16 + (i & 15)) * 25 + (i >> 4)] = tot;
+      else if (db) db[co] = tot;
+    }
+  }
 }
 
 // dw[co][ci][kh][kw] = Σ_cta partial[cta][q·32 + (kw&1)·16 + ci][co] with q = 3·kh + kw/2;  db[co] = Σ_n dysum[n][co]
@@ -1450,27 +1477,47 @@ void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, fl
   check_launch("wgrad_fold");
 }
 
+void make_wgrad_win_tmaps(const float* x_pad, const float* dy_pad, int B, CUtensorMap* tm_x, CUtensorMap* tm_dy) {
+  const uint64_t rows = static_cast<uint64_t>(B) * WgradWinCfg::kFrame;
+  // overlapping-row view of the haloed NHWC frames: row r = the 32 floats starting at position r (two adjacent pixels × 16 ch)
+  cuuint64_t dims[2] = {32, rows - 1};
+  cuuint64_t strides[1] = {64};
+  cuuint32_t box[2] = {32, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = driver().cuTensorMapEncodeTiled(tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x_pad), dims, strides, box, estr,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(overlapping rows) failed: " + cu_error(r));
+  *tm_dy = make_tmap_2d(dy_pad, 32, rows, 32, kTileM, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
 void launch_conv5x5_wgrad_win(const float* dy_pad, const float* x_pad, const float* dysum, float* dw, float* db, int B, ReduceScratch scr,
-                              cudaStream_t st) {
+                              cudaStream_t st, GridSync gs) {
   using Cfg = WgradWinCfg;
   const int grid = std::min(B, sm_count());
   if (static_cast<long long>(grid) * Cfg::kMRows * 32 > scr.capacity_floats) throw std::invalid_argument("conv5x5 wgrad (window): scratch too small");
-  const uint64_t rows = static_cast<uint64_t>(B) * Cfg::kFrame;
-  // overlapping-row view of the haloed NHWC frames: row r = the 32 floats starting at position r (two adjacent pixels × 16 ch)
-  CUtensorMap tm_x;
-  {
-    cuuint64_t dims[2] = {32, rows - 1};
-    cuuint64_t strides[1] = {64};
-    cuuint32_t box[2] = {32, 64};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = driver().cuTensorMapEncodeTiled(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x_pad), dims, strides, box, estr,
-                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(overlapping rows) failed: " + cu_error(r));
-  }
-  CUtensorMap tm_dy = make_tmap_2d(dy_pad, 32, rows, 32, kTileM, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  CUtensorMap tm_x, tm_dy;
+  make_wgrad_win_tmaps(x_pad, dy_pad, B, &tm_x, &tm_dy);
   opt_in_smem(conv5x5_wgrad_win_kernel, Cfg::kSmem);
-  conv5x5_wgrad_win_kernel<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tm_x, tm_dy, scr.partials, B);
+  static const bool one_launch = [] { const char* e = getenv("PDT_WGRAD_WIN_FOLD"); return !(e && e[0] == '0'); }();
+  if (one_launch && gs.epoch != nullptr) {
+    // cooperative launch (one CTA per SM at most): the fold happens after a grid barrier inside the kernel
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv5x5_wgrad_win_kernel, tm_x, tm_dy, scr.partials, B, dysum, dw, db, gs);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("launch of conv5x5_wgrad_win failed: ") + cudaGetErrorString(e));
+    count_kernel_launch();
+    return;
+  }
+  conv5x5_wgrad_win_kernel<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tm_x, tm_dy, scr.partials, B, nullptr, nullptr, nullptr, GridSync{nullptr, nullptr});
   check_launch("conv5x5_wgrad_win");
   wgrad_win_fold_kernel<<<401, 256, 0, st>>>(scr.partials, grid, dysum, B, dw, db);
   check_launch("wgrad_win_fold");

@@ -1,7 +1,9 @@
 // tcgen05/TMEM/TMA kernels (sm_100a): TF32 GEMM self-test and the implicit-GEMM 5x5 convolution.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "grid_sync.cuh"
 #include "ops_kernels.h"
 
 namespace pdt {
@@ -33,8 +35,13 @@ void launch_conv5x5_wgrad_tcgen05(const float* dy, const float* x, float* dw, fl
 
 // Window formulation for zero-haloed 18×18 frames (cooperative fused layers): dy_pad [B,18,18,32], x_pad [B,18,18,16], dysum [B,32]
 // (per-image Σdy rows, folded into db).  All operands arrive by TMA: no im2col gather.
+// With a grid-barrier descriptor the per-CTA partials are folded inside the same (cooperative) launch; without one a second
+// kernel folds them.
+// Tensor maps of the window weight gradient: tm_x = overlapping-row view of the x frame [B,18,18,16] (row pitch 64 B, row length
+// 128 B, box 64 rows), tm_dy = the dy frame [B,18,18,32] as rows of 32 floats (box 128 rows); both SWIZZLE_128B_ATOM_32B.
+void make_wgrad_win_tmaps(const float* x_pad, const float* dy_pad, int B, CUtensorMap* tm_x, CUtensorMap* tm_dy);
 void launch_conv5x5_wgrad_win(const float* dy_pad, const float* x_pad, const float* dysum, float* dw, float* db, int B, ReduceScratch scr,
-                              cudaStream_t st);
+                              cudaStream_t st, GridSync gs = GridSync{nullptr, nullptr});
 
 // D[M,N] = A[M,K] · B[N,K]^T, fp32 in/out, TF32 tensor-core math (K % 4 == 0, N % 16 == 0, N <= 256).
 void launch_gemm_tf32_tcgen05(const float* a, const float* b, float* d, int M, int N, int K, cudaStream_t st);

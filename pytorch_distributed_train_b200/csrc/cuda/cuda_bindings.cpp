@@ -235,6 +235,27 @@ void register_cuda_bindings(py::module_& m) {
                           scr.partials, scr.partials + static_cast<size_t>(B) * 64,
                           GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x));
   });
+  m.def("convnet_l1_bwd_wgrad", [](const at::Tensor& dp, const at::Tensor& y, const at::Tensor& x, const at::Tensor& saved,
+                                   c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta, at::Tensor dgamma, at::Tensor dbeta, at::Tensor dw,
+                                   c10::optional<at::Tensor> db, const at::Tensor& dy2_pad, const at::Tensor& x2_pad, const at::Tensor& dysum2,
+                                   at::Tensor dw2, c10::optional<at::Tensor> db2) {
+    chk(dp, "dp"); chk(y, "y"); chk(x, "x"); chk(saved, "saved"); chk(dgamma, "dgamma"); chk(dbeta, "dbeta"); chk(dw, "dw");
+    chk(dy2_pad, "dy2_pad"); chk(x2_pad, "x2_pad"); chk(dysum2, "dysum2"); chk(dw2, "dw2");
+    c10::cuda::CUDAGuard g(x.device());
+    const int B = static_cast<int>(y.size(0));
+    TORCH_CHECK(dp.numel() == static_cast<int64_t>(B) * 5184 && x.numel() == static_cast<int64_t>(B) * 784 && dw.numel() == 400 &&
+                    dgamma.numel() == 16 && dbeta.numel() == 16, "convnet_l1_bwd_wgrad: layer-1 shape mismatch");
+    TORCH_CHECK(dy2_pad.numel() == static_cast<int64_t>(B) * 324 * 32 && x2_pad.numel() == static_cast<int64_t>(B) * 324 * 16 &&
+                    dysum2.numel() == static_cast<int64_t>(B) * 32 && dw2.numel() == 12800, "convnet_l1_bwd_wgrad: layer-2 shape mismatch");
+    ReduceScratch scr = scratch(x);
+    const size_t l1_floats = static_cast<size_t>(B) * (64 + 512);
+    TORCH_CHECK(static_cast<long long>(l1_floats) + static_cast<long long>(B) * 512 * 32 <= scr.capacity_floats, "convnet_l1_bwd_wgrad: scratch too small");
+    launch_convnet_l1_bwd_wgrad(dp.data_ptr<float>(), y.data_ptr<float>(), x.data_ptr<float>(), saved.data_ptr<float>(), opt_ptr(gamma, "gamma"),
+                                opt_ptr(beta, "beta"), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"),
+                                dy2_pad.data_ptr<float>(), x2_pad.data_ptr<float>(), dysum2.data_ptr<float>(), dw2.data_ptr<float>(),
+                                opt_mut(db2, "db2"), B, scr.partials, scr.partials + static_cast<size_t>(B) * 64, scr.partials + l1_floats,
+                                GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x));
+  });
   m.def("convnet_l2_fwd", [](const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> gamma,
                              c10::optional<at::Tensor> beta, c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
                              c10::optional<at::Tensor> nbt, double momentum, double eps, c10::optional<at::Tensor> fcw,
@@ -318,8 +339,9 @@ void register_cuda_bindings(py::module_& m) {
     const int B = static_cast<int>(dy_pad.size(0));
     TORCH_CHECK(dy_pad.numel() == static_cast<int64_t>(B) * 324 * 32 && x_pad.numel() == static_cast<int64_t>(B) * 324 * 16 &&
                     dysum.numel() == static_cast<int64_t>(B) * 32 && dw.numel() == 12800, "conv5x5_wgrad_win: shape mismatch");
+    ReduceScratch scr = scratch(dy_pad);
     launch_conv5x5_wgrad_win(dy_pad.data_ptr<float>(), x_pad.data_ptr<float>(), dysum.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"), B,
-                             scratch(dy_pad), cur_stream(dy_pad));
+                             scr, cur_stream(dy_pad), GridSync{scr.counter + 512, scr.counter + 520});
   }, py::arg("dy_pad"), py::arg("x_pad"), py::arg("dysum"), py::arg("dw"), py::arg("db") = py::none());
 
   // ---- BN + ReLU + pool ------------------------------------------------------------------------------

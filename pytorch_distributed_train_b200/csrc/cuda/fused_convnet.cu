@@ -25,7 +25,9 @@
 #include <string>
 
 #include "cuda_utils.h"
+#include "conv_tcgen05.h"
 #include "fused_convnet.h"
+#include "grid_sync.cuh"
 #include "umma_ptx.cuh"
 
 namespace pdt {
@@ -33,55 +35,6 @@ namespace pdt {
 namespace {
 
 using namespace ptx;
-
-// ---------------------------------------------------------------------------------------------------------------------
-// grid barrier (sense = generation counter; count returns to zero, so the words are reusable across launches/replays)
-// ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_gpu(unsigned int* p, unsigned int v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Grid barrier: one arrival counter, one monotonically increasing epoch word.  Thread 0 of a CTA arrives with a fence +
-// atomicAdd; the last arriver zeroes the counter and publishes the barrier's epoch; everybody else polls the epoch word
-// with *relaxed* loads (one poller per CTA; an acquire per spin would invalidate L1 every iteration).  Everything read
-// after the barrier comes from L2 (ld.global.cg), the GPU's coherence point, so no trailing fence is needed.  Each CTA
-// tracks the epoch locally (read once at kernel start, +1 per barrier): no read of the word before arriving, nothing to
-// reset between launches or CUDA-graph replays, any grid size.  A flag-per-CTA variant (every CTA polling every flag)
-// was measured at 5.5 µs per barrier against 2-3 µs for the counter: 10^4 pollers on four cache lines (profiles/r2).
-struct GridBar {
-  unsigned int e;
-  __device__ __forceinline__ explicit GridBar(GridSync gs) : e(*reinterpret_cast<volatile unsigned int*>(gs.epoch)) {}
-  __device__ __forceinline__ void sync(GridSync gs) {
-    ++e;
-    __syncthreads();   // the CTA's partial row is complete
-    if (threadIdx.x == 0) {
-      __threadfence();   // ... and performed at GPU scope before the arrival (bar.sync makes the fence cumulative over the CTA)
-      const unsigned int prev = atomicAdd(gs.flags, 1u);
-      if (prev == gridDim.x - 1) {
-        st_relaxed_gpu(gs.flags, 0u);
-        __threadfence();
-        st_relaxed_gpu(gs.epoch, e);
-      } else {
-        while (static_cast<int>(ld_relaxed_gpu(gs.epoch) - e) < 0) {}
-      }
-    }
-    __syncthreads();
-  }
-  __device__ __forceinline__ void finish(GridSync) {}
-};
 
 // ---- optional phase trace (PDT_FUSED_TRACE=1): globaltimer stamps of thread 0 of every CTA, read back by tools ----------
 __device__ unsigned long long g_trace[4][160][12];
@@ -94,9 +47,17 @@ __device__ __forceinline__ void trace(int kernel, int phase) {
   }
 }
 
+// CTA-wide sync of the first NAMED threads (named barrier 1) or of the whole CTA (NAMED = 0): kernels with extra
+// role warps keep their "main" threads in step without involving the others.
+template <int NAMED>
+__device__ __forceinline__ void cta_sync() {
+  if constexpr (NAMED > 0) asm volatile("bar.sync 1, %0;" ::"n"(NAMED) : "memory");
+  else __syncthreads();
+}
+
 // Sum `rows` partial rows of `W` floats (written by other CTAs before a grid barrier) in a fixed order.
-// Called by all threads; the totals land in s_out[0..W).  s_tmp: [4][W] floats.  Needs blockDim.x >= 4*W.
-template <int W>
+// Called by all (main) threads; the totals land in s_out[0..W).  s_tmp: [4][W] floats.  Needs >= 4*W threads.
+template <int W, int NAMED = 0>
 __device__ __forceinline__ void fold_rows(const float* __restrict__ partials, int rows, float* s_tmp, float* s_out) {
   const int tid = threadIdx.x;
   if (tid < 4 * W) {
@@ -111,9 +72,9 @@ __device__ __forceinline__ void fold_rows(const float* __restrict__ partials, in
     }
     s_tmp[grp * W + col] = s;
   }
-  __syncthreads();
+  cta_sync<NAMED>();
   if (tid < W) s_out[tid] = (s_tmp[tid] + s_tmp[W + tid]) + (s_tmp[2 * W + tid] + s_tmp[3 * W + tid]);
-  __syncthreads();
+  cta_sync<NAMED>();
 }
 
 // Warp-level reduction of 32 per-thread values with 31 shuffles: after the call lane l holds Σ_lanes v[l] in v[0].
@@ -154,9 +115,10 @@ struct L1Map {
   }
 };
 
+template <int NAMED = 0>
 __device__ __forceinline__ void l1_load_image(const float* __restrict__ x, float* xs /*[32][32]*/, int tid) {
   for (int i = tid; i < 1024; i += kL1Threads) xs[i] = 0.f;
-  __syncthreads();
+  cta_sync<NAMED>();
   if (tid < 784) {
     const int rr = tid / 28, cc = tid - rr * 28;
     xs[(rr + 2) * 32 + cc + 2] = x[tid];
@@ -280,9 +242,30 @@ convnet_l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   trace(0, 5);
 }
 
-// ---- layer 1 backward -------------------------------------------------------------------------------------------------
-// dynamic smem: dys [784][16] | fold [25 warps][16 co][32 taps]
+// ---- layer 1 backward (+ conv2 weight gradient riding along) ---------------------------------------------------------------
+// dynamic smem: dys [784][16] | fold [25 warps][16 co][32 taps]   (+ WG: the tensor-core weight-gradient pipeline, below)
 constexpr int kL1BwdSmem = (784 * 16 + kL1Warps * 512) * 4;
+
+// The conv2 weight gradient of an image needs nothing from layer-1 backward — only the dy / x frames that layer-2 backward
+// left in global memory — and layer-1 backward leaves the tensor cores, TMA and most of shared memory idle.  With WG the
+// CTA carries two extra warps (a TMA producer and a tcgen05 issuer) that run the "window" weight gradient
+// (conv_tcgen05.cu: conv5x5_wgrad_win_kernel has the derivation) of the same image concurrently with the SIMT work of the
+// 25 layer-1 warps; its per-CTA partial [512][32] is read out of TMEM by 16 of the layer-1 warps just before the kernel's
+// second grid barrier, and folded after it next to the conv1 gradient.  One launch and one grid barrier less than running
+// the two kernels back to back, and the tensor-core pipeline hides completely behind the SIMT phases.
+struct L1WgCfg {
+  static constexpr int kThreads = kL1Threads + 64;        // + producer warp (25) + MMA warp (26)
+  static constexpr int kFrame = 18 * 18, kFirst = 2 * 18 + 2;
+  static constexpr int kAStageBytes = 4 * 8 * 1024;                // [4 tap pairs][64 positions][128 B]
+  // two dedicated A stages + three that alias the layer-1 staging buffers (dys | fold), which layer 1 does not touch before
+  // its first grid barrier has passed: the layer-1 threads wait for the tensor-core pipeline to drain before they write them
+  static constexpr int kOwnStages = 2, kAliasStages = 3, kStages = kOwnStages + kAliasStages;
+  static_assert(kAliasStages * kAStageBytes <= kL1BwdSmem, "aliased stages must fit into dys | fold");
+  static constexpr int kBBytes = 2 * 128 * 128;                    // both 128-position dy tiles of the image
+  static constexpr int kTmemCols = 128;
+  static constexpr int kOff = (kL1BwdSmem + 1023) / 1024 * 1024;   // pipeline starts 1024-aligned behind the layer-1 buffers
+  static constexpr size_t kSmem = 1024 + kOff + kOwnStages * kAStageBytes + kBBytes + 256;
+};
 
 __device__ __forceinline__ uint32_t f32_to_tf32(float v) {
   uint32_t r;
@@ -296,24 +279,118 @@ __device__ __forceinline__ void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(kL1Threads, 1)
+template <bool WG>
+__global__ void __launch_bounds__(WG ? L1WgCfg::kThreads : kL1Threads, 1)
 convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ saved,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* dgamma, float* dbeta, float* dw, float* db,
-                      float* partials, float* partials_w, GridSync gs) {
-  extern __shared__ __align__(16) float dsm[];
+                      float* partials, float* partials_w, GridSync gs,
+                      // WG only: conv2 weight gradient of the same image
+                      const __grid_constant__ CUtensorMap tm_x2, const __grid_constant__ CUtensorMap tm_dy2, float* __restrict__ wpart,
+                      const float* __restrict__ dysum2, float* dw2, float* db2) {
+  constexpr int NAMED = WG ? kL1Threads : 0;
+  extern __shared__ __align__(16) uint8_t dsm_raw[];
+  // WG: everything is placed relative to a 1024-aligned base (the swizzled TMA tiles need it)
+  uint8_t* dsm_b = WG ? reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dsm_raw) + 1023) & ~uintptr_t(1023)) : dsm_raw;
+  float* dsm = reinterpret_cast<float*>(dsm_b);
   float* dys = dsm;                  // [784][16]
   float* fold = dsm + 784 * 16;      // [25 warps][16][32]
+  uint8_t* sa = dsm_b + L1WgCfg::kOff;                              // WG: the two dedicated A stages
+  uint8_t* sb = sa + L1WgCfg::kOwnStages * L1WgCfg::kAStageBytes;   // WG: dy tiles
+  auto a_stage = [&](int s) -> uint8_t* {                           // WG: stage s of the A ring (2.. alias dys | fold)
+    return s < L1WgCfg::kOwnStages ? sa + s * L1WgCfg::kAStageBytes : dsm_b + (s - L1WgCfg::kOwnStages) * L1WgCfg::kAStageBytes;
+  };
+  uint64_t* afull = reinterpret_cast<uint64_t*>(sb + L1WgCfg::kBBytes);
+  uint64_t* aempty = afull + L1WgCfg::kStages;
+  uint64_t* bfull = aempty + L1WgCfg::kStages;
+  uint64_t* acc_full = bfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   __shared__ float xs[32 * 32];
   __shared__ float red[kL1Warps * 32];
   __shared__ float s_tmp[4 * 32];
   __shared__ float s_tot[32];
   __shared__ float s_scale[16], s_shift[16], s_mean[16], s_invstd[16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
+
+  if constexpr (WG) {
+    if (warp >= kL1Warps) {
+      // ================= tensor-core weight gradient of image n: producer (warp 25) and issuer (warp 26) =================
+      using Cfg = L1WgCfg;
+      if (warp == kL1Warps) {
+        if (lane == 0) {
+          tma_prefetch_desc(&tm_x2);
+          tma_prefetch_desc(&tm_dy2);
+          for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+          mbar_init(bfull, 1);
+          mbar_init(acc_full, 1);
+          fence_mbar_init();
+        }
+      } else {
+        tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+        tc_fence_before();
+      }
+      asm volatile("bar.sync 2, 64;" ::: "memory");   // barriers initialised, TMEM allocated: both role warps may start
+      asm volatile("bar.arrive 0, %0;" ::"n"(L1WgCfg::kThreads) : "memory");   // (1) ... and the layer-1 warps may use them (they sync on 0 later)
+      if (warp == kL1Warps) {
+        if (elect_one()) {
+          const int row0 = n * Cfg::kFrame + Cfg::kFirst;   // first interior position of the image's frames
+          mbar_arrive_expect_tx(bfull, Cfg::kBBytes);
+          tma_load_2d(sb, &tm_dy2, bfull, 0, row0);
+          tma_load_2d(sb + 128 * 128, &tm_dy2, bfull, 0, row0 + 128);
+          int g = 0;
+          for (int t = 0; t < 2; ++t)
+            for (int mt = 0; mt < 4; ++mt) {
+              const int npairs = mt == 3 ? 3 : 4;           // tap pair 15 does not exist
+              for (int half = 0; half < 2; ++half, ++g) {
+                const int s = g % Cfg::kStages;
+                mbar_wait(&aempty[s], ((g / Cfg::kStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&afull[s], npairs * 8192);
+                for (int a = 0; a < npairs; ++a) {
+                  const int q = mt * 4 + a, kh = q / 3, kw = 2 * (q - kh * 3);
+                  // x position of dy position P for tap (kh, kw): P + (kh-2)·18 + (kw-2); rows outside the tensor are zero-filled
+                  tma_load_2d(a_stage(s) + a * 8192, &tm_x2, &afull[s], 0, row0 + 128 * t + 64 * half + (kh - 2) * 18 + (kw - 2));
+                }
+              }
+            }
+        }
+      } else {
+        tc_fence_after();
+        const uint32_t tmem_base = *tmem_slot;
+        constexpr uint32_t idesc = umma_idesc_tf32(128, 32) | (1u << 15) | (1u << 16);  // A and B are MN-major
+        mbar_wait(bfull, 0);
+        int g = 0;
+        for (int t = 0; t < 2; ++t)
+          for (int mt = 0; mt < 4; ++mt)
+            for (int h = 0; h < 2; ++h, ++g) {
+              const int s = g % Cfg::kStages;
+              mbar_wait(&afull[s], (g / Cfg::kStages) & 1);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a0 = smem_u32(a_stage(s)), b0 = smem_u32(sb) + t * 16 * 1024 + h * 8 * 1024;
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb)
+                  umma_tf32(tmem_base + mt * 32, umma_desc_mn_sw128_32b(a0 + kb * 1024, 8 * 1024, 512),
+                            umma_desc_mn_sw128_32b(b0 + kb * 1024, 1024, 512), idesc, (t | h | kb) != 0);
+                umma_commit(&aempty[s]);
+              }
+              __syncwarp();
+            }
+        if (elect_one()) umma_commit(acc_full);
+        __syncwarp();
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(L1WgCfg::kThreads) : "memory");   // (2) the layer-1 warps have read the accumulators
+      if (warp == kL1Warps + 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(*tmem_slot);
+      }
+      return;
+    }
+  }
+
   const L1Map m(tid);
   GridBar bar(gs);
   trace(1, 0);
 
-  l1_load_image(x + static_cast<size_t>(n) * 784, xs, tid);
+  l1_load_image<NAMED>(x + static_cast<size_t>(n) * 784, xs, tid);
   if (tid < 16) {
     const float mean = saved[tid], invstd = saved[16 + tid];
     const float g = gamma ? gamma[tid] : 1.f, b = beta ? beta[tid] : 0.f;
@@ -322,7 +399,7 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     s_scale[tid] = g * invstd;
     s_shift[tid] = b - mean * g * invstd;
   }
-  __syncthreads();
+  cta_sync<NAMED>();
 
   float yv[16], dz[16];
   {
@@ -368,7 +445,7 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     warp_transpose_reduce32(v, lane);
     red[warp * 32 + lane] = v[0];
   }
-  __syncthreads();
+  cta_sync<NAMED>();
   if (tid < 32) {
     float s = 0.f;
 #pragma unroll 5
@@ -376,15 +453,21 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     partials[static_cast<size_t>(n) * 32 + tid] = s;
   }
   trace(1, 1);
-  bar.sync(gs);
+  bar.sync<NAMED>(gs);
   trace(1, 2);
-  fold_rows<32>(partials, B, s_tmp, s_tot);  // [0..16) Σdz, [16..32) Σdz·x̂
+  fold_rows<32, NAMED>(partials, B, s_tmp, s_tot);  // [0..16) Σdz, [16..32) Σdz·x̂
   trace(1, 3);
   if (n == 0 && tid < 16) {
     if (dbeta) dbeta[tid] = s_tot[tid];
     if (dgamma) dgamma[tid] = s_tot[16 + tid];
   }
   const float inv_cnt = 1.f / (static_cast<float>(B) * 784.f);
+  if constexpr (WG) {
+    // dys | fold double as A stages of the tensor-core pipeline: every MMA that reads them must have completed
+    // (tcgen05.commit → acc_full).  Barrier 0 (1): the role warps arrived on it right after initialising the mbarriers.
+    asm volatile("bar.sync 0, %0;" ::"n"(L1WgCfg::kThreads) : "memory");
+    mbar_wait(acc_full, 0);
+  }
   if (m.valid) {
     float4* dst = reinterpret_cast<float4*>(dys + (m.r * 28 + m.c) * 16);
 #pragma unroll
@@ -398,7 +481,7 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
       dst[q] = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
-  __syncthreads();
+  cta_sync<NAMED>();
   // conv1 weight gradient of this image on the tensor cores: dW[co][tap] = Σ_px dy[px][co] · x[px + tap] is a
   // 16 × 32 × 784 GEMM (taps 25..31 padded; tap 25 multiplies a column of ones → the bias gradient).  M = 16 is below
   // tcgen05's minimum tile, so this is warp-level mma.sync m16n8k8 (TF32 in, fp32 accumulate): a warp takes every
@@ -447,10 +530,10 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     const int co = tid & 15, part = tid >> 4;
     for (int p = part; p < 784; p += 32) dbp += dys[p * 16 + co];
   }
-  __syncthreads();
+  cta_sync<NAMED>();
   float* s_db = red;   // [32 parts][16]  (the statistics scratch is free again)
   if (tid < 512) s_db[tid] = dbp;
-  __syncthreads();
+  cta_sync<NAMED>();
   if (tid < 512) {
     float sacc = 0.f;
     if ((tid & 31) == 25) {
@@ -464,7 +547,30 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     partials_w[static_cast<size_t>(n) * 512 + tid] = sacc;   // index = co·32 + tap  (tap 25 = bias, 26..31 unused)
   }
   trace(1, 4);
-  bar.sync(gs);
+  if constexpr (WG) {
+    // the tensor-core pipeline has been running since the kernel started; pick up its four 128 × 32 accumulators
+    // (16 warps: TMEM lane quarter = warp % 4, accumulator = warp / 4) and write this image's partial [512][32]
+    if (warp < 16) {
+      tc_fence_after();
+      const uint32_t tmem_base = *tmem_slot;
+      const int mt = warp >> 2, lq = warp & 3;
+      float v[32];
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        float t[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + mt * 32 + c0, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c0 + j] = t[j];
+      }
+      float* o = wpart + (static_cast<size_t>(n) * 512 + mt * 128 + lq * 32 + lane) * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      tc_fence_before();
+    }
+    asm volatile("bar.arrive 3, %0;" ::"n"(L1WgCfg::kThreads) : "memory");   // (2) TMEM may be released
+    trace(1, 7);
+  }
+  bar.sync<NAMED>(gs);
   trace(1, 5);
   // every CTA folds a few of the 16 × 26 outputs over the B partial rows: one warp per output, fixed order
   for (int j = n + warp * B; j < 512; j += kL1Warps * B) {
@@ -477,6 +583,59 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     if (lane == 0) {
       if (tap < 25) dw[co * 25 + tap] = s;
       else if (db) db[co] = s;
+    }
+  }
+  if constexpr (WG) {
+    // conv2 weight gradient: CTA n folds outputs n, n + B, … of the 400 (tap, ci) rows × 32 co (+ row 400: the bias, from the
+    // per-image Σdy rows) over the B per-image partials — warp = one of 25 partial classes, lane = co, classes combined
+    // through smem in a fixed order, up to five outputs per round so that ~20 L2 loads per thread are in flight
+    float* s_f = fold;   // [5][25][32]
+    constexpr size_t kStride = 512 * 32;
+    for (int base = n; base < 401; base += 5 * B) {
+      float acc[5];
+      const float* src[5];
+      size_t stride[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int i = base + u * B;
+        if (i < 400) {
+          const int tap = i >> 4, ci = i & 15, kh = tap / 5, kw = tap - kh * 5;
+          src[u] = wpart + static_cast<size_t>((3 * kh + (kw >> 1)) * 32 + (kw & 1) * 16 + ci) * 32 + lane;
+          stride[u] = kStride;
+        } else {
+          src[u] = i == 400 ? dysum2 + lane : nullptr;   // row 400: the bias gradient from the per-image Σdy rows
+          stride[u] = 32;
+        }
+        acc[u] = 0.f;
+      }
+      for (int c0 = warp; c0 < B; c0 += 4 * kL1Warps) {   // 5 outputs × 4 rows = 20 independent L2 loads in flight per thread
+        float t[5][4];
+#pragma unroll
+        for (int u = 0; u < 5; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j * kL1Warps;
+            t[u][j] = (src[u] != nullptr && c < B) ? __ldcg(src[u] + static_cast<size_t>(c) * stride[u]) : 0.f;
+          }
+#pragma unroll
+        for (int u = 0; u < 5; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[u] += t[u][j];
+      }
+      cta_sync<NAMED>();
+#pragma unroll
+      for (int u = 0; u < 5; ++u) s_f[(u * kL1Warps + warp) * 32 + lane] = acc[u];
+      cta_sync<NAMED>();
+      if (tid < 160) {
+        const int u = tid >> 5, i = base + u * B;
+        if (i <= 400) {
+          float tot = 0.f;
+#pragma unroll 5
+          for (int wi = 0; wi < kL1Warps; ++wi) tot += s_f[(u * kL1Warps + wi) * 32 + lane];
+          if (i < 400) dw2[(lane * 16 + (i & 15)) * 25 + (i >> 4)] = tot;
+          else if (db2) db2[lane] = tot;
+        }
+      }
     }
   }
   bar.finish(gs);
@@ -1323,8 +1482,19 @@ void launch_convnet_l1_fwd(const float* x, const float* w, const float* bias, co
 void launch_convnet_l1_bwd(const float* dp, const float* y, const float* x, const float* saved, const float* gamma, const float* beta,
                            float* dgamma, float* dbeta, float* dw, float* db, int B, float* partials, float* partials_w, GridSync gs,
                            cudaStream_t st) {
-  launch_coop(convnet_l1_bwd_kernel, B, kL1Threads, static_cast<size_t>(kL1BwdSmem), st, "convnet_l1_bwd", dp, y, x, saved, gamma, beta, dgamma, dbeta,
-              dw, db, partials, partials_w, gs);
+  CUtensorMap none{};
+  launch_coop(convnet_l1_bwd_kernel<false>, B, kL1Threads, static_cast<size_t>(kL1BwdSmem), st, "convnet_l1_bwd", dp, y, x, saved, gamma, beta, dgamma,
+              dbeta, dw, db, partials, partials_w, gs, none, none, static_cast<float*>(nullptr), static_cast<const float*>(nullptr),
+              static_cast<float*>(nullptr), static_cast<float*>(nullptr));
+}
+
+void launch_convnet_l1_bwd_wgrad(const float* dp, const float* y, const float* x, const float* saved, const float* gamma, const float* beta,
+                                 float* dgamma, float* dbeta, float* dw, float* db, const float* dy2_pad, const float* x2_pad, const float* dysum2,
+                                 float* dw2, float* db2, int B, float* partials, float* partials_w, float* wpart, GridSync gs, cudaStream_t st) {
+  CUtensorMap tm_x, tm_dy;
+  make_wgrad_win_tmaps(x2_pad, dy2_pad, B, &tm_x, &tm_dy);
+  launch_coop(convnet_l1_bwd_kernel<true>, B, L1WgCfg::kThreads, L1WgCfg::kSmem, st, "convnet_l1_bwd_wgrad", dp, y, x, saved, gamma, beta, dgamma,
+              dbeta, dw, db, partials, partials_w, gs, tm_x, tm_dy, wpart, dysum2, dw2, db2);
 }
 
 void launch_convnet_l2_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float* y, float* out,

@@ -2,16 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "grid_sync.cuh"
 #include "ops_kernels.h"
 
 namespace pdt {
-
-// Device memory of the grid barrier shared by every cooperative kernel of a device (zero before first use):
-// a monotonically increasing epoch word and an arrival counter (see GridBar in fused_convnet.cu).
-struct GridSync {
-  unsigned int* epoch;
-  unsigned int* flags;   // [0] = arrival counter
-};
 
 // One CTA per image, all co-resident: the batch must not exceed the number of SMs.
 bool fused_convnet_supported(int B);
@@ -30,6 +24,12 @@ void launch_convnet_l1_fwd(const float* x, const float* w, const float* bias, co
 void launch_convnet_l1_bwd(const float* dp, const float* y, const float* x, const float* saved, const float* gamma, const float* beta,
                            float* dgamma, float* dbeta, float* dw, float* db, int B, float* partials, float* partials_w, GridSync gs,
                            cudaStream_t st);
+// Layer-1 backward with the conv2 weight gradient of the same image running on the tensor cores next to it (two extra warps):
+// dy2_pad [B,18,18,32] / x2_pad [B,18,18,16] frames and dysum2 [B,32] from layer-2 backward → dw2 [32,16,5,5], db2 [32].
+// wpart: B·512·32 floats of scratch, disjoint from partials / partials_w.
+void launch_convnet_l1_bwd_wgrad(const float* dp, const float* y, const float* x, const float* saved, const float* gamma, const float* beta,
+                                 float* dgamma, float* dbeta, float* dw, float* db, const float* dy2_pad, const float* x2_pad, const float* dysum2,
+                                 float* dw2, float* db2, int B, float* partials, float* partials_w, float* wpart, GridSync gs, cudaStream_t st);
 // x [B,18,18,16] frame → y [B,14,14,32], out [B,32,7,7] NCHW, saved [64]; logits [B,ncls] = fc(out) when logits != nullptr.
 // partials: B·64 floats.
 void launch_convnet_l2_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float* y, float* out,

@@ -150,5 +150,17 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
 }
 
 
+// MN-major operand, SWIZZLE_128B with 32-byte atoms (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  LBO = byte stride between
+// 32-element MN atoms, SBO = byte stride between 4-row K atoms (512 B when the 8 rows of one MMA are contiguous).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;
+  return d;
+}
+
 }  // namespace ptx
 }  // namespace pdt

@@ -134,50 +134,71 @@ def fused_convnet_ok(x: torch.Tensor, model) -> bool:
     return all(p.is_contiguous() for p in (c1.weight, c2.weight, fc.weight))
 
 
+def _wgrad_rides_on_layer1() -> bool:
+    """conv2's weight gradient runs on the tensor cores *inside* the layer-1 backward kernel (two extra warps per CTA)
+    instead of as a kernel of its own between the two layer kernels.  PDT_WGRAD_MERGED=0 restores the separate launch."""
+    return (os.environ.get("PDT_WGRAD_MERGED", "1") != "0" and os.environ.get("PDT_WGRAD_WIN", "1") != "0"
+            and hasattr(_C, "convnet_l1_bwd_wgrad"))
+
+
 class _FusedLayer1(torch.autograd.Function):
-    """conv1 + BN1 + ReLU + pool1 forward, and its whole backward, as one cooperative kernel each."""
+    """conv1 + BN1 + ReLU + pool1 forward, and its whole backward, as one cooperative kernel each.
+
+    ``w2`` / ``b2`` (conv2's parameters) are inputs of this node on purpose: when conv2's weight gradient rides on the
+    layer-1 backward kernel, *this* node returns it, so autograd (and DDP's reducer hooks behind it) sees the gradient
+    only after the kernel that produces it has been launched."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, whole=None):
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, w2=None, b2=None, whole=None, link=None):
         if whole is not None:
             # ONE launch for the whole forward pass (csrc/cuda/fused_convnet.cu: convnet_fwd_kernel): layer 2 and the
             # classifier of an image run in the same CTA; their results are handed to the next autograd nodes through `whole`
-            c2, b2, fc = whole["conv2"], whole["bn2"], whole["fc"]
+            c2, bn2, fc = whole["conv2"], whole["bn2"], whole["fc"]
             out, y, saved, p2, y2, saved2, logits = _C.convnet_fwd(
-                x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, c2.weight, c2.bias, b2.weight, b2.bias,
-                b2.running_mean, b2.running_var, b2.num_batches_tracked, float(b2.momentum), float(b2.eps), fc.weight, fc.bias)
+                x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, c2.weight, c2.bias, bn2.weight, bn2.bias,
+                bn2.running_mean, bn2.running_var, bn2.num_batches_tracked, float(bn2.momentum), float(bn2.eps), fc.weight, fc.bias)
             whole["layer2"] = (p2, y2, saved2, logits)
         else:
             out, y, saved = _C.convnet_l1_fwd(x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps)
         ctx.save_for_backward(x, y, saved, gamma, beta)
-        ctx.params = (w, b, gamma, beta)
+        ctx.params = (w, b, gamma, beta, w2, b2)
+        ctx.link = link
         return out  # [B,18,18,16]: zero-haloed NHWC frame
 
     @staticmethod
     def backward(ctx, dp):
         x, y, saved, gamma, beta = ctx.saved_tensors
-        w_p, b_p, g_p, be_p = ctx.params
+        w_p, b_p, g_p, be_p, w2_p, b2_p = ctx.params
         dw = _grad_dst(w_p, w_p)
         db = _grad_dst(b_p, b_p) if b_p is not None else None
         dg = _grad_dst(g_p, gamma)
         dbe = _grad_dst(be_p, beta)
-        _C.convnet_l1_bwd(dp.contiguous(), y, x, saved, gamma, beta, dg, dbe, dw, db)
-        return None, dw, db, dg, dbe, None, None, None, None, None, None
+        pending = ctx.link.pop("wgrad", None) if ctx.link is not None else None
+        dw2 = db2 = None
+        if pending is not None:
+            dy2, p1, dysum2 = pending
+            dw2 = _grad_dst(w2_p, w2_p)
+            db2 = _grad_dst(b2_p, b2_p) if b2_p is not None else None
+            _C.convnet_l1_bwd_wgrad(dp.contiguous(), y, x, saved, gamma, beta, dg, dbe, dw, db, dy2, p1, dysum2, dw2, db2)
+        else:
+            _C.convnet_l1_bwd(dp.contiguous(), y, x, saved, gamma, beta, dg, dbe, dw, db)
+        return None, dw, db, dg, dbe, None, None, None, None, None, dw2, db2, None, None
 
 
 class _FusedLayer2(torch.autograd.Function):
     """conv2 (tcgen05) + BN2 + ReLU + pool2 (+ the classifier's logits, which ride on the pooled activations while they
-    are still in shared memory) forward; pool/ReLU/BN backward + conv2 data gradient as one kernel backward, then the
-    tensor-core weight gradient."""
+    are still in shared memory) forward; pool/ReLU/BN backward + conv2 data gradient as one kernel backward.  The
+    tensor-core weight gradient follows as its own kernel, or — the default — rides on layer 1's backward kernel."""
 
     @staticmethod
-    def forward(ctx, p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb, whole=None):
+    def forward(ctx, p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb, whole=None, link=None):
         if whole is not None and "layer2" in whole:
             out, y, saved, logits = whole.pop("layer2")   # produced by the whole-forward launch of layer 1's node
         else:
             out, y, saved, logits = _C.convnet_l2_fwd(p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb)
         ctx.save_for_backward(p1, y, saved, gamma, beta, w)
         ctx.params = (w, b, gamma, beta)
+        ctx.link = link
         ctx.mark_non_differentiable(logits)
         return out, logits  # [B,32,7,7] NCHW, [B,classes]
 
@@ -188,6 +209,10 @@ class _FusedLayer2(torch.autograd.Function):
         dg = _grad_dst(g_p, gamma)
         dbe = _grad_dst(be_p, beta)
         dy, dp1, dysum = _C.convnet_l2_bwd(dout.contiguous(), y, saved, gamma, beta, w, dg, dbe)
+        if ctx.link is not None and ctx.needs_input_grad[0]:
+            # layer 1's backward kernel computes (and layer 1's node returns) conv2's weight / bias gradient
+            ctx.link["wgrad"] = (dy, p1, dysum)
+            return dp1, None, None, dg, dbe, None, None, None, None, None, None, None, None, None
         dw = _grad_dst(w_p, w)
         db = _grad_dst(b_p, b_p) if b_p is not None else None
         if os.environ.get("PDT_WGRAD_WIN", "1") != "0":
@@ -195,7 +220,7 @@ class _FusedLayer2(torch.autograd.Function):
             _C.conv5x5_wgrad_win(dy, p1, dysum, dw, db)
         else:  # im2col-gather kernel on the frames' interiors
             _C.conv5x5_wgrad(dy[:, 2:16, 2:16, :].contiguous(), p1[:, 2:16, 2:16, :].contiguous(), dw, db, "auto")
-        return dp1, dw, db, dg, dbe, None, None, None, None, None, None, None, None
+        return dp1, dw, db, dg, dbe, None, None, None, None, None, None, None, None, None
 
 
 class _FusedClassifier(torch.autograd.Function):
@@ -219,14 +244,18 @@ class _FusedClassifier(torch.autograd.Function):
 
 def fused_convnet_forward(x: torch.Tensor, model) -> torch.Tensor:
     """The reference ConvNet's training forward as ONE kernel (two with PDT_FUSED_WHOLE_FWD=0) (ref: ddp_example.py:36-41)."""
-    c1, b1, c2, b2, fc = model.layer1[0], model.layer1[1], model.layer2[0], model.layer2[1], model.fc
+    c1, b1, c2, b2_bn, fc = model.layer1[0], model.layer1[1], model.layer2[0], model.layer2[1], model.fc
     whole = None
     if os.environ.get("PDT_FUSED_WHOLE_FWD", "1") != "0" and fc.weight.shape[0] <= 16 and hasattr(_C, "convnet_fwd"):
-        whole = {"conv2": c2, "bn2": b2, "fc": fc}
+        whole = {"conv2": c2, "bn2": b2_bn, "fc": fc}
+    # conv2's weight gradient is produced by layer 1's backward kernel: layer 1's node owns (w2, b2) for autograd, `link` carries
+    # the operands from layer 2's backward to it.  Only when conv1's parameters need gradients (layer 1's backward runs at all).
+    link = {} if (_wgrad_rides_on_layer1() and c1.weight.requires_grad and c2.weight.requires_grad) else None
+    w2, b2 = (c2.weight, c2.bias) if link is not None else (None, None)
     p1 = _FusedLayer1.apply(x, c1.weight, c1.bias, b1.weight, b1.bias, b1.running_mean, b1.running_var, b1.num_batches_tracked,
-                            float(b1.momentum), float(b1.eps), whole)
-    p2, logits = _FusedLayer2.apply(p1, c2.weight, c2.bias, b2.weight, b2.bias, b2.running_mean, b2.running_var, b2.num_batches_tracked,
-                                    float(b2.momentum), float(b2.eps), fc.weight, fc.bias, whole)
+                            float(b1.momentum), float(b1.eps), w2, b2, whole, link)
+    p2, logits = _FusedLayer2.apply(p1, c2.weight, c2.bias, b2_bn.weight, b2_bn.bias, b2_bn.running_mean, b2_bn.running_var,
+                                    b2_bn.num_batches_tracked, float(b2_bn.momentum), float(b2_bn.eps), fc.weight, fc.bias, whole, link)
     return _FusedClassifier.apply(p2, fc.weight, fc.bias, logits)
 
 

@@ -19,7 +19,7 @@ def test_idx_roundtrip_and_mnist(tmp_path):
     t = (torch.arange(2 * 28 * 28) % 251).to(torch.uint8).view(2, 28, 28)
     write_idx(str(tmp_path / "x-idx3-ubyte"), t)
     assert torch.equal(read_idx(str(tmp_path / "x-idx3-ubyte")), t)
-    with pytest.raises(RuntimeError, match="never touches the network"):
+    with pytest.raises(RuntimeError, match="no network is reachable"):
         MNIST(str(tmp_path / "none"), download=True)
     synthesize_mnist_files(str(tmp_path), n=300)
     ds = MNIST(str(tmp_path), train=True, download=True)

@@ -226,11 +226,13 @@ def test_convnet_fused_matches_unfused(syncbn_module):
     assert torch.allclose(net(x).double(), ref(x.double()), atol=3e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("merged_wgrad", ["1", "0"])
 @pytest.mark.parametrize("B", [100, 3, 148])
-def test_cooperative_fused_layers_match_per_op_kernels(B, monkeypatch):
+def test_cooperative_fused_layers_match_per_op_kernels(B, merged_wgrad, monkeypatch):
     """csrc/cuda/fused_convnet.cu (one cooperative kernel per layer and direction, grid barrier for the batch
     statistics) against the per-op kernels on the same weights and data: same TF32 convolution, same fp32 rest —
     only summation orders differ."""
+    monkeypatch.setenv("PDT_WGRAD_MERGED", merged_wgrad)   # conv2 weight gradient inside the layer-1 backward kernel / as its own kernel
     torch.manual_seed(2)
     a = pdt.models.ConvNet(fused=True).to(dev())
     b = pdt.models.ConvNet(fused=True).to(dev())
@@ -293,6 +295,27 @@ def test_cooperative_layer2_exact_on_small_integers():
                                          dyq[:, 2:16, 2:16, :].permute(0, 3, 1, 2).double(), padding=2)
     assert torch.equal(dw.double(), ref_dw), (dw.double() - ref_dw).abs().max()
     assert torch.equal(dbias.double(), dyq.double().sum((0, 1, 2)))
+    # the same weight gradient riding on the layer-1 backward kernel (extra TMA + tcgen05 warps): still exact, and the
+    # layer-1 results are those of the plain layer-1 backward kernel, bit for bit
+    x1 = torch.rand(B, 1, 28, 28, device=dev())
+    w1, b1 = torch.randn(16, 1, 5, 5, device=dev()) * 0.2, torch.randn(16, device=dev()) * 0.1
+    g1, be1 = torch.rand(16, device=dev()) + 0.5, torch.randn(16, device=dev()) * 0.1
+    _, y1, sv1 = _C.convnet_l1_fwd(x1, w1, b1, g1, be1, None, None, None, 0.1, 1e-5)
+    dp1 = torch.zeros(B, 18, 18, 16, device=dev())
+    dp1[:, 2:16, 2:16, :] = torch.randn(B, 14, 14, 16, device=dev())
+
+    def l1_outputs():
+        return [torch.full((16,), 7.0, device=dev()), torch.full((16,), 7.0, device=dev()), torch.full((16, 1, 5, 5), 7.0, device=dev()),
+                torch.full((16,), 7.0, device=dev())]
+
+    plain, riding = l1_outputs(), l1_outputs()
+    _C.convnet_l1_bwd(dp1, y1, x1, sv1, g1, be1, *plain)
+    dw_m, db_m = torch.full((32, 16, 5, 5), 7.0, device=dev()), torch.full((32,), 7.0, device=dev())
+    _C.convnet_l1_bwd_wgrad(dp1, y1, x1, sv1, g1, be1, *riding, dyq, p1, dyq[:, 2:16, 2:16, :].sum((1, 2)).contiguous(), dw_m, db_m)
+    assert torch.equal(dw_m.double(), ref_dw), (dw_m.double() - ref_dw).abs().max()
+    assert torch.equal(db_m.double(), dyq.double().sum((0, 1, 2)))
+    for got, want in zip(riding, plain):
+        assert torch.equal(got, want)
 
 
 def test_generic_bn_kernels_match_torch():
@@ -355,5 +378,31 @@ def test_single_gpu_ddp_and_graphed_step():
         l0 = step(x, t).item()
         l1 = step(x, t).item()
         assert l1 < l0 < eager[2] + 1e-3
+    finally:
+        pdt.destroy_process_group()
+
+
+def test_parameter_used_twice_sums_both_gradients():
+    """a weight used twice in one forward must get dW1 + dW2, not two aliases of one bucket slot."""
+    torch.cuda.set_device(0)
+    _one_rank_group()
+    try:
+        class Tied(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.fc = torch.nn.Linear(64, 64)
+
+            def forward(self, x):
+                return ops.linear(torch.relu(ops.linear(x, self.fc.weight, self.fc.bias)), self.fc.weight, self.fc.bias)
+
+        torch.manual_seed(0)
+        model = Tied().to(dev())
+        ddp = pdt.DistributedDataParallel(model, device_ids=[0])
+        x = torch.randn(32, 64, device=dev())
+        ddp(x).square().mean().backward()
+        w, b = model.fc.weight.detach().clone().requires_grad_(), model.fc.bias.detach().clone().requires_grad_()
+        F.linear(torch.relu(F.linear(x, w, b)), w, b).square().mean().backward()
+        assert torch.allclose(model.fc.weight.grad, w.grad, atol=1e-5, rtol=1e-4)
+        assert torch.allclose(model.fc.bias.grad, b.grad, atol=1e-5, rtol=1e-4)
     finally:
         pdt.destroy_process_group()

@@ -29,13 +29,19 @@ crit(net(x), y).backward()
 t = _C.fused_convnet_trace_read()[:, :B, :].double()
 _C.fused_convnet_trace_enable(False)
 names = {0: ("l1_fwd", ["start", "conv done", "partial written", "barrier passed", "folded", "end"]),
-         1: ("l1_bwd", ["start", "partial written", "barrier passed", "folded", "wgrad partial written", "barrier 2 passed", "end"]),
+         1: ("l1_bwd (+conv2 wgrad)", ["start", "partial written", "barrier passed", "folded", "conv1 wgrad partial written", "barrier 2 passed", "end",
+                                       "conv2 wgrad read out of TMEM"]),
          2: ("l2_fwd", ["start", "B built + sync", "epilogue done", "partial written", "barrier passed", "folded", "pooled out written", "end"]),
          3: ("l2_bwd", ["start", "B built", "partial written", "barrier passed", "folded", "dy written", "end"])}
 for k, (name, phases) in names.items():
     tk = t[k]
+    if tk[:, 0].max() == 0:
+        continue   # kernel did not run in this configuration
     t0 = tk[:, 0].min()
-    print(f"== {name}: kernel span {(tk[:, len(phases) - 1].max() - t0) / 1e3:.2f} us (first CTA start -> last CTA end)")
-    for i, ph in enumerate(phases):
+    print(f"== {name}: kernel span {(tk.max() - t0) / 1e3:.2f} us (first CTA start -> last CTA end)")
+    order = sorted(range(len(phases)), key=lambda i: tk[:, i].median().item())
+    for i in order:
+        if tk[:, i].max() == 0:
+            continue
         col = (tk[:, i] - t0) / 1e3
-        print(f"   {ph:24s} min {col.min():7.2f}  median {col.median():7.2f}  max {col.max():7.2f}")
+        print(f"   {phases[i]:30s} min {col.min():7.2f}  median {col.median():7.2f}  max {col.max():7.2f}")

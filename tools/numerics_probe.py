@@ -27,9 +27,16 @@ def worker(rank, world, port):
     torch.backends.cuda.matmul.allow_tf32 = False
     td.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
     comm = dist.get_default_group().comm
-    out = {}
+    class _Out(dict):
+        """results are also printed as they arrive, so a crash further down keeps what was measured"""
+        def __setitem__(self, k, v):
+            super().__setitem__(k, v)
+            if rank == 0:
+                print("[probe]", k, json.dumps(v), flush=True)
+
+    out = _Out()
     # ---- A/B: one SyncBN layer ------------------------------------------------------------------------
-    for shape in [(4, 64, 32, 32)]:
+    for shape in [(4, 64, 32, 32), (4, 512, 2, 2)]:
         for busy in (False, True):
             for kernels in ("15", "31", "0"):
                 os.environ["PDT_SYNCBN_KERNELS"] = kernels
@@ -92,6 +99,8 @@ def worker(rank, world, port):
         worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
         out[f"{name}|syncbn={syncbn}|kernels={kernels}"] = {"loss": (lo, lt), "worst": worst,
                                                              "gnorm": {n: gt[n].abs().max().item() for n, _ in worst}}
+        if name == "resnet" and syncbn and max(errs.values()) > 1e-3:
+            out[f"{name}|syncbn|kernels={kernels}|all"] = {n: round(e, 5) for n, e in errs.items() if "bn" in n or n.startswith("fc")}
     # ---- E: precision of one ConvNet step against a float64 oracle (single GPU, no DDP) ---------------------
     os.environ["PDT_SYNCBN_KERNELS"] = "15"
     if rank == 0:
@@ -116,7 +125,7 @@ def worker(rank, world, port):
         out["precision_vs_fp64|torch cudnn allow_tf32=False"] = arm(False, False)
         torch.backends.cudnn.allow_tf32 = False
     td.destroy_process_group()
-    return out
+    return dict(out)
 
 
 if __name__ == "__main__":
