@@ -333,6 +333,28 @@ void register_cuda_bindings(py::module_& m) {
                           cur_stream(y));
     return py::make_tuple(dy, dx, dysum);
   });
+  m.def("convnet_l2_bwd_fc", [](const at::Tensor& dlogits, const at::Tensor& fcw, const at::Tensor& pooled, at::Tensor dfcw, c10::optional<at::Tensor> dfcb,
+                                const at::Tensor& y, const at::Tensor& saved, c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta,
+                                const at::Tensor& w, at::Tensor dgamma, at::Tensor dbeta) {
+    chk(dlogits, "dlogits"); chk(fcw, "fc weight"); chk(pooled, "pooled"); chk(dfcw, "dfcw");
+    chk(y, "y"); chk(saved, "saved"); chk(w, "w"); chk(dgamma, "dgamma"); chk(dbeta, "dbeta");
+    c10::cuda::CUDAGuard g(y.device());
+    const int B = static_cast<int>(y.size(0));
+    const int ncls = static_cast<int>(fcw.size(0));
+    TORCH_CHECK(fcw.dim() == 2 && fcw.size(1) == 1568 && ncls <= 16 && dlogits.numel() == static_cast<int64_t>(B) * ncls &&
+                    pooled.numel() == static_cast<int64_t>(B) * 1568 && dfcw.numel() == fcw.numel() && y.numel() == static_cast<int64_t>(B) * 6272 &&
+                    w.numel() == 12800 && dgamma.numel() == 32 && dbeta.numel() == 32, "convnet_l2_bwd_fc: shape mismatch");
+    TORCH_CHECK(reinterpret_cast<uintptr_t>(fcw.data_ptr()) % 16 == 0, "convnet_l2_bwd_fc: fc weight must be 16-byte aligned");
+    at::Tensor dy = at::empty({B, 18, 18, 32}, y.options());
+    at::Tensor dx = at::empty({B, 18, 18, 16}, y.options());
+    at::Tensor dysum = at::empty({B, 32}, y.options());
+    ReduceScratch scr = scratch(y);
+    launch_convnet_l2_bwd_fc(dlogits.data_ptr<float>(), fcw.data_ptr<float>(), pooled.data_ptr<float>(), dfcw.data_ptr<float>(), opt_mut(dfcb, "dfcb"),
+                             ncls, y.data_ptr<float>(), saved.data_ptr<float>(), opt_ptr(gamma, "gamma"), opt_ptr(beta, "beta"), w.data_ptr<float>(),
+                             dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dy.data_ptr<float>(), dx.data_ptr<float>(), dysum.data_ptr<float>(), B,
+                             scr.partials, GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(y));
+    return py::make_tuple(dy, dx, dysum);
+  });
   m.def("conv5x5_wgrad_win", [](const at::Tensor& dy_pad, const at::Tensor& x_pad, const at::Tensor& dysum, at::Tensor dw, c10::optional<at::Tensor> db) {
     chk(dy_pad, "dy_pad"); chk(x_pad, "x_pad"); chk(dysum, "dysum"); chk(dw, "dw");
     c10::cuda::CUDAGuard g(dy_pad.device());

@@ -247,24 +247,30 @@ convnet_l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 constexpr int kL1BwdSmem = (784 * 16 + kL1Warps * 512) * 4;
 
 // The conv2 weight gradient of an image needs nothing from layer-1 backward — only the dy / x frames that layer-2 backward
-// left in global memory — and layer-1 backward leaves the tensor cores, TMA and most of shared memory idle.  With WG the
-// CTA carries two extra warps (a TMA producer and a tcgen05 issuer) that run the "window" weight gradient
-// (conv_tcgen05.cu: conv5x5_wgrad_win_kernel has the derivation) of the same image concurrently with the SIMT work of the
-// 25 layer-1 warps; its per-CTA partial [512][32] is read out of TMEM by 16 of the layer-1 warps just before the kernel's
-// second grid barrier, and folded after it next to the conv1 gradient.  One launch and one grid barrier less than running
-// the two kernels back to back, and the tensor-core pipeline hides completely behind the SIMT phases.
+// left in global memory — and layer-1 backward leaves the tensor cores, TMA and half of shared memory idle.  With WG the CTA
+// carries one extra warp that computes dW2ᵀ[(kh, kw, ci)][co] = Σ_P xpad[P + (kh−2)·18 + (kw−2)][ci] · dypad[P][co] of the same
+// image on tcgen05 while the 25 layer-1 warps do their SIMT work:
+//   * B (dy, MN-major): the 256 positions starting at the first interior one, two TMA boxes.
+//   * A (x, MN-major): the "window" trick of the forward pass, applied to an MN-major operand.  Row r of the overlapping-row view
+//     of the frame (pitch 64 B, length 128 B) holds positions r and r+1 = two horizontally adjacent taps × 16 channels, i.e. one
+//     32-wide M atom for K index r.  The whole image is loaded ONCE (384 rows, 48 KB); the atom of tap pair (kh, kw/2) for K
+//     position P is the same buffer read (kh−2)·18 + (kw−2) rows further down — a descriptor start address, not a copy
+//     (SWIZZLE_128B_ATOM_32B follows the absolute smem address, like the K-major case probed in profiles/r2/rowshift_probe.log).
+//     An M = 128 MMA takes four atoms at a uniform stride (the descriptor's LBO): tile kw/2 ∈ {0,1,2} stacks kh = 0..3 (stride
+//     18 rows), tile 3 holds kh = 4 with kw/2 = 0..3 (stride 2 rows; the fourth atom is a dummy).  The stand-alone kernel
+//     (conv_tcgen05.cu) materialises every tap pair by TMA instead: 491 KB of L2 reads per image where this one needs 48 KB.
+//   * four 128 × 32 accumulators in TMEM; 128 MMAs (K = 8 each); the per-CTA partial [512][32] is read out of TMEM by 16 of the
+//     layer-1 warps just before the kernel's second grid barrier and folded after it, next to the conv1 gradient.
+// One launch and one grid barrier less than running the two kernels back to back; the tensor-core work hides behind the SIMT phases.
 struct L1WgCfg {
-  static constexpr int kThreads = kL1Threads + 64;        // + producer warp (25) + MMA warp (26)
+  static constexpr int kThreads = kL1Threads + 32;        // + one warp: TMA loads, then the tcgen05 issue loop
   static constexpr int kFrame = 18 * 18, kFirst = 2 * 18 + 2;
-  static constexpr int kAStageBytes = 4 * 8 * 1024;                // [4 tap pairs][64 positions][128 B]
-  // two dedicated A stages + three that alias the layer-1 staging buffers (dys | fold), which layer 1 does not touch before
-  // its first grid barrier has passed: the layer-1 threads wait for the tensor-core pipeline to drain before they write them
-  static constexpr int kOwnStages = 2, kAliasStages = 3, kStages = kOwnStages + kAliasStages;
-  static_assert(kAliasStages * kAStageBytes <= kL1BwdSmem, "aliased stages must fit into dys | fold");
+  // A window: rows [0, 384) of the image's overlapping-row view (row r = positions r, r+1 × 16 channels = 128 B), six 64-row boxes
+  static constexpr int kABoxes = 6, kABytes = kABoxes * 64 * 128;
   static constexpr int kBBytes = 2 * 128 * 128;                    // both 128-position dy tiles of the image
   static constexpr int kTmemCols = 128;
-  static constexpr int kOff = (kL1BwdSmem + 1023) / 1024 * 1024;   // pipeline starts 1024-aligned behind the layer-1 buffers
-  static constexpr size_t kSmem = 1024 + kOff + kOwnStages * kAStageBytes + kBBytes + 256;
+  static constexpr int kOff = (kL1BwdSmem + 1023) / 1024 * 1024;   // window starts 1024-aligned behind the layer-1 buffers
+  static constexpr size_t kSmem = 1024 + kOff + kABytes + kBBytes + 256;
 };
 
 __device__ __forceinline__ uint32_t f32_to_tf32(float v) {
@@ -294,15 +300,10 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
   float* dsm = reinterpret_cast<float*>(dsm_b);
   float* dys = dsm;                  // [784][16]
   float* fold = dsm + 784 * 16;      // [25 warps][16][32]
-  uint8_t* sa = dsm_b + L1WgCfg::kOff;                              // WG: the two dedicated A stages
-  uint8_t* sb = sa + L1WgCfg::kOwnStages * L1WgCfg::kAStageBytes;   // WG: dy tiles
-  auto a_stage = [&](int s) -> uint8_t* {                           // WG: stage s of the A ring (2.. alias dys | fold)
-    return s < L1WgCfg::kOwnStages ? sa + s * L1WgCfg::kAStageBytes : dsm_b + (s - L1WgCfg::kOwnStages) * L1WgCfg::kAStageBytes;
-  };
-  uint64_t* afull = reinterpret_cast<uint64_t*>(sb + L1WgCfg::kBBytes);
-  uint64_t* aempty = afull + L1WgCfg::kStages;
-  uint64_t* bfull = aempty + L1WgCfg::kStages;
-  uint64_t* acc_full = bfull + 1;
+  uint8_t* sa = dsm_b + L1WgCfg::kOff;                              // WG: A window
+  uint8_t* sb = sa + L1WgCfg::kABytes;                              // WG: dy tiles
+  uint64_t* ld_full = reinterpret_cast<uint64_t*>(sb + L1WgCfg::kBBytes);
+  uint64_t* acc_full = ld_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   __shared__ float xs[32 * 32];
   __shared__ float red[kL1Warps * 32];
@@ -312,76 +313,56 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
 
   if constexpr (WG) {
-    if (warp >= kL1Warps) {
-      // ================= tensor-core weight gradient of image n: producer (warp 25) and issuer (warp 26) =================
+    if (warp == kL1Warps) {
+      // ================= tensor-core weight gradient of image n: one warp loads by TMA, then issues the MMAs =================
       using Cfg = L1WgCfg;
-      if (warp == kL1Warps) {
-        if (lane == 0) {
-          tma_prefetch_desc(&tm_x2);
-          tma_prefetch_desc(&tm_dy2);
-          for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
-          mbar_init(bfull, 1);
-          mbar_init(acc_full, 1);
-          fence_mbar_init();
-        }
-      } else {
-        tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-        tc_fence_before();
+      if (lane == 0) {
+        tma_prefetch_desc(&tm_x2);
+        tma_prefetch_desc(&tm_dy2);
+        mbar_init(ld_full, 1);
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
       }
-      asm volatile("bar.sync 2, 64;" ::: "memory");   // barriers initialised, TMEM allocated: both role warps may start
-      asm volatile("bar.arrive 0, %0;" ::"n"(L1WgCfg::kThreads) : "memory");   // (1) ... and the layer-1 warps may use them (they sync on 0 later)
-      if (warp == kL1Warps) {
-        if (elect_one()) {
-          const int row0 = n * Cfg::kFrame + Cfg::kFirst;   // first interior position of the image's frames
-          mbar_arrive_expect_tx(bfull, Cfg::kBBytes);
-          tma_load_2d(sb, &tm_dy2, bfull, 0, row0);
-          tma_load_2d(sb + 128 * 128, &tm_dy2, bfull, 0, row0 + 128);
-          int g = 0;
-          for (int t = 0; t < 2; ++t)
-            for (int mt = 0; mt < 4; ++mt) {
-              const int npairs = mt == 3 ? 3 : 4;           // tap pair 15 does not exist
-              for (int half = 0; half < 2; ++half, ++g) {
-                const int s = g % Cfg::kStages;
-                mbar_wait(&aempty[s], ((g / Cfg::kStages) & 1) ^ 1);
-                mbar_arrive_expect_tx(&afull[s], npairs * 8192);
-                for (int a = 0; a < npairs; ++a) {
-                  const int q = mt * 4 + a, kh = q / 3, kw = 2 * (q - kh * 3);
-                  // x position of dy position P for tap (kh, kw): P + (kh-2)·18 + (kw-2); rows outside the tensor are zero-filled
-                  tma_load_2d(a_stage(s) + a * 8192, &tm_x2, &afull[s], 0, row0 + 128 * t + 64 * half + (kh - 2) * 18 + (kw - 2));
-                }
-              }
-            }
-        }
-      } else {
-        tc_fence_after();
-        const uint32_t tmem_base = *tmem_slot;
+      __syncwarp();
+      tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+      tc_fence_before();
+      asm volatile("bar.arrive 0, %0;" ::"n"(L1WgCfg::kThreads) : "memory");   // (1) the layer-1 warps sync on barrier 0 before they touch these
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t tmem_base = *tmem_slot;
+      const int frame0 = n * Cfg::kFrame;
+      // the weight gradient has ~10 µs of slack: let the layer-1 warps have the L2 → SM path for their opening loads first
+      asm volatile("bar.sync 4, %0;" ::"n"(L1WgCfg::kThreads) : "memory");
+      if (elect_one()) {
+        mbar_arrive_expect_tx(ld_full, Cfg::kABytes + Cfg::kBBytes);
+        for (int bx = 0; bx < Cfg::kABoxes; ++bx) tma_load_2d(sa + bx * 8192, &tm_x2, ld_full, 0, frame0 + 64 * bx);   // rows past the tensor are zero-filled
+        tma_load_2d(sb, &tm_dy2, ld_full, 0, frame0 + Cfg::kFirst);
+        tma_load_2d(sb + 128 * 128, &tm_dy2, ld_full, 0, frame0 + Cfg::kFirst + 128);
+      }
+      __syncwarp();
+      mbar_wait(ld_full, 0);
+      tc_fence_after();
+      if (elect_one()) {
         constexpr uint32_t idesc = umma_idesc_tf32(128, 32) | (1u << 15) | (1u << 16);  // A and B are MN-major
-        mbar_wait(bfull, 0);
-        int g = 0;
-        for (int t = 0; t < 2; ++t)
-          for (int mt = 0; mt < 4; ++mt)
-            for (int h = 0; h < 2; ++h, ++g) {
-              const int s = g % Cfg::kStages;
-              mbar_wait(&afull[s], (g / Cfg::kStages) & 1);
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t a0 = smem_u32(a_stage(s)), b0 = smem_u32(sb) + t * 16 * 1024 + h * 8 * 1024;
-#pragma unroll
-                for (int kb = 0; kb < 8; ++kb)
-                  umma_tf32(tmem_base + mt * 32, umma_desc_mn_sw128_32b(a0 + kb * 1024, 8 * 1024, 512),
-                            umma_desc_mn_sw128_32b(b0 + kb * 1024, 1024, 512), idesc, (t | h | kb) != 0);
-                umma_commit(&aempty[s]);
-              }
-              __syncwarp();
-            }
-        if (elect_one()) umma_commit(acc_full);
-        __syncwarp();
+        const uint32_t a_base = smem_u32(sa), b_base = smem_u32(sb);
+#pragma unroll 1
+        for (int mt = 0; mt < 4; ++mt) {
+          // first atom's row shift and the stride between the tile's four atoms
+          const int shift0 = mt < 3 ? (0 - 2) * 18 + 2 * mt - 2 : 2 * 18 - 2;
+          const uint32_t lbo = mt < 3 ? 18 * 128 : 2 * 128;
+#pragma unroll 1
+          for (int kc = 0; kc < 32; ++kc) {   // K = 256 positions in steps of 8
+            const uint32_t a0 = a_base + static_cast<uint32_t>(Cfg::kFirst + 8 * kc + shift0) * 128;
+            umma_tf32(tmem_base + mt * 32, umma_desc_mn_sw128_32b(a0, lbo, 512), umma_desc_mn_sw128_32b(b_base + kc * 1024, 1024, 512), idesc,
+                      kc != 0);
+          }
+        }
+        umma_commit(acc_full);
       }
+      __syncwarp();
       asm volatile("bar.sync 3, %0;" ::"n"(L1WgCfg::kThreads) : "memory");   // (2) the layer-1 warps have read the accumulators
-      if (warp == kL1Warps + 1) {
-        tc_fence_after();
-        tmem_dealloc<Cfg::kTmemCols>(*tmem_slot);
-      }
+      tc_fence_after();
+      tmem_dealloc<Cfg::kTmemCols>(tmem_base);
       return;
     }
   }
@@ -424,6 +405,7 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     zmax[j] = t;
     mine |= (z == t ? 1u : 0u) << j;
   }
+  if constexpr (WG) asm volatile("bar.arrive 4, %0;" ::"n"(L1WgCfg::kThreads) : "memory");   // y / dp have arrived: the tensor-core warp may load
   unsigned int lower = 0;  // positions of the window that come before this one
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -462,12 +444,6 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     if (dgamma) dgamma[tid] = s_tot[16 + tid];
   }
   const float inv_cnt = 1.f / (static_cast<float>(B) * 784.f);
-  if constexpr (WG) {
-    // dys | fold double as A stages of the tensor-core pipeline: every MMA that reads them must have completed
-    // (tcgen05.commit → acc_full).  Barrier 0 (1): the role warps arrived on it right after initialising the mbarriers.
-    asm volatile("bar.sync 0, %0;" ::"n"(L1WgCfg::kThreads) : "memory");
-    mbar_wait(acc_full, 0);
-  }
   if (m.valid) {
     float4* dst = reinterpret_cast<float4*>(dys + (m.r * 28 + m.c) * 16);
 #pragma unroll
@@ -550,7 +526,10 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
   if constexpr (WG) {
     // the tensor-core pipeline has been running since the kernel started; pick up its four 128 × 32 accumulators
     // (16 warps: TMEM lane quarter = warp % 4, accumulator = warp / 4) and write this image's partial [512][32]
+    asm volatile("bar.sync 0, %0;" ::"n"(L1WgCfg::kThreads) : "memory");   // (1) mbarriers initialised, TMEM slot written (long ago)
     if (warp < 16) {
+      mbar_wait(acc_full, 0);
+      __syncwarp();
       tc_fence_after();
       const uint32_t tmem_base = *tmem_slot;
       const int mt = warp >> 2, lq = warp & 3;
@@ -600,7 +579,9 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
         const int i = base + u * B;
         if (i < 400) {
           const int tap = i >> 4, ci = i & 15, kh = tap / 5, kw = tap - kh * 5;
-          src[u] = wpart + static_cast<size_t>((3 * kh + (kw >> 1)) * 32 + (kw & 1) * 16 + ci) * 32 + lane;
+          // accumulator row of (kh, kw, ci): tiles 0-2 = kw/2 with kh 0..3 stacked, tile 3 = kh 4 with kw/2 stacked
+          const int mrow = (kh < 4 ? (kw >> 1) * 128 + kh * 32 : 384 + (kw >> 1) * 32) + (kw & 1) * 16 + ci;
+          src[u] = wpart + static_cast<size_t>(mrow) * 32 + lane;
           stride[u] = kStride;
         } else {
           src[u] = i == 400 ? dysum2 + lane : nullptr;   // row 400: the bias gradient from the per-image Σdy rows
@@ -1200,14 +1181,26 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
 struct L2BwdSmem {
   static constexpr int kB = 25 * 16 * 128;       // dgrad weights: [tap][16 ci][128 B = 32 co]                  51,200
   static constexpr int kTotal = 1024 + kPatchAlloc + kB + 4096;
+  // FC (the classifier's backward rides along): fc weights [16][1568] | dlogits [B ≤ 160][16] | pooled slice [B ≤ 160][16]
+  static constexpr int kFcW = 16 * 1568 * 4, kFcDl = 160 * 16 * 4, kFcP = 160 * 16 * 4;
+  static constexpr int kTotalFc = kTotal + kFcW + kFcDl + kFcP;
 };
 
+// FC: the classifier's backward rides along.  The gradient of the pooled activations is not read from `dout` but computed
+// on the fly, d(out)[n][k] = Σ_j dlogits[n][j] · Wfc[j][k] (fc weights staged in smem once per CTA); the classifier's weight
+// gradient dWfc[j][k] = Σ_n dlogits[n][j] · out[n][k] is produced in 16-column slices, one slice per CTA (all images, fixed
+// order: deterministic, no partials), the bias gradient by the CTA that owns "slice 98".  One kernel and ~7 µs less per step.
+template <bool FC>
 __global__ void __launch_bounds__(kL2Threads, 1)
 convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float* __restrict__ y /*[B,14,14,32]*/,
                       const float* __restrict__ saved, const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ w, float* dgamma, float* dbeta, float* __restrict__ dy /*[B,18,18,32] zero-haloed frame*/,
                       float* __restrict__ dx /*[B,18,18,16] frame, interior written*/, float* __restrict__ dysum /*[B,32]*/,
-                      float* partials, GridSync gs) {
+                      float* partials, GridSync gs,
+                      // FC only
+                      const float* __restrict__ dlogits /*[B,ncls]*/, const float* __restrict__ fcw /*[ncls,1568]*/,
+                      const float* __restrict__ pooled /*[B,1568] = forward's out*/, float* dfcw /*[ncls,1568]*/, float* dfcb /*[ncls]*/,
+                      int ncls) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sa = smem;                                  // dy patch, written by the CTA in the TMA/UMMA SWIZZLE_128B layout
@@ -1220,6 +1213,9 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
   float* s_shift = misc + 864;
   float* s_mean = misc + 896;
   float* s_invstd = misc + 928;
+  float* s_fcw = misc + 1024;                                   // FC: [ncls][1568]
+  float* s_dl = s_fcw + L2BwdSmem::kFcW / 4;                    // FC: [B][16] (columns >= ncls zero)
+  float* s_pool = s_dl + L2BwdSmem::kFcDl / 4;                  // FC: [B][16] slice of the pooled activations
   __shared__ uint64_t bar_mma;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
@@ -1231,6 +1227,27 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<32>(&tmem_slot);
+  if constexpr (FC) {
+    // stage the classifier weights (cp.async, no registers, lands while the dgrad weights are built), every image's dlogits and this
+    // CTA's first 16-column slice of the pooled activations (loads batched in registers: one L2 latency, not one per element)
+    for (int i = tid; i < ncls * 392; i += kL2Threads) cp_async_16(smem_u32(s_fcw + 4 * i), fcw + 4 * i, 16);
+    cp_async_commit();
+    float tdl[10], tp[10];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      const int i = tid + q * kL2Threads, r = i >> 4, j = i & 15;
+      tdl[q] = (i < B * 16 && j < ncls) ? __ldg(dlogits + static_cast<size_t>(r) * ncls + j) : 0.f;
+      tp[q] = (i < B * 16 && n < 98) ? __ldg(pooled + static_cast<size_t>(r) * 1568 + n * 16 + j) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      const int i = tid + q * kL2Threads;
+      if (i < B * 16) {
+        s_dl[i] = tdl[q];
+        s_pool[i] = tp[q];
+      }
+    }
+  }
   for (int i = tid; i < kPatchAlloc / 16; i += kL2Threads) reinterpret_cast<float4*>(sa)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // halo = 0
   if (tid < 32) {
     const float mean = saved[tid], invstd = saved[32 + tid];
@@ -1257,6 +1274,7 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
       for (int tap = 0; tap < 25; ++tap) *reinterpret_cast<float*>(dst + (24 - tap) * 2048) = wv[j][tap];
     }
   }
+  if constexpr (FC) cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1284,7 +1302,20 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
         const float z = fmaf(yv[k][d], sc, sh);
         if (z > best) { best = z; arg[k] = d; }
       }
-      const float go = dout[static_cast<size_t>(n) * 1568 + c * 49 + pp];
+      float go;
+      if constexpr (FC) {
+        const float* wk = s_fcw + c * 49 + pp;       // bank = (17·c + pp) mod 32: conflict-free across the warp's 32 channels
+        const float* dl = s_dl + n * 16;
+        float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {            // independent smem loads (classes >= ncls: dlogits column is zero, weight not read)
+          g0 = fmaf(dl[j], j < ncls ? wk[j * 1568] : 0.f, g0);
+          g1 = fmaf(dl[j + 1], j + 1 < ncls ? wk[(j + 1) * 1568] : 0.f, g1);
+        }
+        go = g0 + g1;
+      } else {
+        go = dout[static_cast<size_t>(n) * 1568 + c * 49 + pp];
+      }
       dzv[k] = best > 0.f ? go : 0.f;
       float xh = 0.f;
 #pragma unroll
@@ -1301,6 +1332,44 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
 #pragma unroll
     for (int q = 0; q < 8; ++q) s += s_part[q * 64 + tid];
     partials[static_cast<size_t>(n) * 64 + tid] = s;
+  }
+  if constexpr (FC) {
+    // classifier weight gradient, slice = 16 consecutive columns (98 slices; "slice 98" = the bias): thread = (column, class).
+    // The first slice of this CTA (slice n) was staged at kernel start.
+    const int kl = tid & 15, j = tid >> 4;
+    for (int slice = n; slice < 99; slice += B) {
+      if (slice < 98) {
+        if (slice != n) {
+          __syncthreads();   // s_pool free (previous slice consumed)
+          float tp[10];
+#pragma unroll
+          for (int q = 0; q < 10; ++q) {
+            const int i = tid + q * kL2Threads;
+            tp[q] = i < B * 16 ? __ldg(pooled + static_cast<size_t>(i >> 4) * 1568 + slice * 16 + (i & 15)) : 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < 10; ++q) {
+            const int i = tid + q * kL2Threads;
+            if (i < B * 16) s_pool[i] = tp[q];
+          }
+          __syncthreads();
+        }
+        if (j < ncls) {
+          float a[4] = {0.f, 0.f, 0.f, 0.f};
+          int r = 0;
+          for (; r + 3 < B; r += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = fmaf(s_dl[(r + u) * 16 + j], s_pool[(r + u) * 16 + kl], a[u]);
+          }
+          for (; r < B; ++r) a[0] = fmaf(s_dl[r * 16 + j], s_pool[r * 16 + kl], a[0]);
+          dfcw[static_cast<size_t>(j) * 1568 + slice * 16 + kl] = (a[0] + a[1]) + (a[2] + a[3]);
+        }
+      } else if (dfcb != nullptr && tid < ncls) {
+        float a = 0.f;
+        for (int r = 0; r < B; ++r) a += s_dl[r * 16 + tid];
+        dfcb[tid] = a;
+      }
+    }
   }
   trace(3, 2);
   bar.sync(gs);
@@ -1517,8 +1586,19 @@ void launch_convnet_fwd(const float* x, const float* w1, const float* b1, const 
 void launch_convnet_l2_bwd(const float* dout, const float* y, const float* saved, const float* gamma, const float* beta, const float* w,
                            float* dgamma, float* dbeta, float* dy, float* dx, float* dysum, int B, float* partials, GridSync gs,
                            cudaStream_t st) {
-  launch_coop(convnet_l2_bwd_kernel, B, kL2Threads, static_cast<size_t>(L2BwdSmem::kTotal), st, "convnet_l2_bwd", dout, y, saved, gamma, beta, w, dgamma,
-              dbeta, dy, dx, dysum, partials, gs);
+  launch_coop(convnet_l2_bwd_kernel<false>, B, kL2Threads, static_cast<size_t>(L2BwdSmem::kTotal), st, "convnet_l2_bwd", dout, y, saved, gamma, beta, w,
+              dgamma, dbeta, dy, dx, dysum, partials, gs, static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
+              static_cast<const float*>(nullptr), static_cast<float*>(nullptr), static_cast<float*>(nullptr), 0);
+}
+
+void launch_convnet_l2_bwd_fc(const float* dlogits, const float* fcw, const float* pooled, float* dfcw, float* dfcb, int ncls, const float* y,
+                              const float* saved, const float* gamma, const float* beta, const float* w, float* dgamma, float* dbeta, float* dy,
+                              float* dx, float* dysum, int B, float* partials, GridSync gs, cudaStream_t st) {
+  if (ncls < 1 || ncls > 16) throw std::invalid_argument("convnet_l2_bwd_fc: 1..16 classes");
+  if (B > 160) throw std::invalid_argument("convnet_l2_bwd_fc: batch too large for the staged dlogits");
+  launch_coop(convnet_l2_bwd_kernel<true>, B, kL2Threads, static_cast<size_t>(L2BwdSmem::kTotalFc), st, "convnet_l2_bwd_fc",
+              static_cast<const float*>(nullptr), y, saved, gamma, beta, w, dgamma, dbeta, dy, dx, dysum, partials, gs, dlogits, fcw, pooled, dfcw,
+              dfcb, ncls);
 }
 
 }  // namespace pdt

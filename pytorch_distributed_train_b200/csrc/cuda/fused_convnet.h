@@ -45,5 +45,10 @@ void launch_convnet_fwd(const float* x, const float* w1, const float* b1, const 
 // (data gradient, interior written), dysum [B,32] (per-image Σdy: the conv2 bias gradient is the sum of its rows).
 void launch_convnet_l2_bwd(const float* dout, const float* y, const float* saved, const float* gamma, const float* beta, const float* w,
                            float* dgamma, float* dbeta, float* dy, float* dx, float* dysum, int B, float* partials, GridSync gs, cudaStream_t st);
+// The same with the classifier's backward riding along: d(out) is computed from dlogits [B,ncls] and the fc weights [ncls,1568]
+// inside the kernel; dfcw [ncls,1568] / dfcb [ncls] are produced from `pooled` = the forward's out [B,1568].  ncls ≤ 16.
+void launch_convnet_l2_bwd_fc(const float* dlogits, const float* fcw, const float* pooled, float* dfcw, float* dfcb, int ncls, const float* y,
+                              const float* saved, const float* gamma, const float* beta, const float* w, float* dgamma, float* dbeta, float* dy,
+                              float* dx, float* dysum, int B, float* partials, GridSync gs, cudaStream_t st);
 
 }  // namespace pdt

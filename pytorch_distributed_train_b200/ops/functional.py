@@ -191,28 +191,43 @@ class _FusedLayer2(torch.autograd.Function):
     tensor-core weight gradient follows as its own kernel, or — the default — rides on layer 1's backward kernel."""
 
     @staticmethod
-    def forward(ctx, p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb, whole=None, link=None):
+    def forward(ctx, p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb, whole=None, link=None, fc_rides=False):
         if whole is not None and "layer2" in whole:
             out, y, saved, logits = whole.pop("layer2")   # produced by the whole-forward launch of layer 1's node
         else:
             out, y, saved, logits = _C.convnet_l2_fwd(p1, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, fcw, fcb)
-        ctx.save_for_backward(p1, y, saved, gamma, beta, w)
-        ctx.params = (w, b, gamma, beta)
+        ctx.params = (w, b, gamma, beta, fcw, fcb)
         ctx.link = link
-        ctx.mark_non_differentiable(logits)
+        ctx.fc_rides = fc_rides
+        if fc_rides:
+            # the classifier's backward runs inside this node's backward kernel: the logits are this node's differentiable output
+            ctx.save_for_backward(p1, y, saved, gamma, beta, w, out, fcw)
+            ctx.set_materialize_grads(False)
+        else:
+            ctx.save_for_backward(p1, y, saved, gamma, beta, w)
+            ctx.mark_non_differentiable(logits)
         return out, logits  # [B,32,7,7] NCHW, [B,classes]
 
     @staticmethod
-    def backward(ctx, dout, _dlogits):
-        p1, y, saved, gamma, beta, w = ctx.saved_tensors
-        w_p, b_p, g_p, be_p = ctx.params
-        dg = _grad_dst(g_p, gamma)
-        dbe = _grad_dst(be_p, beta)
-        dy, dp1, dysum = _C.convnet_l2_bwd(dout.contiguous(), y, saved, gamma, beta, w, dg, dbe)
+    def backward(ctx, dout, dlogits):
+        w_p, b_p, g_p, be_p, fcw_p, fcb_p = ctx.params
+        dg = _grad_dst(g_p, ctx.saved_tensors[3])
+        dbe = _grad_dst(be_p, ctx.saved_tensors[4])
+        dfcw = dfcb = None
+        if ctx.fc_rides:
+            p1, y, saved, gamma, beta, w, out, fcw = ctx.saved_tensors
+            if dout is not None:
+                raise RuntimeError("fused ConvNet: the pooled activations of the fused classifier path must not be used outside the model")
+            dfcw = _grad_dst(fcw_p, fcw)
+            dfcb = _grad_dst(fcb_p, fcb_p) if fcb_p is not None else None
+            dy, dp1, dysum = _C.convnet_l2_bwd_fc(dlogits.contiguous(), fcw, out, dfcw, dfcb, y, saved, gamma, beta, w, dg, dbe)
+        else:
+            p1, y, saved, gamma, beta, w = ctx.saved_tensors
+            dy, dp1, dysum = _C.convnet_l2_bwd(dout.contiguous(), y, saved, gamma, beta, w, dg, dbe)
         if ctx.link is not None and ctx.needs_input_grad[0]:
             # layer 1's backward kernel computes (and layer 1's node returns) conv2's weight / bias gradient
             ctx.link["wgrad"] = (dy, p1, dysum)
-            return dp1, None, None, dg, dbe, None, None, None, None, None, None, None, None, None
+            return dp1, None, None, dg, dbe, None, None, None, None, None, dfcw, dfcb, None, None, None
         dw = _grad_dst(w_p, w)
         db = _grad_dst(b_p, b_p) if b_p is not None else None
         if os.environ.get("PDT_WGRAD_WIN", "1") != "0":
@@ -220,7 +235,7 @@ class _FusedLayer2(torch.autograd.Function):
             _C.conv5x5_wgrad_win(dy, p1, dysum, dw, db)
         else:  # im2col-gather kernel on the frames' interiors
             _C.conv5x5_wgrad(dy[:, 2:16, 2:16, :].contiguous(), p1[:, 2:16, 2:16, :].contiguous(), dw, db, "auto")
-        return dp1, dw, db, dg, dbe, None, None, None, None, None, None, None, None, None
+        return dp1, dw, db, dg, dbe, None, None, None, None, None, dfcw, dfcb, None, None, None
 
 
 class _FusedClassifier(torch.autograd.Function):
@@ -254,8 +269,13 @@ def fused_convnet_forward(x: torch.Tensor, model) -> torch.Tensor:
     w2, b2 = (c2.weight, c2.bias) if link is not None else (None, None)
     p1 = _FusedLayer1.apply(x, c1.weight, c1.bias, b1.weight, b1.bias, b1.running_mean, b1.running_var, b1.num_batches_tracked,
                             float(b1.momentum), float(b1.eps), w2, b2, whole, link)
+    # the classifier's backward rides on layer 2's backward kernel (PDT_FC_MERGED=0: separate linear_bwd launch)
+    fc_rides = (os.environ.get("PDT_FC_MERGED", "1") != "0" and hasattr(_C, "convnet_l2_bwd_fc") and fc.weight.shape[0] <= 16
+                and fc.weight.requires_grad and c2.weight.requires_grad and fc.weight.data_ptr() % 16 == 0)
     p2, logits = _FusedLayer2.apply(p1, c2.weight, c2.bias, b2_bn.weight, b2_bn.bias, b2_bn.running_mean, b2_bn.running_var,
-                                    b2_bn.num_batches_tracked, float(b2_bn.momentum), float(b2_bn.eps), fc.weight, fc.bias, whole, link)
+                                    b2_bn.num_batches_tracked, float(b2_bn.momentum), float(b2_bn.eps), fc.weight, fc.bias, whole, link, fc_rides)
+    if fc_rides:
+        return logits
     return _FusedClassifier.apply(p2, fc.weight, fc.bias, logits)
 
 

@@ -226,13 +226,14 @@ def test_convnet_fused_matches_unfused(syncbn_module):
     assert torch.allclose(net(x).double(), ref(x.double()), atol=3e-2, rtol=1e-2)
 
 
-@pytest.mark.parametrize("merged_wgrad", ["1", "0"])
+@pytest.mark.parametrize("riders", ["11", "00", "10", "01"])
 @pytest.mark.parametrize("B", [100, 3, 148])
-def test_cooperative_fused_layers_match_per_op_kernels(B, merged_wgrad, monkeypatch):
+def test_cooperative_fused_layers_match_per_op_kernels(B, riders, monkeypatch):
     """csrc/cuda/fused_convnet.cu (one cooperative kernel per layer and direction, grid barrier for the batch
     statistics) against the per-op kernels on the same weights and data: same TF32 convolution, same fp32 rest —
     only summation orders differ."""
-    monkeypatch.setenv("PDT_WGRAD_MERGED", merged_wgrad)   # conv2 weight gradient inside the layer-1 backward kernel / as its own kernel
+    monkeypatch.setenv("PDT_WGRAD_MERGED", riders[0])   # conv2 weight gradient inside the layer-1 backward kernel / as its own kernel
+    monkeypatch.setenv("PDT_FC_MERGED", riders[1])      # classifier backward inside the layer-2 backward kernel / as its own kernel
     torch.manual_seed(2)
     a = pdt.models.ConvNet(fused=True).to(dev())
     b = pdt.models.ConvNet(fused=True).to(dev())
