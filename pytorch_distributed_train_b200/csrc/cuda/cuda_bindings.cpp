@@ -292,7 +292,8 @@ void register_cuda_bindings(py::module_& m) {
                           c10::optional<at::Tensor> be1, c10::optional<at::Tensor> rm1, c10::optional<at::Tensor> rv1, c10::optional<at::Tensor> nbt1,
                           double mom1, double eps1, const at::Tensor& w2, c10::optional<at::Tensor> b2, c10::optional<at::Tensor> g2,
                           c10::optional<at::Tensor> be2, c10::optional<at::Tensor> rm2, c10::optional<at::Tensor> rv2, c10::optional<at::Tensor> nbt2,
-                          double mom2, double eps2, const at::Tensor& fcw, c10::optional<at::Tensor> fcb) {
+                          double mom2, double eps2, const at::Tensor& fcw, c10::optional<at::Tensor> fcb, c10::optional<at::Tensor> target,
+                          bool defer_loss_mean) {
     chk(x, "x"); chk(w1, "w1"); chk(w2, "w2"); chk(fcw, "fc weight");
     c10::cuda::CUDAGuard g(x.device());
     TORCH_CHECK(x.numel() % 784 == 0 && w1.numel() == 400 && w2.numel() == 12800 && fcw.dim() == 2 && fcw.size(1) == 1568 && fcw.size(0) <= 16,
@@ -308,14 +309,30 @@ void register_cuda_bindings(py::module_& m) {
       return reinterpret_cast<long long*>(t->data_ptr<int64_t>());
     };
     ReduceScratch scr = scratch(x);
+    FusedCe ce;
+    at::Tensor loss, dlogits, loss_parts;
+    if (target.has_value() && target->defined()) {
+      chk(*target, "target", at::kLong);
+      TORCH_CHECK(target->numel() == B, "convnet_fwd: one target per image expected");
+      loss = at::empty({}, x.options());
+      dlogits = at::empty({B, ncls}, x.options());
+      loss_parts = at::empty({B}, x.options());
+      ce.target = reinterpret_cast<const long long*>(target->data_ptr<int64_t>());
+      ce.loss_parts = loss_parts.data_ptr<float>();
+      ce.loss = defer_loss_mean ? nullptr : loss.data_ptr<float>();   // deferred: convnet_l2_bwd_fc(…, loss_parts, loss) writes it
+      ce.dlogits = dlogits.data_ptr<float>();
+      ce.counter = scr.counter + 528;
+    }
     launch_convnet_fwd(x.data_ptr<float>(), w1.data_ptr<float>(), opt_ptr(b1, "b1"), opt_ptr(g1, "g1"), opt_ptr(be1, "be1"), y1.data_ptr<float>(),
                        p1.data_ptr<float>(), saved1.data_ptr<float>(), opt_mut(rm1, "rm1"), opt_mut(rv1, "rv1"), nbt_ptr(nbt1), static_cast<float>(mom1),
                        static_cast<float>(eps1), w2.data_ptr<float>(), opt_ptr(b2, "b2"), opt_ptr(g2, "g2"), opt_ptr(be2, "be2"), y2.data_ptr<float>(),
                        out.data_ptr<float>(), saved2.data_ptr<float>(), opt_mut(rm2, "rm2"), opt_mut(rv2, "rv2"), nbt_ptr(nbt2), static_cast<float>(mom2),
                        static_cast<float>(eps2), fcw.data_ptr<float>(), opt_ptr(fcb, "fc bias"), logits.data_ptr<float>(), ncls, B, scr.partials,
-                       GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x));
-    return py::make_tuple(p1, y1, saved1, out, y2, saved2, logits);
-  });
+                       GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x), ce);
+    return py::make_tuple(p1, y1, saved1, out, y2, saved2, logits, loss, dlogits, loss_parts);
+  }, py::arg("x"), py::arg("w1"), py::arg("b1"), py::arg("g1"), py::arg("be1"), py::arg("rm1"), py::arg("rv1"), py::arg("nbt1"), py::arg("mom1"),
+     py::arg("eps1"), py::arg("w2"), py::arg("b2"), py::arg("g2"), py::arg("be2"), py::arg("rm2"), py::arg("rv2"), py::arg("nbt2"), py::arg("mom2"),
+     py::arg("eps2"), py::arg("fcw"), py::arg("fcb"), py::arg("target") = py::none(), py::arg("defer_loss_mean") = false);
   m.def("convnet_l2_bwd", [](const at::Tensor& dout, const at::Tensor& y, const at::Tensor& saved, c10::optional<at::Tensor> gamma,
                              c10::optional<at::Tensor> beta, const at::Tensor& w, at::Tensor dgamma, at::Tensor dbeta) {
     chk(dout, "dout"); chk(y, "y"); chk(saved, "saved"); chk(w, "w"); chk(dgamma, "dgamma"); chk(dbeta, "dbeta");
@@ -335,7 +352,8 @@ void register_cuda_bindings(py::module_& m) {
   });
   m.def("convnet_l2_bwd_fc", [](const at::Tensor& dlogits, const at::Tensor& fcw, const at::Tensor& pooled, at::Tensor dfcw, c10::optional<at::Tensor> dfcb,
                                 const at::Tensor& y, const at::Tensor& saved, c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta,
-                                const at::Tensor& w, at::Tensor dgamma, at::Tensor dbeta) {
+                                const at::Tensor& w, at::Tensor dgamma, at::Tensor dbeta, c10::optional<at::Tensor> loss_parts,
+                                c10::optional<at::Tensor> loss_out) {
     chk(dlogits, "dlogits"); chk(fcw, "fc weight"); chk(pooled, "pooled"); chk(dfcw, "dfcw");
     chk(y, "y"); chk(saved, "saved"); chk(w, "w"); chk(dgamma, "dgamma"); chk(dbeta, "dbeta");
     c10::cuda::CUDAGuard g(y.device());
@@ -352,9 +370,11 @@ void register_cuda_bindings(py::module_& m) {
     launch_convnet_l2_bwd_fc(dlogits.data_ptr<float>(), fcw.data_ptr<float>(), pooled.data_ptr<float>(), dfcw.data_ptr<float>(), opt_mut(dfcb, "dfcb"),
                              ncls, y.data_ptr<float>(), saved.data_ptr<float>(), opt_ptr(gamma, "gamma"), opt_ptr(beta, "beta"), w.data_ptr<float>(),
                              dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dy.data_ptr<float>(), dx.data_ptr<float>(), dysum.data_ptr<float>(), B,
-                             scr.partials, GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(y));
+                             scr.partials, GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(y), opt_ptr(loss_parts, "loss_parts"),
+                             opt_mut(loss_out, "loss_out"));
     return py::make_tuple(dy, dx, dysum);
-  });
+  }, py::arg("dlogits"), py::arg("fcw"), py::arg("pooled"), py::arg("dfcw"), py::arg("dfcb"), py::arg("y"), py::arg("saved"), py::arg("gamma"),
+     py::arg("beta"), py::arg("w"), py::arg("dgamma"), py::arg("dbeta"), py::arg("loss_parts") = py::none(), py::arg("loss_out") = py::none());
   m.def("conv5x5_wgrad_win", [](const at::Tensor& dy_pad, const at::Tensor& x_pad, const at::Tensor& dysum, at::Tensor dw, c10::optional<at::Tensor> db) {
     chk(dy_pad, "dy_pad"); chk(x_pad, "x_pad"); chk(dysum, "dysum"); chk(dw, "dw");
     c10::cuda::CUDAGuard g(dy_pad.device());

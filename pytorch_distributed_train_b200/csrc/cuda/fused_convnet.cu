@@ -39,13 +39,17 @@ using namespace ptx;
 // ---- optional phase trace (PDT_FUSED_TRACE=1): globaltimer stamps of thread 0 of every CTA, read back by tools ----------
 __device__ unsigned long long g_trace[4][160][12];
 __device__ int g_trace_on = 0;
-__device__ __forceinline__ void trace(int kernel, int phase) {
-  if (g_trace_on && threadIdx.x == 0) {
+// The switch is read ONCE per kernel (TRACE_INIT, one global load whose latency overlaps the prologue); a stamp is then a predicated
+// branch on a register — a load of the switch per stamp cost ~0.2 µs each on the critical path (12 stamps in the forward kernel).
+#define TRACE_INIT() const bool trace_on_ = (threadIdx.x == 0) && (*reinterpret_cast<volatile int*>(&g_trace_on) != 0)
+__device__ __forceinline__ void trace_stamp(bool on, int kernel, int phase) {
+  if (on) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_trace[kernel][blockIdx.x][phase] = t;
   }
 }
+#define trace(kernel, phase) trace_stamp(trace_on_, kernel, phase)
 
 // CTA-wide sync of the first NAMED threads (named barrier 1) or of the whole CTA (NAMED = 0): kernels with extra
 // role warps keep their "main" threads in step without involving the others.
@@ -74,6 +78,34 @@ __device__ __forceinline__ void fold_rows(const float* __restrict__ partials, in
   }
   cta_sync<NAMED>();
   if (tid < W) s_out[tid] = (s_tmp[tid] + s_tmp[W + tid]) + (s_tmp[2 * W + tid] + s_tmp[3 * W + tid]);
+  cta_sync<NAMED>();
+}
+
+// The same with every thread of a THREADS-wide CTA loading: G = THREADS / W row classes, one L2 round trip for up to 8·G rows.
+// s_tmp: [G][W] floats.
+template <int W, int THREADS, int NAMED = 0>
+__device__ __forceinline__ void fold_rows_wide(const float* __restrict__ partials, int rows, float* s_tmp, float* s_out) {
+  constexpr int G = THREADS / W;
+  const int tid = threadIdx.x;
+  if (tid < G * W) {
+    const int col = tid % W, grp = tid / W;
+    float s = 0.f;
+    for (int r = grp; r < rows; r += 8 * G) {
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = (r + G * j < rows) ? __ldcg(partials + static_cast<size_t>(r + G * j) * W + col) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += t[j];
+    }
+    s_tmp[grp * W + col] = s;
+  }
+  cta_sync<NAMED>();
+  if (tid < W) {
+    float tot = 0.f;
+#pragma unroll
+    for (int g = 0; g < G; ++g) tot += s_tmp[g * W + tid];
+    s_out[tid] = tot;
+  }
   cta_sync<NAMED>();
 }
 
@@ -139,6 +171,7 @@ convnet_l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
   const L1Map m(tid);
   GridBar bar(gs);
+  TRACE_INIT();
   trace(0, 0);
 
   l1_load_image(x + static_cast<size_t>(n) * 784, xs, tid);
@@ -307,7 +340,7 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   __shared__ float xs[32 * 32];
   __shared__ float red[kL1Warps * 32];
-  __shared__ float s_tmp[4 * 32];
+  __shared__ float s_tmp[kL1Warps * 32];
   __shared__ float s_tot[32];
   __shared__ float s_scale[16], s_shift[16], s_mean[16], s_invstd[16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
@@ -369,6 +402,7 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
 
   const L1Map m(tid);
   GridBar bar(gs);
+  TRACE_INIT();
   trace(1, 0);
 
   l1_load_image<NAMED>(x + static_cast<size_t>(n) * 784, xs, tid);
@@ -437,7 +471,7 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
   trace(1, 1);
   bar.sync<NAMED>(gs);
   trace(1, 2);
-  fold_rows<32, NAMED>(partials, B, s_tmp, s_tot);  // [0..16) Σdz, [16..32) Σdz·x̂
+  fold_rows_wide<32, kL1Threads, NAMED>(partials, B, s_tmp, s_tot);  // [0..16) Σdz, [16..32) Σdz·x̂
   trace(1, 3);
   if (n == 0 && tid < 16) {
     if (dbeta) dbeta[tid] = s_tot[tid];
@@ -668,6 +702,7 @@ convnet_l2_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
 
   GridBar bar(gs);
+  TRACE_INIT();
   trace(2, 0);
   if (tid == 0) {
     tma_prefetch_desc(&tm_x);
@@ -891,7 +926,7 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
                    long long* nbt1, float mom1, float eps1, const float* __restrict__ w2, const float* __restrict__ b2,
                    const float* __restrict__ g2, const float* __restrict__ be2, float* __restrict__ y2, float* __restrict__ out, float* saved2,
                    float* rm2, float* rv2, long long* nbt2, float mom2, float eps2, const float* __restrict__ fcw,
-                   const float* __restrict__ fcb, float* __restrict__ logits, int ncls, float* partials, GridSync gs) {
+                   const float* __restrict__ fcb, float* __restrict__ logits, int ncls, float* partials, GridSync gs, FusedCe ce) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sa = smem;                                  // conv2 input patch, written by this CTA's layer-1 epilogue
@@ -899,14 +934,14 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
   float* ys = reinterpret_cast<float*>(sb + L2FwdSmem::kB);
   float* misc = ys + 196 * 32;                         // 2048 floats
   float* s_part = misc;                                // [4][64] / [25 warps][16]
-  float* s_tmp2 = misc + 512;                          // [4][64]
+  float* s_tmp2 = misc + 1024;                         // [12][64]
   float* s_tot2 = misc + 768;                          // [64]
   float* s_scale2 = misc + 832;                        // [32]
   float* s_shift2 = misc + 864;                        // [32]
   __shared__ float xs[32 * 32];
   __shared__ __align__(16) float ws[25 * 16];
   __shared__ float red[kL1Warps * 32];
-  __shared__ float s_tmp[4 * 32];
+  __shared__ float s_tmp[kL1Warps * 32];
   __shared__ float s_tot[32];
   __shared__ float s_scale[16], s_shift[16];
   __shared__ uint64_t bar_mma;
@@ -914,6 +949,8 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
   const L1Map m(tid);
   GridBar bar(gs);
+  TRACE_INIT();
+  trace(0, 0);
 
   if (tid == 0) {
     mbar_init(&bar_mma, 1);
@@ -937,6 +974,7 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  trace(0, 11);
 
   // ---- layer 1 ------------------------------------------------------------------------------------------------------
   float acc[16];
@@ -958,6 +996,7 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
       }
     }
   }
+  trace(0, 1);
   if (tid < 512) {
     const int co = tid >> 4, ci = tid & 15;
     uint8_t* dst = sb + sw128_off(co, ci >> 2) + (ci & 3) * 4;
@@ -981,8 +1020,21 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
     for (int wi = 0; wi < kL1Warps; ++wi) s += red[wi * 32 + tid];
     partials[static_cast<size_t>(n) * 32 + tid] = s;
   }
-  bar.sync(gs);
-  fold_rows<32>(partials, B, s_tmp, s_tot);
+  trace(0, 2);
+  bar.arrive(gs);
+  // in the barrier's shadow: everything layer 1 owes to global memory (backward reads it; nothing in this kernel does)
+  if (m.valid) {
+    float4* yp = reinterpret_cast<float4*>(y1 + ((static_cast<size_t>(n) * 28 + m.r) * 28 + m.c) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) yp[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+  for (int i = tid; i < 324 * 4; i += kL1Threads) {
+    const int P = i >> 2, pr = P / 18, pc = P - pr * 18;
+    if (pr < 2 || pr >= 16 || pc < 2 || pc >= 16) reinterpret_cast<float4*>(p1 + (static_cast<size_t>(n) * 324 + P) * 16)[i & 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  bar.wait(gs);
+  trace(0, 3);
+  fold_rows_wide<32, kL1Threads>(partials, B, s_tmp, s_tot);
   if (tid < 16) {
     const float cnt = static_cast<float>(B) * 784.f;
     const float mean = s_tot[tid] / cnt;
@@ -1025,6 +1077,7 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
   }
   fence_proxy_async_smem();   // generic-proxy writes of the patch and of the weights → visible to the tensor core
   __syncthreads();
+  trace(0, 4);
   // ---- layer 2: 100 MMAs, one elected thread -----------------------------------------------------------------------------
   if (warp == 0) {
     tc_fence_after();
@@ -1048,16 +1101,6 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
       umma_commit(&bar_mma);
     }
     __syncwarp();
-  }
-  // meanwhile: everything layer 1 still owes to global memory (nothing in this kernel waits for it)
-  if (m.valid) {
-    float4* yp = reinterpret_cast<float4*>(y1 + ((static_cast<size_t>(n) * 28 + m.r) * 28 + m.c) * 16);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) yp[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-  }
-  for (int i = tid; i < 324 * 4; i += kL1Threads) {
-    const int P = i >> 2, pr = P / 18, pc = P - pr * 18;
-    if (pr < 2 || pr >= 16 || pc < 2 || pc >= 16) reinterpret_cast<float4*>(p1 + (static_cast<size_t>(n) * 324 + P) * 16)[i & 3] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (warp >= 4 && warp < 8) {   // epilogue: TMEM lane quadrant = warp % 4
     mbar_wait(&bar_mma, 0);
@@ -1087,6 +1130,7 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
     tc_fence_before();
   }
   __syncthreads();
+  trace(0, 5);
   if (tid < 128) {
     const int c = tid & 31, part = tid >> 5;
     float s1 = 0.f, s2 = 0.f;
@@ -1101,12 +1145,21 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
   __syncthreads();
   float* partials2 = partials + static_cast<size_t>(B) * 32;
   if (tid < 64) partials2[static_cast<size_t>(n) * 64 + tid] = (s_part[tid] + s_part[64 + tid]) + (s_part[128 + tid] + s_part[192 + tid]);
-  bar.sync(gs);
-  for (int i = tid; i < 196 * 8; i += kL1Threads) {
+  trace(0, 6);
+  bar.arrive(gs);
+  float* fcs = reinterpret_cast<float*>(sb + 8192);   // classifier weights, staged behind the pooled activations (conv2's weights are dead)
+  const bool fc_staged = logits != nullptr && (reinterpret_cast<uintptr_t>(fcw) & 15) == 0;
+  if (fc_staged) {
+    for (int i = tid; i < ncls * 392; i += kL1Threads) cp_async_16(smem_u32(fcs + 4 * i), fcw + 4 * i, 16);
+    cp_async_commit();
+  }
+  for (int i = tid; i < 196 * 8; i += kL1Threads) {   // in the barrier's shadow: conv2's output for the backward pass
     const int pix = i >> 3, q = i & 7;
     reinterpret_cast<float4*>(y2 + (static_cast<size_t>(n) * 196 + pix) * 32)[q] = reinterpret_cast<const float4*>(ys + pix * 32)[(q + pix) & 7];
   }
-  fold_rows<64>(partials2, B, s_tmp2, s_tot2);
+  bar.wait(gs);
+  trace(0, 7);
+  fold_rows_wide<64, kL1Threads>(partials2, B, s_tmp2, s_tot2);
   if (tid < 32) {
     const float cnt = static_cast<float>(B) * 196.f;
     const float mean = s_tot2[tid] / cnt;
@@ -1139,7 +1192,9 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
     }
     pool[c * 49 + pp] = mx;
   }
+  cp_async_wait<0>();
   __syncthreads();
+  trace(0, 8);
   for (int i = tid; i < 1568; i += kL1Threads) out[static_cast<size_t>(n) * 1568 + i] = pool[i];
   if (logits != nullptr) {
     // classifier: thread t owns features t and t + 800 for every class (≤ 16): all weight loads independent
@@ -1149,9 +1204,9 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
     for (int c16 = 0; c16 < 16; ++c16) {
       float sacc = 0.f;
       if (c16 < ncls) {
-        const float* wr = fcw + static_cast<size_t>(c16) * 1568 + tid;
-        sacc = pv0 * __ldg(wr);
-        if (tid + kL1Threads < 1568) sacc = fmaf(pv1, __ldg(wr + kL1Threads), sacc);
+        const float* wr = (fc_staged ? fcs : fcw) + static_cast<size_t>(c16) * 1568 + tid;
+        sacc = pv0 * wr[0];
+        if (tid + kL1Threads < 1568) sacc = fmaf(pv1, wr[kL1Threads], sacc);
       }
       accv[c16] = sacc;
     }
@@ -1165,13 +1220,52 @@ convnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w1, co
       for (int c16 = 0; c16 < 16; ++c16) s_part[warp * 16 + c16] = accv[c16];
     }
     __syncthreads();
-    if (tid < ncls) {
-      float sfin = fcb ? fcb[tid] : 0.f;
+    if (warp == 0) {
+      float lg = -INFINITY;   // lanes < ncls: this image's logits
+      if (lane < ncls) {
+        lg = fcb ? fcb[lane] : 0.f;
 #pragma unroll 5
-      for (int wi = 0; wi < kL1Warps; ++wi) sfin += s_part[wi * 16 + tid];
-      logits[static_cast<size_t>(n) * ncls + tid] = sfin;
+        for (int wi = 0; wi < kL1Warps; ++wi) lg += s_part[wi * 16 + lane];
+        logits[static_cast<size_t>(n) * ncls + lane] = lg;
+      }
+      trace(0, 9);
+      if (ce.target != nullptr) {
+        // cross-entropy of this image and its gradient for a unit incoming gradient
+        float mx = lg;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        const float e = lane < ncls ? __expf(lg - mx) : 0.f;
+        float ssum = e;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, off);
+        const long long t = ce.target[n];
+        const bool t_ok = t >= 0 && t < ncls;
+        const float lt = __shfl_sync(0xffffffffu, lg, t_ok ? static_cast<int>(t) : 0);
+        if (lane < ncls) ce.dlogits[static_cast<size_t>(n) * ncls + lane] = (e / ssum - (t == lane ? 1.f : 0.f)) / static_cast<float>(B);
+        if (lane == 0) ce.loss_parts[n] = t_ok ? mx + __logf(ssum) - lt : 0.f;
+        if (ce.loss != nullptr) {   // batch mean now (otherwise layer-2 backward folds it: ce.loss == nullptr)
+          int last = 0;
+          if (lane == 0) {
+            __threadfence();
+            last = atomicAdd(ce.counter, 1u) == static_cast<unsigned int>(B) - 1u;
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last) {   // every image's term is in L2: the CTA that finished last folds the batch mean in a fixed order
+            __threadfence();
+            float sl = 0.f;
+            for (int r = lane; r < B; r += 32) sl += __ldcg(ce.loss_parts + r);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, off);
+            if (lane == 0) {
+              *ce.loss = sl / static_cast<float>(B);
+              *ce.counter = 0u;
+            }
+          }
+        }
+      }
     }
   }
+  trace(0, 10);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<64>(tmem_base);
@@ -1200,7 +1294,7 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
                       // FC only
                       const float* __restrict__ dlogits /*[B,ncls]*/, const float* __restrict__ fcw /*[ncls,1568]*/,
                       const float* __restrict__ pooled /*[B,1568] = forward's out*/, float* dfcw /*[ncls,1568]*/, float* dfcb /*[ncls]*/,
-                      int ncls) {
+                      int ncls, const float* __restrict__ loss_parts /*[B] or null*/, float* loss_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sa = smem;                                  // dy patch, written by the CTA in the TMA/UMMA SWIZZLE_128B layout
@@ -1221,6 +1315,7 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.x, B = gridDim.x;
 
   GridBar bar(gs);
+  TRACE_INIT();
   trace(3, 0);
   if (tid == 0) {
     mbar_init(&bar_mma, 1);
@@ -1333,6 +1428,14 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
     for (int q = 0; q < 8; ++q) s += s_part[q * 64 + tid];
     partials[static_cast<size_t>(n) * 64 + tid] = s;
   }
+  trace(3, 2);
+  bar.arrive(gs);
+  // ---- in the shadow of the grid barrier: work that no other CTA waits for ----
+  // zero halo of the global dy frame (the weight gradient sums over all 324 positions)
+  for (int i = tid; i < 324 * 8; i += kL2Threads) {
+    const int P = i >> 3, pr = P / 18, pc = P - pr * 18;
+    if (pr < 2 || pr >= 16 || pc < 2 || pc >= 16) reinterpret_cast<float4*>(dy + (static_cast<size_t>(n) * 324 + P) * 32)[i & 7] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if constexpr (FC) {
     // classifier weight gradient, slice = 16 consecutive columns (98 slices; "slice 98" = the bias): thread = (column, class).
     // The first slice of this CTA (slice n) was staged at kernel start.
@@ -1364,15 +1467,23 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
           for (; r < B; ++r) a[0] = fmaf(s_dl[r * 16 + j], s_pool[r * 16 + kl], a[0]);
           dfcw[static_cast<size_t>(j) * 1568 + slice * 16 + kl] = (a[0] + a[1]) + (a[2] + a[3]);
         }
-      } else if (dfcb != nullptr && tid < ncls) {
-        float a = 0.f;
-        for (int r = 0; r < B; ++r) a += s_dl[r * 16 + tid];
-        dfcb[tid] = a;
+      } else {
+        if (dfcb != nullptr && tid < ncls) {
+          float a = 0.f;
+          for (int r = 0; r < B; ++r) a += s_dl[r * 16 + tid];
+          dfcb[tid] = a;
+        }
+        if (loss_parts != nullptr && warp == 7) {   // the forward kernel left one cross-entropy term per image: batch mean, fixed order
+          float sl = 0.f;
+          for (int r = lane; r < B; r += 32) sl += __ldg(loss_parts + r);
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, off);
+          if (lane == 0) *loss_out = sl / static_cast<float>(B);
+        }
       }
     }
   }
-  trace(3, 2);
-  bar.sync(gs);
+  bar.wait(gs);
   trace(3, 3);
   fold_rows<64>(partials, B, s_tmp, s_tot);
   trace(3, 4);
@@ -1402,11 +1513,6 @@ convnet_l2_bwd_kernel(const float* __restrict__ dout /*[B,32,7,7]*/, const float
       }
     }
     s_part[g * 64 + c] = dsum;
-  }
-  // zero halo of the global dy frame (the weight gradient sums over all 324 positions)
-  for (int i = tid; i < 324 * 8; i += kL2Threads) {
-    const int P = i >> 3, pr = P / 18, pc = P - pr * 18;
-    if (pr < 2 || pr >= 16 || pc < 2 || pc >= 16) reinterpret_cast<float4*>(dy + (static_cast<size_t>(n) * 324 + P) * 32)[i & 7] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   fence_proxy_async_smem();
   __syncthreads();
@@ -1577,10 +1683,12 @@ void launch_convnet_l2_fwd(const float* x, const float* w, const float* bias, co
 void launch_convnet_fwd(const float* x, const float* w1, const float* b1, const float* g1, const float* be1, float* y1, float* p1, float* saved1,
                         float* rm1, float* rv1, long long* nbt1, float mom1, float eps1, const float* w2, const float* b2, const float* g2,
                         const float* be2, float* y2, float* out, float* saved2, float* rm2, float* rv2, long long* nbt2, float mom2, float eps2,
-                        const float* fcw, const float* fcb, float* logits, int ncls, int B, float* partials, GridSync gs, cudaStream_t st) {
+                        const float* fcw, const float* fcb, float* logits, int ncls, int B, float* partials, GridSync gs, cudaStream_t st,
+                        FusedCe ce) {
   if (logits != nullptr && ncls > 16) throw std::invalid_argument("convnet_fwd: the fused classifier handles at most 16 classes");
+  if (ce.target != nullptr && logits == nullptr) throw std::invalid_argument("convnet_fwd: the fused cross-entropy needs the fused classifier");
   launch_coop(convnet_fwd_kernel, B, kL1Threads, static_cast<size_t>(L2FwdSmem::kTotal), st, "convnet_fwd", x, w1, b1, g1, be1, y1, p1, saved1, rm1, rv1,
-              nbt1, mom1, eps1, w2, b2, g2, be2, y2, out, saved2, rm2, rv2, nbt2, mom2, eps2, fcw, fcb, logits, ncls, partials, gs);
+              nbt1, mom1, eps1, w2, b2, g2, be2, y2, out, saved2, rm2, rv2, nbt2, mom2, eps2, fcw, fcb, logits, ncls, partials, gs, ce);
 }
 
 void launch_convnet_l2_bwd(const float* dout, const float* y, const float* saved, const float* gamma, const float* beta, const float* w,
@@ -1588,17 +1696,18 @@ void launch_convnet_l2_bwd(const float* dout, const float* y, const float* saved
                            cudaStream_t st) {
   launch_coop(convnet_l2_bwd_kernel<false>, B, kL2Threads, static_cast<size_t>(L2BwdSmem::kTotal), st, "convnet_l2_bwd", dout, y, saved, gamma, beta, w,
               dgamma, dbeta, dy, dx, dysum, partials, gs, static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
-              static_cast<const float*>(nullptr), static_cast<float*>(nullptr), static_cast<float*>(nullptr), 0);
+              static_cast<const float*>(nullptr), static_cast<float*>(nullptr), static_cast<float*>(nullptr), 0, static_cast<const float*>(nullptr),
+              static_cast<float*>(nullptr));
 }
 
 void launch_convnet_l2_bwd_fc(const float* dlogits, const float* fcw, const float* pooled, float* dfcw, float* dfcb, int ncls, const float* y,
                               const float* saved, const float* gamma, const float* beta, const float* w, float* dgamma, float* dbeta, float* dy,
-                              float* dx, float* dysum, int B, float* partials, GridSync gs, cudaStream_t st) {
+                              float* dx, float* dysum, int B, float* partials, GridSync gs, cudaStream_t st, const float* loss_parts, float* loss_out) {
   if (ncls < 1 || ncls > 16) throw std::invalid_argument("convnet_l2_bwd_fc: 1..16 classes");
   if (B > 160) throw std::invalid_argument("convnet_l2_bwd_fc: batch too large for the staged dlogits");
   launch_coop(convnet_l2_bwd_kernel<true>, B, kL2Threads, static_cast<size_t>(L2BwdSmem::kTotalFc), st, "convnet_l2_bwd_fc",
               static_cast<const float*>(nullptr), y, saved, gamma, beta, w, dgamma, dbeta, dy, dx, dysum, partials, gs, dlogits, fcw, pooled, dfcw,
-              dfcb, ncls);
+              dfcb, ncls, loss_parts, loss_out);
 }
 
 }  // namespace pdt

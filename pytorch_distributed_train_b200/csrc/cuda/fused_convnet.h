@@ -35,12 +35,24 @@ void launch_convnet_l1_bwd_wgrad(const float* dp, const float* y, const float* x
 void launch_convnet_l2_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float* y, float* out,
                            float* saved, float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
                            const float* fcw, const float* fcb, float* logits, int ncls, int B, float* partials, GridSync gs, cudaStream_t st);
+// Optional rider of the whole-forward kernel: the mean cross-entropy of the logits against `target` and its gradient
+// (softmax − onehot)/B, computed by the CTA that owns the image; the batch mean is folded by the CTA that finishes last
+// (arrival counter, fixed summation order).  target == nullptr: off.
+struct FusedCe {
+  const long long* target = nullptr;   // [B]
+  float* loss_parts = nullptr;         // [B] scratch
+  float* loss = nullptr;               // scalar; nullptr = the mean is folded later (launch_convnet_l2_bwd_fc)
+  float* dlogits = nullptr;            // [B, ncls]
+  unsigned int* counter = nullptr;     // zero before first use; reset by the kernel
+};
+
 // The whole training forward in one launch: layer 1 and layer 2 (+ classifier, ncls ≤ 16) of an image in the same CTA; the
 // pooled layer-1 activations go into conv2's shared-memory patch directly.  partials: B·(32 + 64) floats.
 void launch_convnet_fwd(const float* x, const float* w1, const float* b1, const float* g1, const float* be1, float* y1, float* p1, float* saved1,
                         float* rm1, float* rv1, long long* nbt1, float mom1, float eps1, const float* w2, const float* b2, const float* g2,
                         const float* be2, float* y2, float* out, float* saved2, float* rm2, float* rv2, long long* nbt2, float mom2, float eps2,
-                        const float* fcw, const float* fcb, float* logits, int ncls, int B, float* partials, GridSync gs, cudaStream_t st);
+                        const float* fcw, const float* fcb, float* logits, int ncls, int B, float* partials, GridSync gs, cudaStream_t st,
+                        FusedCe ce = FusedCe{});
 // dout [B,32,7,7] → dgamma/dbeta [32], dy [B,18,18,32] frame with zero halo (gradient at the conv2 output), dx [B,18,18,16] frame
 // (data gradient, interior written), dysum [B,32] (per-image Σdy: the conv2 bias gradient is the sum of its rows).
 void launch_convnet_l2_bwd(const float* dout, const float* y, const float* saved, const float* gamma, const float* beta, const float* w,
@@ -49,6 +61,7 @@ void launch_convnet_l2_bwd(const float* dout, const float* y, const float* saved
 // inside the kernel; dfcw [ncls,1568] / dfcb [ncls] are produced from `pooled` = the forward's out [B,1568].  ncls ≤ 16.
 void launch_convnet_l2_bwd_fc(const float* dlogits, const float* fcw, const float* pooled, float* dfcw, float* dfcb, int ncls, const float* y,
                               const float* saved, const float* gamma, const float* beta, const float* w, float* dgamma, float* dbeta, float* dy,
-                              float* dx, float* dysum, int B, float* partials, GridSync gs, cudaStream_t st);
+                              float* dx, float* dysum, int B, float* partials, GridSync gs, cudaStream_t st,
+                              const float* loss_parts = nullptr, float* loss_out = nullptr);   // batch mean of the forward kernel's CE terms
 
 }  // namespace pdt

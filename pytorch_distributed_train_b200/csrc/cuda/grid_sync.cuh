@@ -45,8 +45,10 @@ struct GridBar {
     if constexpr (NAMED > 0) asm volatile("bar.sync 1, %0;" ::"n"(NAMED) : "memory");
     else __syncthreads();
   }
+  // Split form: arrive() publishes this CTA's contribution, wait() blocks until every CTA has arrived.  Work placed between
+  // the two runs in the barrier's shadow (≈ 2 µs of latency plus the skew between CTAs) — it must not depend on other CTAs.
   template <int NAMED = 0>
-  __device__ __forceinline__ void sync(GridSync gs) {
+  __device__ __forceinline__ void arrive(GridSync gs) {
     ++e;
     cta_sync<NAMED>();   // the CTA's partial row is complete
     if (threadIdx.x == 0) {
@@ -56,21 +58,30 @@ struct GridBar {
         st_relaxed_gpu(gs.flags, 0u);
         __threadfence();
         st_relaxed_gpu(gs.epoch, e);
-      } else {
-        unsigned int spins = 0;
-        unsigned long long t0 = 0;
-        while (static_cast<int>(ld_relaxed_gpu(gs.epoch) - e) < 0) {
-          // a grid that is not fully resident (non-cooperative launch on a busy GPU) would spin forever: trap after 4 s instead
-          if ((++spins & 0xFFFu) == 0) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            if (t0 == 0) t0 = t;
-            else if (t - t0 > 4000000000ull) asm volatile("trap;");
-          }
+      }
+    }
+  }
+  template <int NAMED = 0>
+  __device__ __forceinline__ void wait(GridSync gs) {
+    if (threadIdx.x == 0) {
+      unsigned int spins = 0;
+      unsigned long long t0 = 0;
+      while (static_cast<int>(ld_relaxed_gpu(gs.epoch) - e) < 0) {
+        // a grid that is not fully resident (non-cooperative launch on a busy GPU) would spin forever: trap after 4 s instead
+        if ((++spins & 0xFFFu) == 0) {
+          unsigned long long t;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+          if (t0 == 0) t0 = t;
+          else if (t - t0 > 4000000000ull) asm volatile("trap;");
         }
       }
     }
     cta_sync<NAMED>();
+  }
+  template <int NAMED = 0>
+  __device__ __forceinline__ void sync(GridSync gs) {
+    arrive<NAMED>(gs);
+    wait<NAMED>(gs);
   }
   __device__ __forceinline__ void finish(GridSync) {}
 };

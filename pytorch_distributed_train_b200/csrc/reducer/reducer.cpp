@@ -163,6 +163,16 @@ void Reducer::plan_chunks(Bucket& bk) const {
       cur.off = end;
     }
   }
+  // A last chunk much smaller than the target is not worth a kernel (and a cross-GPU barrier) of its own: the gradients that
+  // arrive last are the ones nothing can hide, so they ride with the chunk before them.
+  if (bk.chunks.size() >= 2 && bk.chunks.back().len * esize * 4 < target) {
+    const Chunk tail = bk.chunks.back();
+    bk.chunks.pop_back();
+    Chunk& prev = bk.chunks.back();
+    prev.end_slot = tail.end_slot;
+    prev.len += tail.len;
+    for (size_t q = tail.first_slot; q < tail.end_slot; ++q) bk.slot_chunk[q] = bk.chunks.size() - 1;
+  }
 }
 
 void Reducer::set_chunking(int64_t min_chunk_bytes, int64_t max_chunks) {

@@ -25,19 +25,22 @@ from __future__ import annotations
 
 from typing import Optional, Sequence
 
+import os
+
 import torch
 
 
 class GraphedTrainStep:
     def __init__(self, model, criterion, optimizer, example_inputs: Sequence[torch.Tensor], warmup: int = 3,
-                 zero_grad_set_to_none: bool = True, fuse_optimizer: bool = True, double_buffer_inputs: bool = False):
+                 zero_grad_set_to_none: bool = True, fuse_optimizer: bool = True, double_buffer_inputs: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainStep needs CUDA")
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.static_inputs = [t.clone() for t in example_inputs]
-        # EXPERIMENTAL (off by default, not yet validated on hardware): two input buffers, one captured graph each; the
-        # next batch's host→device copy runs on a copy stream while the current replay computes (NOTES_NEXT.md §2)
-        self.double_buffer = bool(double_buffer_inputs)
+        # two input buffers, one captured graph each: the next batch's copy into the step's static inputs (host→device from pinned
+        # memory, or device→device) runs on a copy stream while the current replay computes, instead of in front of it
+        # (PDT_DOUBLE_BUFFER_INPUTS=0: one buffer, copies on the compute stream)
+        self.double_buffer = bool(double_buffer_inputs) and os.environ.get("PDT_DOUBLE_BUFFER_INPUTS", "1") != "0"
         self.input_sets = [self.static_inputs] + ([[t.clone() for t in example_inputs]] if self.double_buffer else [])
         self.set_to_none = zero_grad_set_to_none
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -53,7 +56,12 @@ class GraphedTrainStep:
 
     def _eager_step(self, inputs=None):
         inputs = self.static_inputs if inputs is None else inputs
-        out = self.model(inputs[0])
+        from ..ops import functional as OF
+
+        # the step owns the targets before the model runs: a model whose forward kernel can fold the loss in does so
+        # (ops.functional.upcoming_targets); the criterion then finds value and gradient ready
+        with OF.upcoming_targets(inputs[1] if len(inputs) == 2 else None, loss_read_after_backward=True):
+            out = self.model(inputs[0])
         loss = self.criterion(out, *inputs[1:])
         self.optimizer.zero_grad(set_to_none=self.set_to_none)
         if self._seed is None or self._seed.shape != loss.shape or self._seed.dtype != loss.dtype:
@@ -104,12 +112,15 @@ class GraphedTrainStep:
             for e in self._done:
                 e.record(torch.cuda.current_stream(dev))
 
-    def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
+    def __call__(self, *inputs: torch.Tensor, inputs_ready: bool = False) -> torch.Tensor:
+        """One training step on ``inputs`` (pinned host tensors or device tensors).  ``inputs_ready=True``: the caller guarantees
+        that device-resident inputs are complete already (a GPU-resident dataset, a batch produced on another stream and
+        synchronised) — their copy into the step's buffers then overlaps the previous step instead of queueing behind it."""
         i = self.replays % len(self.graphs)
         if self.double_buffer:
             cur = torch.cuda.current_stream(self.static_inputs[0].device)
             self.copy_stream.wait_event(self._done[i])       # the replay that last read this buffer has finished
-            if any(t.is_cuda for t in inputs):
+            if not inputs_ready and any(t.is_cuda for t in inputs):
                 self.copy_stream.wait_stream(cur)            # device-resident sources may still be in flight on the caller's stream
             with torch.cuda.stream(self.copy_stream):
                 for dst, src in zip(self.input_sets[i], inputs):

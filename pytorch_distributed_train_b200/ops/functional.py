@@ -134,6 +134,34 @@ def fused_convnet_ok(x: torch.Tensor, model) -> bool:
     return all(p.is_contiguous() for p in (c1.weight, c2.weight, fc.weight))
 
 
+# Targets of the batch whose forward pass is about to run (engine.GraphedTrainStep knows them before it calls the model): the
+# whole-forward kernel then also produces the mean cross-entropy and its gradient, and `cross_entropy(logits, target)` picks
+# them up instead of launching a kernel.  A plain `loss = criterion(model(x), y)` loop never sets this and is unaffected.
+_upcoming_target: Optional[torch.Tensor] = None
+
+
+_loss_read_after_backward = False
+
+
+class upcoming_targets:
+    """``loss_read_after_backward=True`` (a captured step: nobody looks at the loss before the whole step has run) lets the
+    batch mean of the per-image loss terms be folded by the first backward kernel instead of by the forward kernel's tail."""
+
+    def __init__(self, target: Optional[torch.Tensor], loss_read_after_backward: bool = False):
+        self.target, self.late = target, loss_read_after_backward
+
+    def __enter__(self):
+        global _upcoming_target, _loss_read_after_backward
+        self.prev = (_upcoming_target, _loss_read_after_backward)
+        _upcoming_target, _loss_read_after_backward = self.target, self.late
+        return self
+
+    def __exit__(self, *exc):
+        global _upcoming_target, _loss_read_after_backward
+        _upcoming_target, _loss_read_after_backward = self.prev
+        return False
+
+
 def _wgrad_rides_on_layer1() -> bool:
     """conv2's weight gradient runs on the tensor cores *inside* the layer-1 backward kernel (two extra warps per CTA)
     instead of as a kernel of its own between the two layer kernels.  PDT_WGRAD_MERGED=0 restores the separate launch."""
@@ -154,10 +182,14 @@ class _FusedLayer1(torch.autograd.Function):
             # ONE launch for the whole forward pass (csrc/cuda/fused_convnet.cu: convnet_fwd_kernel): layer 2 and the
             # classifier of an image run in the same CTA; their results are handed to the next autograd nodes through `whole`
             c2, bn2, fc = whole["conv2"], whole["bn2"], whole["fc"]
-            out, y, saved, p2, y2, saved2, logits = _C.convnet_fwd(
+            defer = bool(whole.get("defer_loss_mean", False))
+            out, y, saved, p2, y2, saved2, logits, loss, dlogits, loss_parts = _C.convnet_fwd(
                 x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps, c2.weight, c2.bias, bn2.weight, bn2.bias,
-                bn2.running_mean, bn2.running_var, bn2.num_batches_tracked, float(bn2.momentum), float(bn2.eps), fc.weight, fc.bias)
+                bn2.running_mean, bn2.running_var, bn2.num_batches_tracked, float(bn2.momentum), float(bn2.eps), fc.weight, fc.bias,
+                whole.get("target"), defer)
             whole["layer2"] = (p2, y2, saved2, logits)
+            whole["ce"] = (loss, dlogits)
+            whole["ce_deferred"] = (loss_parts, loss) if defer else None
         else:
             out, y, saved = _C.convnet_l1_fwd(x, w, b, gamma, beta, running_mean, running_var, nbt, momentum, eps)
         ctx.save_for_backward(x, y, saved, gamma, beta)
@@ -199,6 +231,7 @@ class _FusedLayer2(torch.autograd.Function):
         ctx.params = (w, b, gamma, beta, fcw, fcb)
         ctx.link = link
         ctx.fc_rides = fc_rides
+        ctx.ce_deferred = whole.get("ce_deferred") if (whole is not None and fc_rides) else None
         if fc_rides:
             # the classifier's backward runs inside this node's backward kernel: the logits are this node's differentiable output
             ctx.save_for_backward(p1, y, saved, gamma, beta, w, out, fcw)
@@ -220,7 +253,8 @@ class _FusedLayer2(torch.autograd.Function):
                 raise RuntimeError("fused ConvNet: the pooled activations of the fused classifier path must not be used outside the model")
             dfcw = _grad_dst(fcw_p, fcw)
             dfcb = _grad_dst(fcb_p, fcb_p) if fcb_p is not None else None
-            dy, dp1, dysum = _C.convnet_l2_bwd_fc(dlogits.contiguous(), fcw, out, dfcw, dfcb, y, saved, gamma, beta, w, dg, dbe)
+            lp, lo = ctx.ce_deferred if ctx.ce_deferred is not None else (None, None)
+            dy, dp1, dysum = _C.convnet_l2_bwd_fc(dlogits.contiguous(), fcw, out, dfcw, dfcb, y, saved, gamma, beta, w, dg, dbe, lp, lo)
         else:
             p1, y, saved, gamma, beta, w = ctx.saved_tensors
             dy, dp1, dysum = _C.convnet_l2_bwd(dout.contiguous(), y, saved, gamma, beta, w, dg, dbe)
@@ -260,20 +294,29 @@ class _FusedClassifier(torch.autograd.Function):
 def fused_convnet_forward(x: torch.Tensor, model) -> torch.Tensor:
     """The reference ConvNet's training forward as ONE kernel (two with PDT_FUSED_WHOLE_FWD=0) (ref: ddp_example.py:36-41)."""
     c1, b1, c2, b2_bn, fc = model.layer1[0], model.layer1[1], model.layer2[0], model.layer2[1], model.fc
+    # the classifier's backward rides on layer 2's backward kernel (PDT_FC_MERGED=0: separate linear_bwd launch)
+    fc_rides = (os.environ.get("PDT_FC_MERGED", "1") != "0" and hasattr(_C, "convnet_l2_bwd_fc") and fc.weight.shape[0] <= 16
+                and fc.weight.requires_grad and c2.weight.requires_grad and fc.weight.data_ptr() % 16 == 0)
     whole = None
     if os.environ.get("PDT_FUSED_WHOLE_FWD", "1") != "0" and fc.weight.shape[0] <= 16 and hasattr(_C, "convnet_fwd"):
         whole = {"conv2": c2, "bn2": b2_bn, "fc": fc}
+        t = _upcoming_target
+        if (t is not None and os.environ.get("PDT_FUSED_CE", "1") != "0" and t.is_cuda and t.dtype == torch.int64 and t.dim() == 1
+                and t.shape[0] == x.shape[0] and t.is_contiguous() and torch.is_grad_enabled()):
+            whole["target"] = t
+            whole["defer_loss_mean"] = bool(_loss_read_after_backward and fc_rides)
     # conv2's weight gradient is produced by layer 1's backward kernel: layer 1's node owns (w2, b2) for autograd, `link` carries
     # the operands from layer 2's backward to it.  Only when conv1's parameters need gradients (layer 1's backward runs at all).
     link = {} if (_wgrad_rides_on_layer1() and c1.weight.requires_grad and c2.weight.requires_grad) else None
     w2, b2 = (c2.weight, c2.bias) if link is not None else (None, None)
     p1 = _FusedLayer1.apply(x, c1.weight, c1.bias, b1.weight, b1.bias, b1.running_mean, b1.running_var, b1.num_batches_tracked,
                             float(b1.momentum), float(b1.eps), w2, b2, whole, link)
-    # the classifier's backward rides on layer 2's backward kernel (PDT_FC_MERGED=0: separate linear_bwd launch)
-    fc_rides = (os.environ.get("PDT_FC_MERGED", "1") != "0" and hasattr(_C, "convnet_l2_bwd_fc") and fc.weight.shape[0] <= 16
-                and fc.weight.requires_grad and c2.weight.requires_grad and fc.weight.data_ptr() % 16 == 0)
     p2, logits = _FusedLayer2.apply(p1, c2.weight, c2.bias, b2_bn.weight, b2_bn.bias, b2_bn.running_mean, b2_bn.running_var,
                                     b2_bn.num_batches_tracked, float(b2_bn.momentum), float(b2_bn.eps), fc.weight, fc.bias, whole, link, fc_rides)
+    if whole is not None and whole.get("target") is not None:
+        logits = logits if fc_rides else _FusedClassifier.apply(p2, fc.weight, fc.bias, logits)
+        logits._pdt_ce = (whole["target"],) + whole["ce"]   # (target, loss, dlogits) for ops.cross_entropy
+        return logits
     if fc_rides:
         return logits
     return _FusedClassifier.apply(p2, fc.weight, fc.bias, logits)
@@ -375,8 +418,27 @@ class _CrossEntropy(torch.autograd.Function):
         return grad0 * dloss, None
 
 
+class _CrossEntropyPrecomputed(torch.autograd.Function):
+    """Autograd node of a mean cross-entropy whose value and unit-gradient were produced by the model's forward kernel."""
+
+    @staticmethod
+    def forward(ctx, logits, loss, grad0):
+        ctx.save_for_backward(grad0)
+        return loss.view_as(loss)
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad0,) = ctx.saved_tensors
+        if getattr(dloss, "_pdt_unit_seed", False):
+            return grad0, None, None
+        return grad0 * dloss, None, None
+
+
 def cross_entropy(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """Mean cross-entropy over the batch: fused log-softmax + NLL (ref: ddp_example.py:61,87)."""
+    pre = getattr(logits, "_pdt_ce", None)
+    if pre is not None and pre[0] is target:
+        return _CrossEntropyPrecomputed.apply(logits, pre[1], pre[2])
     return _CrossEntropy.apply(logits, target)
 
 
