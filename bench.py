@@ -295,6 +295,8 @@ def run_ours(args):
 
             stall = {"loader": (0.0, -1), "step": (0.0, -1), "readback": (0.0, -1)}
 
+            pending = {"log": None}
+
             def e2e_step(i):
                 t0 = time.perf_counter()
                 images, labels = next(it)                     # pinned host tensors from the loader
@@ -302,13 +304,22 @@ def run_ours(args):
                 state["h2d"] = images.numel() * images.element_size() + labels.numel() * labels.element_size()
                 loss = step(images, labels)                   # H2D of this batch into the step's inputs + graph replay
                 t2 = time.perf_counter()
-                if i >= R:
-                    evs[i % R].synchronize()                  # the slot's previous loss has reached the host
-                host_loss[i % R].copy_(loss.detach(), non_blocking=True)   # D2H of every step's loss
-                evs[i % R].record()
-                if (i + 1) % 10 == 0 and rank == 0:           # the reference's logging cadence: a blocking read (ref: ddp_example.py:93-95)
-                    evs[i % R].synchronize()
-                    state["logged"] = float(host_loss[i % R])
+                if args.no_graph:
+                    if i >= R:
+                        evs[i % R].synchronize()                  # the slot's previous loss has reached the host
+                    host_loss[i % R].copy_(loss.detach(), non_blocking=True)   # D2H of every step's loss
+                    evs[i % R].record()
+                    if (i + 1) % 10 == 0 and rank == 0:           # the reference's logging cadence: a blocking read (ref: ddp_example.py:93-95)
+                        evs[i % R].synchronize()
+                        state["logged"] = float(host_loss[i % R])
+                else:
+                    h = step.loss_to_host()                       # D2H of every step's loss (side stream, pinned ring)
+                    if pending["log"] is not None:                # the log line of step i-1 (ref cadence: every 10th step, ddp_example.py:93-95):
+                        state["logged"] = pending["log"].item()   # blocking read, issued after step i is queued so the device stays busy
+                        pending["log"] = None
+                    if (i + 1) % 10 == 0 and rank == 0:
+                        pending["log"] = h
+                    state["last"] = h
                 t3 = time.perf_counter()
                 if i >= W:   # where the host spends its worst moments (ms, timed step index)
                     for k, d in (("loader", t1 - t0), ("step", t2 - t1), ("readback", t3 - t2)):
@@ -319,7 +330,7 @@ def run_ours(args):
             if e2e_windows is not None:
                 e2e_windows["host_worst_ms"] = stall
             e2e = {"ms": max(ms_e2e_dev, ms_e2e_wall), "dev_ms": ms_e2e_dev, "wall_ms": ms_e2e_wall, "windows": e2e_windows,
-                   "h2d": state["h2d"], "loss": float(host_loss[(W + K - 1) % R])}
+                   "h2d": state["h2d"], "loss": float(host_loss[(W + K - 1) % R]) if args.no_graph else state["last"].item()}
     ms_dev = max_over_ranks(ms_dev)
     out = None
     if e2e is not None:
@@ -356,8 +367,9 @@ def run_ours(args):
                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": 4, "windows": e2e["windows"],
                           "device_ms_per_step": e2e["dev_ms"] / K, "wall_ms_per_step": e2e["wall_ms"] / K,
                           "note": "pdt.data.MNIST(synthetic idx files) -> pdt.DistributedSampler -> pdt.DataLoader(batch 100, pin_memory) -> "
-                                  "GraphedTrainStep(pinned images, pinned labels): H2D + whole-step graph replay; async D2H of every loss, "
-                                  "blocking read every 10 steps on rank 0 (the loop of cli.dist_train / ref ddp_example.py:82-95)"}
+                                  "GraphedTrainStep(pinned images, pinned labels): H2D + whole-step graph replay; step.loss_to_host(): async D2H of every "
+                                  "loss; blocking read of every 10th loss on rank 0, issued after the following step has been queued (the loop of "
+                                  "cli.dist_train; cadence of ref ddp_example.py:93-95)"}
     pdt.destroy_process_group()
     if verify is not None and not verify["ok"]:
         if out is not None:

@@ -110,21 +110,36 @@ def dist_train(gpu: int, args) -> None:
     for epoch in range(first_epoch, args.epochs):
         if args.set_epoch:
             train_sampler.set_epoch(epoch)
+        pending = None   # (step index, loss handle) of a log line whose value is still on its way to the host
+        fmt = "Epoch [{}/{}], Step [{}/{}], Loss: {:.4f}"
         for i, (images, labels) in enumerate(train_loader):
             if args.steps and i >= args.steps:
                 break
-            images = images.to(device, non_blocking=True)
-            labels = labels.to(device, non_blocking=True)
-            if step_fn is not None and images.shape[0] == batch_size:
-                loss = step_fn(images, labels)
+            graphed = step_fn is not None and images.shape[0] == batch_size
+            if graphed:
+                # the (pinned) host batch goes straight into the captured step's input buffers; the copy overlaps the previous step
+                step_fn(images, labels)
+                handle = step_fn.loss_to_host()
             else:
+                images = images.to(device, non_blocking=True)
+                labels = labels.to(device, non_blocking=True)
                 outputs = model(images)
                 loss = criterion(outputs, labels)
                 optimizer.zero_grad()
                 loss.backward()
                 optimizer.step()
+                handle = loss
+            if pending is not None and gpu == 0:
+                # the log line of the previous step, printed once this step has been queued: the GPU keeps working while the host waits
+                print(fmt.format(epoch + 1, args.epochs, pending[0], total_step, pending[1].item()))
+                pending = None
             if (i + 1) % args.log_interval == 0 and gpu == 0:
-                print("Epoch [{}/{}], Step [{}/{}], Loss: {:.4f}".format(epoch + 1, args.epochs, i + 1, total_step, loss.item()))
+                if graphed:
+                    pending = (i + 1, handle)
+                else:
+                    print(fmt.format(epoch + 1, args.epochs, i + 1, total_step, handle.item()))
+        if pending is not None and gpu == 0:
+            print(fmt.format(epoch + 1, args.epochs, pending[0], total_step, pending[1].item()))
         if args.checkpoint:
             pdt.utils.save_checkpoint(args.checkpoint, model, optimizer, epoch=epoch + 1, sampler=train_sampler)
     if use_cuda:

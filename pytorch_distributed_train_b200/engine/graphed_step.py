@@ -46,6 +46,8 @@ class GraphedTrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_loss: Optional[torch.Tensor] = None
         self.replays = 0
+        self._d2h_stream, self._d2h_count, self._last = None, 0, 0
+        self._loss_copied = [None, None]
         self._seed: Optional[torch.Tensor] = None   # d(loss)/d(loss) = 1, allocated once (autograd would fill a new one per step)
         self.fused_optimizer = False
         if fuse_optimizer and hasattr(optimizer, "fuse_with_ddp") and hasattr(model, "enable_optimizer_fusion"):
@@ -132,9 +134,54 @@ class GraphedTrainStep:
                 dst.copy_(src, non_blocking=True)
         if hasattr(self.optimizer, "sync_lr"):
             self.optimizer.sync_lr()  # scheduler changes reach the captured step through a device scalar
+        cur = torch.cuda.current_stream(self.static_inputs[0].device)
+        if self._loss_copied[i] is not None:
+            cur.wait_event(self._loss_copied[i])             # loss_to_host() of this graph's previous replay has read the loss buffer
+            self._loss_copied[i] = None
         self.graphs[i].replay()
         if self.double_buffer:
-            self._done[i].record(torch.cuda.current_stream(self.static_inputs[0].device))
+            self._done[i].record(cur)
         self.replays += 1
+        self._last = i
         self.static_loss = self.losses[i]
         return self.static_loss
+
+    def loss_to_host(self) -> "HostLoss":
+        """Start an asynchronous device→host copy of the last step's loss on a side stream (pinned ring of 16 slots) and return a
+        handle; ``handle.item()`` blocks until that copy has landed.  Nothing is queued on the compute stream, so the next
+        replay is not held up by the copy — call it every step and read the handles you want to log whenever convenient
+        (reading a handle *after* the next step has been enqueued keeps the device busy while the host waits)."""
+        dev = self.static_inputs[0].device
+        if self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream(device=dev)
+            self._host_loss = torch.zeros(16, dtype=self.static_loss.dtype).pin_memory()
+            self._d2h_evs = [torch.cuda.Event() for _ in range(16)]
+        slot = self._d2h_count % 16
+        if self._d2h_count >= 16:
+            self._d2h_evs[slot].synchronize()                # the slot's previous value has been delivered (and may be overwritten)
+        after = torch.cuda.Event()
+        after.record(torch.cuda.current_stream(dev))         # the replay (and anything the caller queued behind it)
+        self._d2h_stream.wait_event(after)
+        with torch.cuda.stream(self._d2h_stream):
+            self._host_loss[slot].copy_(self.static_loss.detach().reshape(()), non_blocking=True)
+            self._d2h_evs[slot].record(self._d2h_stream)
+        self._loss_copied[self._last] = self._d2h_evs[slot]
+        self._d2h_count += 1
+        return HostLoss(self, slot, self._d2h_count)
+
+
+class HostLoss:
+    """Handle of one loss value on its way to pinned host memory (``GraphedTrainStep.loss_to_host``)."""
+
+    __slots__ = ("_owner", "_slot", "_gen", "_value")
+
+    def __init__(self, owner, slot, gen):
+        self._owner, self._slot, self._gen, self._value = owner, slot, gen, None
+
+    def item(self) -> float:
+        if self._value is None:
+            if self._owner._d2h_count - self._gen >= 16:
+                raise RuntimeError("HostLoss: read too late — the pinned slot has been reused (handles stay valid for 16 steps)")
+            self._owner._d2h_evs[self._slot].synchronize()
+            self._value = float(self._owner._host_loss[self._slot])
+        return self._value

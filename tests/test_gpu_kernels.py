@@ -379,6 +379,17 @@ def test_single_gpu_ddp_and_graphed_step():
         l0 = step(x, t).item()
         l1 = step(x, t).item()
         assert l1 < l0 < eager[2] + 1e-3
+        # pinned host batches, double-buffered inputs, losses delivered through the side-stream ring: same trajectory as device batches
+        xp, tp = x.cpu().pin_memory(), t.cpu().pin_memory()
+        handles = []
+        for _ in range(20):
+            step(xp, tp)
+            handles.append(step.loss_to_host())
+        vals = [h.item() for h in handles[-16:]]
+        assert all(a > b for a, b in zip(vals, vals[1:])) and vals[0] < l1, (l1, vals)
+        assert abs(vals[-1] - step.static_loss.item()) < 1e-7
+        with pytest.raises(RuntimeError, match="read too late"):
+            handles[0].item()
     finally:
         pdt.destroy_process_group()
 
