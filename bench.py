@@ -279,7 +279,7 @@ def run_ours(args):
             dataset = pdt.data.MNIST(root=data_root, train=True)
             sampler = pdt.DistributedSampler(dataset, num_replicas=world, rank=rank)
             loader = pdt.DataLoader(dataset=dataset, batch_size=BATCH, shuffle=False, num_workers=0, pin_memory=True, sampler=sampler,
-                                    prefetch=int(os.environ.get("PDT_BENCH_PREFETCH", "4")))
+                                    prefetch=int(os.environ.get("PDT_BENCH_PREFETCH", "8")))
             R = 8
             host_loss = torch.zeros(R, dtype=torch.float32).pin_memory()
             evs = [torch.cuda.Event() for _ in range(R)]
@@ -294,6 +294,7 @@ def run_ours(args):
             it = batches()
 
             stall = {"loader": (0.0, -1), "step": (0.0, -1), "readback": (0.0, -1)}
+            host_samples = {"loader": [], "step": [], "readback": []}
 
             pending = {"log": None}
 
@@ -321,14 +322,17 @@ def run_ours(args):
                         pending["log"] = h
                     state["last"] = h
                 t3 = time.perf_counter()
-                if i >= W:   # where the host spends its worst moments (ms, timed step index)
+                if i >= W:   # where the host spends its time: worst moments (ms, timed step index) and per-phase samples for the medians
                     for k, d in (("loader", t1 - t0), ("step", t2 - t1), ("readback", t3 - t2)):
+                        host_samples[k].append(d * 1e3)
                         if d * 1e3 > stall[k][0]:
                             stall[k] = (round(d * 1e3, 3), i - W)
 
             ms_e2e_dev, ms_e2e_wall, _, e2e_windows = timed(e2e_step, W, K)
             if e2e_windows is not None:
                 e2e_windows["host_worst_ms"] = stall
+                e2e_windows["host_median_ms"] = {k: round(sorted(v)[len(v) // 2], 4) for k, v in host_samples.items() if v}
+                e2e_windows["host_cpus"] = len(os.sched_getaffinity(0))
             e2e = {"ms": max(ms_e2e_dev, ms_e2e_wall), "dev_ms": ms_e2e_dev, "wall_ms": ms_e2e_wall, "windows": e2e_windows,
                    "h2d": state["h2d"], "loss": float(host_loss[(W + K - 1) % R]) if args.no_graph else state["last"].item()}
     ms_dev = max_over_ranks(ms_dev)
@@ -350,7 +354,7 @@ def run_ours(args):
             "details": {"comm": info.get("comm_kind"), "cuda_graph": not args.no_graph, "buckets": info.get("bucket_sizes"),
                         "grad_copies_into_bucket": info.get("copies_into_bucket"),
                         "fused_allreduce_sgd": bool(getattr(optimizer, "_fused_active", False)),
-                        "reduce_chunks": info.get("reduce_chunks"), "backward_comm_exposed_us": info.get("backward_comm_exposed_us"),
+                        "reduce_chunks": info.get("reduce_chunks"), "backward_comm_exposed_us": (info.get("avg_backward_comm_exposed_time_us") if info.get("timed_iterations") else None),  # eager iterations past the reducer's 10-step warm-up only; a replayed graph carries no marks
                         "input_staging": ("double-buffered: the copy of batch k+1 into the step's input buffers (D2D from the resident pool / H2D "
                                           "from pinned memory in e2e) runs on a copy stream while step k replays; every step still copies its "
                                           "own batch" if (not args.no_graph and getattr(graphed, "double_buffer", False)) else "copied on the compute stream in front of the step")},

@@ -6,6 +6,7 @@
 
 #include "comm/comm.h"
 #include "data/batch_loader.h"
+#include "engine/step_pipeline.h"
 #include "common/net.h"
 #include "reducer/bucket_plan.h"
 #include "reducer/reducer.h"
@@ -173,6 +174,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
            py::arg("pin_memory") = false, py::arg("device") = -1)
       .def("start", &BatchStager::start, py::arg("indices"))
       .def("num_batches", &BatchStager::num_batches)
+      .def("stats", &BatchStager::stats)
       .def("next", [](BatchStager& s) -> py::object {
         at::Tensor images, targets;
         bool ok;
@@ -182,6 +184,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         }
         if (!ok) return py::none();
         return py::make_tuple(images, targets);
+      });
+
+  py::class_<StepPipeline, std::shared_ptr<StepPipeline>>(m, "StepPipeline")
+      .def(py::init([](int device, int num_sets, const at::Tensor& loss_like) {
+             return std::make_shared<StepPipeline>(device, num_sets, loss_like.scalar_type());
+           }), py::arg("device"), py::arg("num_sets"), py::arg("loss_like"))
+      .def("stage_inputs", &StepPipeline::stage_inputs, py::arg("set"), py::arg("dst"), py::arg("src"), py::arg("inputs_ready") = false,
+           py::arg("overlap") = true)
+      .def("replayed", &StepPipeline::replayed)
+      .def("loss_to_host", &StepPipeline::loss_to_host)
+      .def("loss_value", [](StepPipeline& p, int64_t gen) {
+        py::gil_scoped_release r;
+        return p.loss_value(gen);
       });
 
   py::class_<Reducer, std::shared_ptr<Reducer>>(m, "Reducer")

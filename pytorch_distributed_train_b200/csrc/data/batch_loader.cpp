@@ -2,6 +2,8 @@
 
 #include <c10/util/Exception.h>
 
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #if PDT_WITH_CUDA
@@ -59,6 +61,7 @@ void BatchStager::alloc_slot(Slot& s) {
   auto to = at::TensorOptions().dtype(targets_.scalar_type()).device(at::kCPU).pinned_memory(pin_);
   s.images = at::empty(shp, io);
   s.targets = at::empty({batch_}, to);
+  s.out = std::make_shared<std::atomic<int>>(0);
 }
 
 void BatchStager::stop_worker() {
@@ -67,7 +70,8 @@ void BatchStager::stop_worker() {
     stop_ = true;
   }
   cv_.notify_all();
-  if (th_.joinable()) th_.join();
+  for (auto& t : workers_) if (t.joinable()) t.join();
+  workers_.clear();
   stop_ = false;
   running_ = false;
 }
@@ -78,18 +82,32 @@ void BatchStager::start(at::Tensor indices) {
   indices_ = indices.contiguous();
   const int64_t n = indices_.numel();
   nbatches_ = drop_last_ ? n / batch_ : (n + batch_ - 1) / batch_;
-  produce_ = consume_ = 0;
-  last_handed_ = -1;
+  produce_ = consume_ = reap_ = 0;
+  st_fill_us_ = st_wait_free_us_ = st_next_wait_us_ = st_ready_sum_ = st_alloc_us_ = 0;
+  st_allocs_ = 0;
+  st_next_calls_ = 0;
+  last_handed_ = prev_handed_ = -1;
   ++epoch_;
+  int64_t slot_index = 0;
   for (auto& s : ring_) {
+    s.seq = slot_index++;
     if (s.state == 2) s.state = 0;   // a batch of the abandoned epoch may still be in user hands: the retention check covers it
     if (s.state == 1) s.state = 0;
+    if (s.state == 3) {              // handed back in the previous epoch, its event still pending: wait for it here, once
+#if PDT_WITH_CUDA
+      if (s.event) static_cast<at::cuda::CUDAEvent*>(s.event.get())->synchronize();
+#endif
+      s.event.reset();
+      s.state = 0;
+    }
   }
   running_ = true;
-  th_ = std::thread([this] { this->worker(); });
+  if (const char* e = std::getenv("PDT_LOADER_WORKERS")) nworkers_ = std::max(1, std::atoi(e));
+  nworkers_ = static_cast<int>(std::min<int64_t>(nworkers_, std::max<int64_t>(1, depth_ / 2)));
+  for (int w = 0; w < nworkers_; ++w) workers_.emplace_back([this, w] { this->worker(w); });
 }
 
-void BatchStager::worker() {
+void BatchStager::worker(int w) {
 #if PDT_WITH_CUDA
   if (pin_ && device_ >= 0) cudaSetDevice(device_);
 #endif
@@ -97,22 +115,23 @@ void BatchStager::worker() {
   const int64_t* idx = indices_.data_ptr<int64_t>();
   const int64_t N = data_.size(0);
   const size_t tsize = targets_.element_size();
-  for (int64_t b = 0; b < nbatches_; ++b) {
+  for (int64_t b = w; b < nbatches_; b += nworkers_) {
     Slot& s = ring_[static_cast<size_t>(b % depth_)];
-    std::shared_ptr<void> ev;
+    const auto tw0 = std::chrono::steady_clock::now();
     {
       std::unique_lock<std::mutex> lk(mu_);
-      cv_.wait(lk, [&] { return stop_ || s.state == 0; });
+      cv_.wait(lk, [&] { return stop_ || (s.state == 0 && s.seq == b); });   // free (handed back, consumer's event completed) and it is batch b's turn
       if (stop_) return;
-      ev = std::move(s.event);
-      s.event.reset();
     }
-#if PDT_WITH_CUDA
-    if (ev) static_cast<at::cuda::CUDAEvent*>(ev.get())->synchronize();   // the consumer's copies out of this slot are done
-#endif
-    // a batch somebody still holds (list(loader), a stashed view) is never overwritten: the slot gets fresh buffers
-    if (s.images.use_count() > 1 || s.targets.use_count() > 1 || s.images.storage().use_count() > 1 || s.targets.storage().use_count() > 1)
+    const auto tw1 = std::chrono::steady_clock::now();
+    // a batch somebody still holds (list(loader), a stashed view) is never overwritten: the slot gets fresh buffers, the old ones
+    // live on until the last tensor handed out over them dies (see next(): outstanding-tensor counter)
+    bool fresh = false;
+    if (s.out->load(std::memory_order_acquire) != 0) {
       alloc_slot(s);
+      fresh = true;
+    }
+    const auto tw1b = std::chrono::steady_clock::now();
     const int64_t lo = b * batch_, hi = std::min(n, lo + batch_);
     float* out = s.images.data_ptr<float>();
     char* tout = static_cast<char*>(s.targets.data_ptr());
@@ -123,6 +142,13 @@ void BatchStager::worker() {
       for (int64_t i = lo; i < hi; ++i) {
         const int64_t r = idx[i];
         TORCH_CHECK(r >= 0 && r < N, "BatchStager: index ", r, " out of range");
+        if (i + 3 < hi) {   // the sampler's order is random: pull the row three samples ahead towards the cache while this one converts
+          const int64_t rn = idx[i + 3];
+          if (rn >= 0 && rn < N) {
+            const char* pn = reinterpret_cast<const char*>(src + rn * row_elems_);
+            for (int64_t off = 0; off < row_elems_; off += 64) __builtin_prefetch(pn + off, 0, 1);
+          }
+        }
         const uint8_t* p = src + r * row_elems_;
         float* o = out + (i - lo) * row_elems_;
         u8_to_f32(p, o, row_elems_, sc);
@@ -134,6 +160,13 @@ void BatchStager::worker() {
       for (int64_t i = lo; i < hi; ++i) {
         const int64_t r = idx[i];
         TORCH_CHECK(r >= 0 && r < N, "BatchStager: index ", r, " out of range");
+        if (i + 3 < hi) {
+          const int64_t rn = idx[i + 3];
+          if (rn >= 0 && rn < N) {
+            const char* pn = reinterpret_cast<const char*>(src + rn * row_elems_);
+            for (int64_t off = 0; off < row_elems_ * 4; off += 64) __builtin_prefetch(pn + off, 0, 1);
+          }
+        }
         const float* p = src + r * row_elems_;
         float* o = out + (i - lo) * row_elems_;
         if (sc == 1.f) std::memcpy(o, p, static_cast<size_t>(row_elems_) * sizeof(float));
@@ -141,20 +174,49 @@ void BatchStager::worker() {
         std::memcpy(tout + (i - lo) * tsize, tin + r * tsize, tsize);
       }
     }
+    const auto tw2 = std::chrono::steady_clock::now();
     {
       std::lock_guard<std::mutex> g(mu_);
       s.rows = hi - lo;
       s.state = 1;
       ++produce_;
+      st_wait_free_us_ += std::chrono::duration<double, std::micro>(tw1 - tw0).count();
+      st_fill_us_ += std::chrono::duration<double, std::micro>(tw2 - tw1b).count();
+      st_alloc_us_ += std::chrono::duration<double, std::micro>(tw1b - tw1).count();
+      st_allocs_ += fresh ? 1 : 0;
     }
     cv_.notify_all();
   }
 }
 
+std::vector<double> BatchStager::stats() const {
+  std::lock_guard<std::mutex> g(const_cast<std::mutex&>(mu_));
+  return {static_cast<double>(produce_), st_fill_us_, st_wait_free_us_, static_cast<double>(st_next_calls_), st_ready_sum_, st_next_wait_us_,
+          static_cast<double>(st_allocs_), st_alloc_us_};
+}
+
+void BatchStager::reap_events_locked() {
+  // events complete in the order they were recorded: stop at the first one that has not
+  for (int64_t b = reap_; b < consume_; ++b) {
+    Slot& p = ring_[static_cast<size_t>(b % depth_)];
+    if (p.state != 3) break;
+#if PDT_WITH_CUDA
+    if (p.event && !static_cast<at::cuda::CUDAEvent*>(p.event.get())->query()) break;
+#endif
+    p.event.reset();
+    p.state = 0;
+    p.seq = b + depth_;
+    reap_ = b + 1;
+  }
+}
+
 bool BatchStager::next(at::Tensor* images, at::Tensor* targets) {
-  // the consumer moves on: everything it enqueued on its current stream for the previous batch precedes this event
-  if (last_handed_ >= 0) {
-    Slot& p = ring_[static_cast<size_t>(last_handed_ % depth_)];
+  // The consumer moves on.  The batch handed out TWO calls ago goes back to the ring: its tensors are no longer referenced by an
+  // ordinary `for batch in loader` loop (the loop variables and the iterator's own frame still hold the *previous* batch while this
+  // call runs — releasing that one here made the retention check below re-allocate its pinned buffers on every step whenever the
+  // device was idle, 150 µs each).  Everything the consumer enqueued on its current stream for that batch precedes the event.
+  if (prev_handed_ >= 0) {
+    Slot& p = ring_[static_cast<size_t>(prev_handed_ % depth_)];
     std::shared_ptr<void> ev;
 #if PDT_WITH_CUDA
     if (pin_ && device_ >= 0) {
@@ -167,20 +229,54 @@ bool BatchStager::next(at::Tensor* images, at::Tensor* targets) {
     {
       std::lock_guard<std::mutex> g(mu_);
       p.event = std::move(ev);
-      p.state = 0;
+      p.state = 3;
+      reap_events_locked();
     }
     cv_.notify_all();
-    last_handed_ = -1;
   }
+  prev_handed_ = last_handed_;
+  last_handed_ = -1;
   if (consume_ >= nbatches_) return false;
   Slot& s = ring_[static_cast<size_t>(consume_ % depth_)];
   {
     std::unique_lock<std::mutex> lk(mu_);
-    cv_.wait(lk, [&] { return s.state == 1; });
+    const auto tn0 = std::chrono::steady_clock::now();
+    ++st_next_calls_;
+    for (const auto& q : ring_) st_ready_sum_ += q.state == 1 ? 1.0 : 0.0;
+    struct Acc {
+      double& dst;
+      std::chrono::steady_clock::time_point t0;
+      ~Acc() { dst += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); }
+    } acc{st_next_wait_us_, tn0};
+    while (s.state != 1) {
+      // the batch is not staged yet: maybe every slot is waiting for the device — keep reaping while we wait
+      const int64_t before = reap_;
+      reap_events_locked();
+      if (reap_ != before) {
+        lk.unlock();
+        cv_.notify_all();
+        lk.lock();
+        continue;
+      }
+      cv_.wait_for(lk, std::chrono::microseconds(20));
+    }
     s.state = 2;
   }
-  *images = s.rows == batch_ ? s.images : s.images.narrow(0, 0, s.rows);
-  *targets = s.rows == batch_ ? s.targets : s.targets.narrow(0, 0, s.rows);
+  // Hand out FRESH tensor objects over the slot's buffers.  Their storage deleter keeps the buffers alive and counts the tensors
+  // still in user hands — the retention check of the worker.  (Handing out the ring's own tensors and looking at use_count() does
+  // not work: once a tensor has had a Python wrapper, the wrapper and the TensorImpl keep each other alive, so the count never
+  // returns to one and every refill re-allocated its pinned buffers, ~150 µs each.)
+  {
+    std::vector<int64_t> shp{s.rows};
+    shp.insert(shp.end(), sample_shape_.begin(), sample_shape_.end());
+    auto out = s.out;
+    at::Tensor keep_i = s.images, keep_t = s.targets;
+    out->fetch_add(2, std::memory_order_acq_rel);
+    *images = at::from_blob(s.images.data_ptr(), shp, [out, keep_i](void*) { out->fetch_sub(1, std::memory_order_acq_rel); },
+                            at::TensorOptions().dtype(at::kFloat).device(at::kCPU));
+    *targets = at::from_blob(s.targets.data_ptr(), {s.rows}, [out, keep_t](void*) { out->fetch_sub(1, std::memory_order_acq_rel); },
+                             at::TensorOptions().dtype(targets_.scalar_type()).device(at::kCPU));
+  }
   last_handed_ = consume_;
   ++consume_;
   return true;

@@ -10,10 +10,13 @@
 // Ring safety: a slot is refilled only after (1) the consumer has asked for a later batch, (2) the CUDA event recorded
 // on the consumer's stream at that moment has completed (so `.to(device, non_blocking=True)` copies out of the slot
 // are done), and (3) nobody else holds a reference to the slot's tensors — if the user kept a batch (list(loader)),
-// the slot gets fresh buffers instead of being overwritten.
+// the slot gets fresh buffers instead of being overwritten.  The events are *queried by the consumer thread* (inside
+// next(), oldest first): a worker parked in cudaEventSynchronize spins inside the driver and slowed every CUDA call of
+// the training thread by 4× (14 → 58 µs per step, profiles/r2/e2e_stalls.md); the worker itself never touches CUDA.
 #pragma once
 #include <ATen/ATen.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -33,16 +36,22 @@ class BatchStager {
   // Blocks (release the GIL around it) until the worker has staged the batch.
   bool next(at::Tensor* images, at::Tensor* targets);
   int64_t num_batches() const { return nbatches_; }
+  // Diagnostics since start(): {batches produced, µs the worker spent filling, µs it waited for a free slot,
+  // next() calls, Σ ready slots seen at next(), µs next() waited, slots re-allocated because a batch was still referenced, µs spent on that}
+  std::vector<double> stats() const;
 
  private:
   struct Slot {
-    at::Tensor images, targets;
-    int state = 0;          // 0 free, 1 ready, 2 handed out
+    at::Tensor images, targets;   // the slot's (pinned) buffers; handed out as from_blob views that count themselves
+    std::shared_ptr<std::atomic<int>> out;   // tensors over these buffers still alive outside the ring
+    int state = 0;          // 0 free, 1 ready, 2 handed out, 3 returned (waiting for the consumer's CUDA event)
     int64_t rows = 0;
+    int64_t seq = 0;        // the batch index this slot takes next (several workers fill slots concurrently)
     std::shared_ptr<void> event;   // at::cuda::CUDAEvent recorded when the consumer moved on (opaque here)
   };
-  void worker();
+  void worker(int w);
   void alloc_slot(Slot& s);
+  void reap_events_locked();   // returned slots whose event has completed become free (consumer thread, mu_ held)
   void stop_worker();
 
   at::Tensor data_, targets_, indices_;
@@ -52,11 +61,15 @@ class BatchStager {
   double scale_;
   int device_;
   std::vector<Slot> ring_;
-  std::thread th_;
+  std::vector<std::thread> workers_;   // worker w stages batches w, w + W, ... (PDT_LOADER_WORKERS, default 3)
+  int nworkers_ = 3;
   std::mutex mu_;
   std::condition_variable cv_;
-  int64_t produce_ = 0, consume_ = 0, epoch_ = 0;
-  int64_t last_handed_ = -1;
+  int64_t produce_ = 0, consume_ = 0, reap_ = 0, epoch_ = 0;
+  double st_fill_us_ = 0, st_wait_free_us_ = 0, st_next_wait_us_ = 0, st_ready_sum_ = 0;
+  int64_t st_next_calls_ = 0, st_allocs_ = 0;
+  double st_alloc_us_ = 0;
+  int64_t last_handed_ = -1, prev_handed_ = -1;
   bool stop_ = false, running_ = false;
 };
 

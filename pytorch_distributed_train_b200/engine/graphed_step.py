@@ -46,8 +46,7 @@ class GraphedTrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.static_loss: Optional[torch.Tensor] = None
         self.replays = 0
-        self._d2h_stream, self._d2h_count, self._last = None, 0, 0
-        self._loss_copied = [None, None]
+        self._last = 0
         self._seed: Optional[torch.Tensor] = None   # d(loss)/d(loss) = 1, allocated once (autograd would fill a new one per step)
         self.fused_optimizer = False
         if fuse_optimizer and hasattr(optimizer, "fuse_with_ddp") and hasattr(model, "enable_optimizer_fusion"):
@@ -107,40 +106,20 @@ class GraphedTrainStep:
             if not self.double_buffer and (parity() == p0 or (ordered is not None and ordered())):
                 break  # even number of staged collectives per step, or case (a): one graph replays safely
         self.graph, self.static_loss = self.graphs[0], self.losses[0]
-        if self.double_buffer:
-            self.copy_stream = torch.cuda.Stream(device=dev)
-            self._ready = [torch.cuda.Event() for _ in self.graphs]
-            self._done = [torch.cuda.Event() for _ in self.graphs]
-            for e in self._done:
-                e.record(torch.cuda.current_stream(dev))
+        # the host side of a replay (input staging on a copy stream, ordering against the replays that use the buffers, losses to pinned
+        # memory on a side stream) is native: csrc/engine/step_pipeline.cpp
+        self._io = _C.StepPipeline(dev.index if dev.index is not None else torch.cuda.current_device(), len(self.graphs), self.static_loss)
 
     def __call__(self, *inputs: torch.Tensor, inputs_ready: bool = False) -> torch.Tensor:
         """One training step on ``inputs`` (pinned host tensors or device tensors).  ``inputs_ready=True``: the caller guarantees
         that device-resident inputs are complete already (a GPU-resident dataset, a batch produced on another stream and
         synchronised) — their copy into the step's buffers then overlaps the previous step instead of queueing behind it."""
         i = self.replays % len(self.graphs)
-        if self.double_buffer:
-            cur = torch.cuda.current_stream(self.static_inputs[0].device)
-            self.copy_stream.wait_event(self._done[i])       # the replay that last read this buffer has finished
-            if not inputs_ready and any(t.is_cuda for t in inputs):
-                self.copy_stream.wait_stream(cur)            # device-resident sources may still be in flight on the caller's stream
-            with torch.cuda.stream(self.copy_stream):
-                for dst, src in zip(self.input_sets[i], inputs):
-                    dst.copy_(src, non_blocking=True)
-                self._ready[i].record(self.copy_stream)
-            cur.wait_event(self._ready[i])
-        else:
-            for dst, src in zip(self.static_inputs, inputs):
-                dst.copy_(src, non_blocking=True)
+        self._io.stage_inputs(i, self.input_sets[i % len(self.input_sets)], list(inputs), inputs_ready, self.double_buffer)
         if hasattr(self.optimizer, "sync_lr"):
             self.optimizer.sync_lr()  # scheduler changes reach the captured step through a device scalar
-        cur = torch.cuda.current_stream(self.static_inputs[0].device)
-        if self._loss_copied[i] is not None:
-            cur.wait_event(self._loss_copied[i])             # loss_to_host() of this graph's previous replay has read the loss buffer
-            self._loss_copied[i] = None
         self.graphs[i].replay()
-        if self.double_buffer:
-            self._done[i].record(cur)
+        self._io.replayed(i)
         self.replays += 1
         self._last = i
         self.static_loss = self.losses[i]
@@ -151,37 +130,18 @@ class GraphedTrainStep:
         handle; ``handle.item()`` blocks until that copy has landed.  Nothing is queued on the compute stream, so the next
         replay is not held up by the copy — call it every step and read the handles you want to log whenever convenient
         (reading a handle *after* the next step has been enqueued keeps the device busy while the host waits)."""
-        dev = self.static_inputs[0].device
-        if self._d2h_stream is None:
-            self._d2h_stream = torch.cuda.Stream(device=dev)
-            self._host_loss = torch.zeros(16, dtype=self.static_loss.dtype).pin_memory()
-            self._d2h_evs = [torch.cuda.Event() for _ in range(16)]
-        slot = self._d2h_count % 16
-        if self._d2h_count >= 16:
-            self._d2h_evs[slot].synchronize()                # the slot's previous value has been delivered (and may be overwritten)
-        after = torch.cuda.Event()
-        after.record(torch.cuda.current_stream(dev))         # the replay (and anything the caller queued behind it)
-        self._d2h_stream.wait_event(after)
-        with torch.cuda.stream(self._d2h_stream):
-            self._host_loss[slot].copy_(self.static_loss.detach().reshape(()), non_blocking=True)
-            self._d2h_evs[slot].record(self._d2h_stream)
-        self._loss_copied[self._last] = self._d2h_evs[slot]
-        self._d2h_count += 1
-        return HostLoss(self, slot, self._d2h_count)
+        return HostLoss(self._io, self._io.loss_to_host(self._last, self.static_loss))
 
 
 class HostLoss:
-    """Handle of one loss value on its way to pinned host memory (``GraphedTrainStep.loss_to_host``)."""
+    """Handle of one loss value on its way to pinned host memory (``GraphedTrainStep.loss_to_host``); valid for 15 further steps."""
 
-    __slots__ = ("_owner", "_slot", "_gen", "_value")
+    __slots__ = ("_io", "_gen", "_value")
 
-    def __init__(self, owner, slot, gen):
-        self._owner, self._slot, self._gen, self._value = owner, slot, gen, None
+    def __init__(self, io, gen):
+        self._io, self._gen, self._value = io, gen, None
 
     def item(self) -> float:
         if self._value is None:
-            if self._owner._d2h_count - self._gen >= 16:
-                raise RuntimeError("HostLoss: read too late — the pinned slot has been reused (handles stay valid for 16 steps)")
-            self._owner._d2h_evs[self._slot].synchronize()
-            self._value = float(self._owner._host_loss[self._slot])
+            self._value = float(self._io.loss_value(self._gen))
         return self._value

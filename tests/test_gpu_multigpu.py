@@ -180,6 +180,11 @@ def _resnet(rank, world, syncbn, port):
 
     dev = torch.device("cuda", rank)
     steps = 3
+    # fp32 convolutions in both arms: with TF32 operand rounding a 1e-7 difference between our SyncBN arithmetic (fp64 sums) and
+    # torch's (Welford) flips roundings in the next convolution, and layer4's BatchNorm over 4·2·2·world samples amplifies that to
+    # several percent of the gradient — a property of the comparison, not of either implementation (profiles/numerics.md §2)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
     def data(s):
         g = torch.Generator().manual_seed(77 * s + rank)
@@ -235,8 +240,8 @@ def test_ddp_resnet18_multibucket_matches_torch(syncbn):
     assert len({r["psum"] for r in res}) == 1, "parameters diverged between ranks"
     assert len(res[0]["buckets"]) >= 3 and sum(res[0]["buckets"]) == 4 * 11181642
     for r in res:
-        assert max(r["grad_rel"].values()) < 2e-2, r["grad_rel"]
-        assert max(abs(a - b) for a, b in zip(r["ours"], r["theirs"])) < 5e-2, (r["ours"], r["theirs"], r["grad_rel"])
+        assert max(r["grad_rel"].values()) < 1e-3, r["grad_rel"]
+        assert max(abs(a - b) for a, b in zip(r["ours"], r["theirs"])) < 5e-3, (r["ours"], r["theirs"], r["grad_rel"])
 
 
 def _graphed(rank, world, syncbn):

@@ -16,9 +16,15 @@ crit = pdt.nn.CrossEntropyLoss()
 opt = pdt.optim.SGD(net.parameters(), 1e-2)
 x = torch.rand(100, 1, 28, 28, device=dev)
 y = torch.randint(0, 10, (100,), device=dev)
+from pytorch_distributed_train_b200.ops import functional as OF
+
 losses = []
 for _ in range(steps):
-    loss = crit(net(x), y)
+    # the engine's step (engine/graphed_step.py::_eager_step): targets announced before the forward pass, so the forward kernel
+    # also produces the loss and its gradient — the kernels launched here are the ones a captured step replays
+    with OF.upcoming_targets(y, loss_read_after_backward=True):
+        out = net(x)
+    loss = crit(out, y)
     opt.zero_grad()
     loss.backward()
     opt.step()

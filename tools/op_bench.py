@@ -85,27 +85,37 @@ def main():
     w2, b2, g2, be2 = c2.weight.detach(), c2.bias.detach(), bn2.weight.detach(), bn2.bias.detach()
     wf, bf = fc.weight.detach(), fc.bias.detach()
 
-    # ---- ours: the cooperative fused layers (what a captured step launches) -------------------------------------------
-    p1, y1, sv1 = _C.convnet_l1_fwd(x, w1, b1, g1, be1, None, None, None, 0.1, 1e-5)
-    p2, y2, sv2, logits = _C.convnet_l2_fwd(p1, w2, b2, g2, be2, None, None, None, 0.1, 1e-5, wf, bf)
-    loss, dlog = _C.cross_entropy_fwd(logits, tgt, True)
+    # ---- ours: the cooperative fused kernels a captured step launches (4 per step), plus the stand-alone variants ----------
+    rm1, rv1, nb1 = bn1.running_mean, bn1.running_var, bn1.num_batches_tracked
+    rm2, rv2, nb2 = bn2.running_mean, bn2.running_var, bn2.num_batches_tracked
+
+    def fwd_whole():
+        return _C.convnet_fwd(x, w1, b1, g1, be1, rm1, rv1, nb1, 0.1, 1e-5, w2, b2, g2, be2, rm2, rv2, nb2, 0.1, 1e-5, wf, bf, tgt, True)
+
+    p1, y1, sv1, p2, y2, sv2, logits, loss, dlog, lparts = fwd_whole()
     dwf, dbf = torch.empty_like(wf), torch.empty_like(bf)
-    dflat = _C.linear_bwd(dlog, p2.reshape(B, -1), wf, True, dwf, dbf)
     dg2, dbe2 = torch.empty(32, device=dev), torch.empty(32, device=dev)
-    dy2, dp1, dysum = _C.convnet_l2_bwd(dflat.view(B, 32, 7, 7), y2, sv2, g2, be2, w2, dg2, dbe2)
+
+    def l2_bwd_fc():
+        return _C.convnet_l2_bwd_fc(dlog, wf, p2, dwf, dbf, y2, sv2, g2, be2, w2, dg2, dbe2, lparts, loss)
+
+    dy2, dp1, dysum = l2_bwd_fc()
     dw2, db2 = torch.empty_like(w2), torch.empty_like(b2)
     dg1, dbe1, dw1, db1 = torch.empty(16, device=dev), torch.empty(16, device=dev), torch.empty_like(w1), torch.empty_like(b1)
     params = [w1, b1, g1, be1, w2, b2, g2, be2, wf, bf]
     grads = [torch.randn_like(p) for p in params]
+    dflat = torch.randn(B, 32, 7, 7, device=dev)
     ours = [
-        ("layer1 fwd: conv1+BN+ReLU+pool (1 kernel)", lambda: _C.convnet_l1_fwd(x, w1, b1, g1, be1, None, None, None, 0.1, 1e-5)),
-        ("layer2 fwd: conv2(tcgen05)+BN+ReLU+pool+fc (1 kernel)", lambda: _C.convnet_l2_fwd(p1, w2, b2, g2, be2, None, None, None, 0.1, 1e-5, wf, bf)),
-        ("cross-entropy fwd (+dlogits) (1 kernel)", lambda: _C.cross_entropy_fwd(logits, tgt, True)),
-        ("fc bwd: dX, dW, db (1 kernel)", lambda: _C.linear_bwd(dlog, p2.reshape(B, -1), wf, True, dwf, dbf)),
-        ("layer2 bwd: pool/ReLU/BN bwd + conv2 dgrad(tcgen05) (1 kernel)", lambda: _C.convnet_l2_bwd(dflat.view(B, 32, 7, 7), y2, sv2, g2, be2, w2, dg2, dbe2)),
-        ("conv2 wgrad, TMA window (tcgen05) + fold (2 kernels)", lambda: _C.conv5x5_wgrad_win(dy2, p1, dysum, dw2, db2)),
-        ("layer1 bwd: pool/ReLU/BN bwd + conv1 wgrad (1 kernel)", lambda: _C.convnet_l1_bwd(dp1, y1, x, sv1, g1, be1, dg1, dbe1, dw1, db1)),
+        ("forward: conv1+BN+ReLU+pool + conv2(tcgen05)+BN+ReLU+pool + fc + cross-entropy (1 kernel)", fwd_whole),
+        ("backward A: classifier bwd + pool/ReLU/BN2 bwd + conv2 dgrad(tcgen05) (1 kernel)", l2_bwd_fc),
+        ("backward B: pool/ReLU/BN1 bwd + conv1 wgrad(mma.sync) + conv2 wgrad(tcgen05, window) (1 kernel)",
+         lambda: _C.convnet_l1_bwd_wgrad(dp1, y1, x, sv1, g1, be1, dg1, dbe1, dw1, db1, dy2, p1, dysum, dw2, db2)),
         ("SGD, 10 tensors (1 kernel)", lambda: _C.sgd_multi(params, grads, [], 1e-4, None, 0.0, 0.0, 0.0, False, False, False)),
+        ("(variant) cross-entropy fwd (+dlogits) as its own kernel", lambda: _C.cross_entropy_fwd(logits, tgt, True)),
+        ("(variant) fc bwd as its own kernel", lambda: _C.linear_bwd(dlog, p2.reshape(B, -1), wf, True, dwf, dbf)),
+        ("(variant) layer-2 bwd without the classifier rider", lambda: _C.convnet_l2_bwd(dflat, y2, sv2, g2, be2, w2, dg2, dbe2)),
+        ("(variant) conv2 wgrad as its own kernel (TMA-materialised tap pairs + in-kernel fold)", lambda: _C.conv5x5_wgrad_win(dy2, p1, dysum, dw2, db2)),
+        ("(variant) layer-1 bwd without the wgrad rider", lambda: _C.convnet_l1_bwd(dp1, y1, x, sv1, g1, be1, dg1, dbe1, dw1, db1)),
     ]
 
     # ---- library: the ATen / cuDNN / cuBLAS ops the reference's modules dispatch to, same shapes -----------------------
@@ -164,7 +174,7 @@ def main():
              "us_cold_eager": cold_time(lambda: go_c1[0, 0, 0, :1].zero_())}
     rows.append(floor)
     print(f"floor    {floor['us_in_graph']:8.2f} us in-graph   {floor['us_cold_eager']:8.2f} us cold eager   {floor['op']}")
-    t_ours = sum(r["us_in_graph"] for r in rows if r["arm"] == "ours" and r["us_in_graph"])
+    t_ours = sum(r["us_in_graph"] for r in rows if r["arm"] == "ours" and r["us_in_graph"] and not r["op"].startswith("(variant)"))
     print(f"ours, sum of the step's kernels in-graph: {t_ours:.1f} us")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "op_bench.json"), "w") as f:

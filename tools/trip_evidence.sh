@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout -s KILL 300 python tools/op_bench.py > gpurun_out/op_bench.log 2>&1; tail -n 32 gpurun_out/op_bench.log | cut -c1-200
 timeout -s KILL 200 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 8 -c 16 --csv --log-file gpurun_out/launches_fused.csv python tools/one_step.py 3 > gpurun_out/ncu_launches.log 2>&1
-for k in convnet_fwd_kernel convnet_l2_bwd_kernel convnet_l1_bwd_kernel conv5x5_wgrad_win_kernel linear_bwd_kernel; do
+for k in convnet_fwd_kernel convnet_l2_bwd_kernel convnet_l1_bwd_kernel; do
   timeout -s KILL 240 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/prof_$k python tools/one_step.py 3 > gpurun_out/ncu_$k.log 2>&1
   tail -n 1 gpurun_out/ncu_$k.log | cut -c1-200
 done
