@@ -238,7 +238,7 @@ void register_cuda_bindings(py::module_& m) {
   m.def("convnet_l1_bwd_wgrad", [](const at::Tensor& dp, const at::Tensor& y, const at::Tensor& x, const at::Tensor& saved,
                                    c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta, at::Tensor dgamma, at::Tensor dbeta, at::Tensor dw,
                                    c10::optional<at::Tensor> db, const at::Tensor& dy2_pad, const at::Tensor& x2_pad, const at::Tensor& dysum2,
-                                   at::Tensor dw2, c10::optional<at::Tensor> db2) {
+                                   at::Tensor dw2, c10::optional<at::Tensor> db2, py::object sgd) {
     chk(dp, "dp"); chk(y, "y"); chk(x, "x"); chk(saved, "saved"); chk(dgamma, "dgamma"); chk(dbeta, "dbeta"); chk(dw, "dw");
     chk(dy2_pad, "dy2_pad"); chk(x2_pad, "x2_pad"); chk(dysum2, "dysum2"); chk(dw2, "dw2");
     c10::cuda::CUDAGuard g(x.device());
@@ -247,6 +247,46 @@ void register_cuda_bindings(py::module_& m) {
                     dgamma.numel() == 16 && dbeta.numel() == 16, "convnet_l1_bwd_wgrad: layer-1 shape mismatch");
     TORCH_CHECK(dy2_pad.numel() == static_cast<int64_t>(B) * 324 * 32 && x2_pad.numel() == static_cast<int64_t>(B) * 324 * 16 &&
                     dysum2.numel() == static_cast<int64_t>(B) * 32 && dw2.numel() == 12800, "convnet_l1_bwd_wgrad: layer-2 shape mismatch");
+    // sgd = (params[10], prev_grads[4], momentum_bufs[10] or [], lr, lr_tensor, momentum, dampening, weight_decay, nesterov, maximize, first_step):
+    // parameters in the order conv1.w, conv1.b, bn1.w, bn1.b, conv2.w, conv2.b, fc.w, fc.b, bn2.w, bn2.b (entries may be None)
+    SgdRider rider;
+    std::vector<at::Tensor> keep;   // keeps converted tensors alive until the launch
+    if (!sgd.is_none()) {
+      auto t = sgd.cast<py::tuple>();
+      TORCH_CHECK(t.size() == 11, "convnet_l1_bwd_wgrad: sgd tuple of 11 entries expected");
+      auto params = t[0].cast<std::vector<c10::optional<at::Tensor>>>();
+      auto prev = t[1].cast<std::vector<c10::optional<at::Tensor>>>();
+      auto bufs = t[2].cast<std::vector<c10::optional<at::Tensor>>>();
+      TORCH_CHECK(params.size() == 10 && prev.size() == 4 && (bufs.empty() || bufs.size() == 10), "convnet_l1_bwd_wgrad: sgd lists have the wrong length");
+      static const int64_t want[10] = {400, 16, 16, 16, 12800, 32, -1, -1, 32, 32};
+      const double momentum = t[5].cast<double>();
+      for (int k = 0; k < 10; ++k) {
+        if (!params[k].has_value() || !params[k]->defined()) continue;
+        chk(*params[k], "sgd param");
+        TORCH_CHECK(want[k] < 0 || params[k]->numel() == want[k], "convnet_l1_bwd_wgrad: sgd parameter ", k, " has the wrong size");
+        rider.p[k] = params[k]->data_ptr<float>();
+        if (momentum != 0.0) {
+          TORCH_CHECK(!bufs.empty() && bufs[k].has_value() && bufs[k]->numel() == params[k]->numel(), "convnet_l1_bwd_wgrad: momentum buffer ", k, " missing");
+          chk(*bufs[k], "momentum buffer");
+          rider.m[k] = bufs[k]->data_ptr<float>();
+        }
+        if (k >= 6) {
+          TORCH_CHECK(prev[k - 6].has_value() && prev[k - 6]->numel() == params[k]->numel(), "convnet_l1_bwd_wgrad: gradient of sgd parameter ", k, " missing");
+          chk(*prev[k - 6], "sgd gradient");
+          rider.g_prev[k - 6] = prev[k - 6]->data_ptr<float>();
+          rider.n_prev[k - 6] = static_cast<int>(params[k]->numel());
+        }
+      }
+      TORCH_CHECK(rider.p[0] && rider.p[4], "convnet_l1_bwd_wgrad: the convolution weights must take part in the fused update");
+      rider.h = SgdHyper{static_cast<float>(t[3].cast<double>()), static_cast<float>(momentum), static_cast<float>(t[6].cast<double>()),
+                         static_cast<float>(t[7].cast<double>()), t[8].cast<bool>() ? 1 : 0, t[9].cast<bool>() ? 1 : 0, t[10].cast<bool>() ? 1 : 0, nullptr};
+      if (!t[4].is_none()) {
+        at::Tensor lrt = t[4].cast<at::Tensor>();
+        chk(lrt, "lr_tensor");
+        rider.h.lr_dev = lrt.data_ptr<float>();
+      }
+      rider.on = 1;
+    }
     ReduceScratch scr = scratch(x);
     const size_t l1_floats = static_cast<size_t>(B) * (64 + 512);
     TORCH_CHECK(static_cast<long long>(l1_floats) + static_cast<long long>(B) * 512 * 32 <= scr.capacity_floats, "convnet_l1_bwd_wgrad: scratch too small");
@@ -254,8 +294,10 @@ void register_cuda_bindings(py::module_& m) {
                                 opt_ptr(beta, "beta"), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dw.data_ptr<float>(), opt_mut(db, "db"),
                                 dy2_pad.data_ptr<float>(), x2_pad.data_ptr<float>(), dysum2.data_ptr<float>(), dw2.data_ptr<float>(),
                                 opt_mut(db2, "db2"), B, scr.partials, scr.partials + static_cast<size_t>(B) * 64, scr.partials + l1_floats,
-                                GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x));
-  });
+                                GridSync{scr.counter + 512, scr.counter + 520}, cur_stream(x), rider);
+  }, py::arg("dp"), py::arg("y"), py::arg("x"), py::arg("saved"), py::arg("gamma"), py::arg("beta"), py::arg("dgamma"), py::arg("dbeta"),
+     py::arg("dw"), py::arg("db"), py::arg("dy2_pad"), py::arg("x2_pad"), py::arg("dysum2"), py::arg("dw2"), py::arg("db2"),
+     py::arg("sgd") = py::none());
   m.def("convnet_l2_fwd", [](const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> gamma,
                              c10::optional<at::Tensor> beta, c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
                              c10::optional<at::Tensor> nbt, double momentum, double eps, c10::optional<at::Tensor> fcw,

@@ -318,6 +318,19 @@ __device__ __forceinline__ void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// One SGD update (the arithmetic of sgd_multi_kernel, ops_simt.cu) of element *p with gradient g.
+__device__ __forceinline__ void sgd_apply(float* p, float g, float* m, const SgdHyper& h, float lr) {
+  float gv = h.maximize ? -g : g;
+  const float pv = *p;
+  if (h.weight_decay != 0.f) gv = fmaf(h.weight_decay, pv, gv);
+  if (h.momentum != 0.f) {
+    const float b = h.first_step ? gv : fmaf(h.momentum, *m, (1.f - h.dampening) * gv);
+    *m = b;
+    gv = h.nesterov ? fmaf(h.momentum, b, gv) : b;
+  }
+  *p = fmaf(-lr, gv, pv);
+}
+
 template <bool WG>
 __global__ void __launch_bounds__(WG ? L1WgCfg::kThreads : kL1Threads, 1)
 convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ saved,
@@ -325,7 +338,7 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
                       float* partials, float* partials_w, GridSync gs,
                       // WG only: conv2 weight gradient of the same image
                       const __grid_constant__ CUtensorMap tm_x2, const __grid_constant__ CUtensorMap tm_dy2, float* __restrict__ wpart,
-                      const float* __restrict__ dysum2, float* dw2, float* db2) {
+                      const float* __restrict__ dysum2, float* dw2, float* db2, const __grid_constant__ SgdRider sr) {
   constexpr int NAMED = WG ? kL1Threads : 0;
   extern __shared__ __align__(16) uint8_t dsm_raw[];
   // WG: everything is placed relative to a 1024-aligned base (the swizzled TMA tiles need it)
@@ -469,7 +482,17 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
     partials[static_cast<size_t>(n) * 32 + tid] = s;
   }
   trace(1, 1);
-  bar.sync<NAMED>(gs);
+  bar.arrive<NAMED>(gs);
+  const float sgd_lr = sr.on ? (sr.h.lr_dev ? __ldg(sr.h.lr_dev) : sr.h.lr) : 0.f;
+  if (sr.on) {
+    // in the barrier's shadow: the optimizer step of the parameters whose gradients were complete before this kernel started
+    // (classifier, bn2) — nothing in this kernel reads them
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      for (int i = n * kL1Threads + tid; i < sr.n_prev[t]; i += B * kL1Threads)
+        sgd_apply(sr.p[6 + t] + i, __ldg(sr.g_prev[t] + i), sr.m[6 + t] ? sr.m[6 + t] + i : nullptr, sr.h, sgd_lr);
+  }
+  bar.wait<NAMED>(gs);
   trace(1, 2);
   fold_rows_wide<32, kL1Threads, NAMED>(partials, B, s_tmp, s_tot);  // [0..16) Σdz, [16..32) Σdz·x̂
   trace(1, 3);
@@ -594,9 +617,20 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) {
-      if (tap < 25) dw[co * 25 + tap] = s;
-      else if (db) db[co] = s;
+      if (tap < 25) {
+        dw[co * 25 + tap] = s;
+        if (sr.on) sgd_apply(sr.p[0] + co * 25 + tap, s, sr.m[0] ? sr.m[0] + co * 25 + tap : nullptr, sr.h, sgd_lr);
+      } else if (db) {
+        db[co] = s;
+        if (sr.on && sr.p[1]) sgd_apply(sr.p[1] + co, s, sr.m[1] ? sr.m[1] + co : nullptr, sr.h, sgd_lr);
+      }
     }
+  }
+  if (sr.on && n == 0 && tid < 16) {
+    // BatchNorm-1 affine parameters: their gradients are the totals this CTA folded after the first barrier.  Every CTA read
+    // gamma / beta before that barrier, so updating them here (after the second one) races with nobody.
+    if (sr.p[3]) sgd_apply(sr.p[3] + tid, s_tot[tid], sr.m[3] ? sr.m[3] + tid : nullptr, sr.h, sgd_lr);
+    if (sr.p[2]) sgd_apply(sr.p[2] + tid, s_tot[16 + tid], sr.m[2] ? sr.m[2] + tid : nullptr, sr.h, sgd_lr);
   }
   if constexpr (WG) {
     // conv2 weight gradient: CTA n folds outputs n, n + B, … of the 400 (tap, ci) rows × 32 co (+ row 400: the bias, from the
@@ -647,8 +681,14 @@ convnet_l1_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ y,
           float tot = 0.f;
 #pragma unroll 5
           for (int wi = 0; wi < kL1Warps; ++wi) tot += s_f[(u * kL1Warps + wi) * 32 + lane];
-          if (i < 400) dw2[(lane * 16 + (i & 15)) * 25 + (i >> 4)] = tot;
-          else if (db2) db2[lane] = tot;
+          if (i < 400) {
+            const int e = (lane * 16 + (i & 15)) * 25 + (i >> 4);
+            dw2[e] = tot;
+            if (sr.on) sgd_apply(sr.p[4] + e, tot, sr.m[4] ? sr.m[4] + e : nullptr, sr.h, sgd_lr);
+          } else if (db2) {
+            db2[lane] = tot;
+            if (sr.on && sr.p[5]) sgd_apply(sr.p[5] + lane, tot, sr.m[5] ? sr.m[5] + lane : nullptr, sr.h, sgd_lr);
+          }
         }
       }
     }
@@ -1660,16 +1700,17 @@ void launch_convnet_l1_bwd(const float* dp, const float* y, const float* x, cons
   CUtensorMap none{};
   launch_coop(convnet_l1_bwd_kernel<false>, B, kL1Threads, static_cast<size_t>(kL1BwdSmem), st, "convnet_l1_bwd", dp, y, x, saved, gamma, beta, dgamma,
               dbeta, dw, db, partials, partials_w, gs, none, none, static_cast<float*>(nullptr), static_cast<const float*>(nullptr),
-              static_cast<float*>(nullptr), static_cast<float*>(nullptr));
+              static_cast<float*>(nullptr), static_cast<float*>(nullptr), SgdRider{});
 }
 
 void launch_convnet_l1_bwd_wgrad(const float* dp, const float* y, const float* x, const float* saved, const float* gamma, const float* beta,
                                  float* dgamma, float* dbeta, float* dw, float* db, const float* dy2_pad, const float* x2_pad, const float* dysum2,
-                                 float* dw2, float* db2, int B, float* partials, float* partials_w, float* wpart, GridSync gs, cudaStream_t st) {
+                                 float* dw2, float* db2, int B, float* partials, float* partials_w, float* wpart, GridSync gs, cudaStream_t st,
+                                 SgdRider sgd) {
   CUtensorMap tm_x, tm_dy;
   make_wgrad_win_tmaps(x2_pad, dy2_pad, B, &tm_x, &tm_dy);
   launch_coop(convnet_l1_bwd_kernel<true>, B, L1WgCfg::kThreads, L1WgCfg::kSmem, st, "convnet_l1_bwd_wgrad", dp, y, x, saved, gamma, beta, dgamma,
-              dbeta, dw, db, partials, partials_w, gs, tm_x, tm_dy, wpart, dysum2, dw2, db2);
+              dbeta, dw, db, partials, partials_w, gs, tm_x, tm_dy, wpart, dysum2, dw2, db2, sgd);
 }
 
 void launch_convnet_l2_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float* y, float* out,

@@ -24,12 +24,26 @@ void launch_convnet_l1_fwd(const float* x, const float* w, const float* bias, co
 void launch_convnet_l1_bwd(const float* dp, const float* y, const float* x, const float* saved, const float* gamma, const float* beta,
                            float* dgamma, float* dbeta, float* dw, float* db, int B, float* partials, float* partials_w, GridSync gs,
                            cudaStream_t st);
+// Optional rider of the last backward kernel: the SGD update of every parameter of the model.  Parameters 0..5 (conv1.w, conv1.b,
+// bn1.w, bn1.b, conv2.w, conv2.b) get their gradient inside this kernel — the thread that writes the folded gradient element applies
+// the update with the value still in its register; parameters 6..9 (gradients complete before the launch: classifier, bn2) are updated
+// in the shadow of the kernel's first grid barrier.  Same arithmetic as sgd_multi_kernel.
+struct SgdRider {
+  int on = 0;
+  float* p[10] = {};
+  float* m[10] = {};           // momentum buffers (nullptr: momentum == 0)
+  const float* g_prev[4] = {}; // gradients of parameters 6..9
+  int n_prev[4] = {};
+  SgdHyper h{};
+};
+
 // Layer-1 backward with the conv2 weight gradient of the same image running on the tensor cores next to it (two extra warps):
 // dy2_pad [B,18,18,32] / x2_pad [B,18,18,16] frames and dysum2 [B,32] from layer-2 backward → dw2 [32,16,5,5], db2 [32].
 // wpart: B·512·32 floats of scratch, disjoint from partials / partials_w.
 void launch_convnet_l1_bwd_wgrad(const float* dp, const float* y, const float* x, const float* saved, const float* gamma, const float* beta,
                                  float* dgamma, float* dbeta, float* dw, float* db, const float* dy2_pad, const float* x2_pad, const float* dysum2,
-                                 float* dw2, float* db2, int B, float* partials, float* partials_w, float* wpart, GridSync gs, cudaStream_t st);
+                                 float* dw2, float* db2, int B, float* partials, float* partials_w, float* wpart, GridSync gs, cudaStream_t st,
+                                 SgdRider sgd = SgdRider{});
 // x [B,18,18,16] frame → y [B,14,14,32], out [B,32,7,7] NCHW, saved [64]; logits [B,ncls] = fc(out) when logits != nullptr.
 // partials: B·64 floats.
 void launch_convnet_l2_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float* y, float* out,

@@ -61,8 +61,8 @@ class BatchStager {
   double scale_;
   int device_;
   std::vector<Slot> ring_;
-  std::vector<std::thread> workers_;   // worker w stages batches w, w + W, ... (PDT_LOADER_WORKERS, default 3)
-  int nworkers_ = 3;
+  std::vector<std::thread> workers_;   // worker w stages batches w, w + W, ... (PDT_LOADER_WORKERS, default 1)
+  int nworkers_ = 1;
   std::mutex mu_;
   std::condition_variable cv_;
   int64_t produce_ = 0, consume_ = 0, reap_ = 0, epoch_ = 0;

@@ -52,6 +52,8 @@ class GraphedTrainStep:
         if fuse_optimizer and hasattr(optimizer, "fuse_with_ddp") and hasattr(model, "enable_optimizer_fusion"):
             optimizer.fuse_with_ddp(model)
             warmup = max(warmup, 4)  # bucket rebuild after step 1, fusion switches on after step 2
+        if fuse_optimizer and hasattr(optimizer, "ride_on_backward"):
+            optimizer.ride_on_backward(model)   # one GPU: the update rides on the model's last backward kernel (no-op when it cannot)
         self._capture(warmup)
         self.fused_optimizer = bool(getattr(optimizer, "_fused_active", False))
 

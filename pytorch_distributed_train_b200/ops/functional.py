@@ -162,6 +162,11 @@ class upcoming_targets:
         return False
 
 
+# The optimizer whose update rides on the last backward kernel (optim.SGD.ride_on_backward, armed by engine.GraphedTrainStep when the
+# gradient reduction does not already carry it, i.e. on one GPU): {"params": [...10 parameters...], "args": callable -> hyper-parameters}
+_sgd_rider: Optional[dict] = None
+
+
 def _wgrad_rides_on_layer1() -> bool:
     """conv2's weight gradient runs on the tensor cores *inside* the layer-1 backward kernel (two extra warps per CTA)
     instead of as a kernel of its own between the two layer kernels.  PDT_WGRAD_MERGED=0 restores the separate launch."""
@@ -205,13 +210,25 @@ class _FusedLayer1(torch.autograd.Function):
         db = _grad_dst(b_p, b_p) if b_p is not None else None
         dg = _grad_dst(g_p, gamma)
         dbe = _grad_dst(be_p, beta)
+        fresh = all(q is None or q.grad is None for q in (w_p, b_p, g_p, be_p, w2_p, b2_p))
         pending = ctx.link.pop("wgrad", None) if ctx.link is not None else None
         dw2 = db2 = None
         if pending is not None:
             dy2, p1, dysum2 = pending
             dw2 = _grad_dst(w2_p, w2_p)
             db2 = _grad_dst(b2_p, b2_p) if b2_p is not None else None
-            _C.convnet_l1_bwd_wgrad(dp.contiguous(), y, x, saved, gamma, beta, dg, dbe, dw, db, dy2, p1, dysum2, dw2, db2)
+            sgd = None
+            prev = ctx.link.pop("prev", None)
+            rider = _sgd_rider
+            if rider is not None and prev is not None and prev[4] and fresh:
+                mine = [w_p, b_p, g_p, be_p, w2_p, b2_p] + [q for q, _ in prev[:4]]
+                if len(mine) == len(rider["params"]) and all(a is b for a, b in zip(mine, rider["params"])):
+                    # autograd has accumulated layer 2's gradients by now (AccumulateGrad runs as soon as its input is ready): they
+                    # must be exactly the tensors layer 2's kernel wrote
+                    grads = [q.grad if q is not None else None for q, _ in prev[:4]]
+                    if all((g is None and ptr == 0) or (g is not None and g.data_ptr() == ptr) for g, (_, ptr) in zip(grads, prev[:4])):
+                        sgd = rider["args"](grads)   # None when the optimizer cannot ride this iteration
+            _C.convnet_l1_bwd_wgrad(dp.contiguous(), y, x, saved, gamma, beta, dg, dbe, dw, db, dy2, p1, dysum2, dw2, db2, sgd)
         else:
             _C.convnet_l1_bwd(dp.contiguous(), y, x, saved, gamma, beta, dg, dbe, dw, db)
         return None, dw, db, dg, dbe, None, None, None, None, None, dw2, db2, None, None
@@ -247,6 +264,8 @@ class _FusedLayer2(torch.autograd.Function):
         dg = _grad_dst(g_p, ctx.saved_tensors[3])
         dbe = _grad_dst(be_p, ctx.saved_tensors[4])
         dfcw = dfcb = None
+        if ctx.link is not None:   # do the gradients written here become `.grad` as they are (nothing to accumulate into)?
+            ctx.link["prev_fresh"] = ctx.fc_rides and all(q is None or q.grad is None for q in (fcw_p, fcb_p, g_p, be_p))
         if ctx.fc_rides:
             p1, y, saved, gamma, beta, w, out, fcw = ctx.saved_tensors
             if dout is not None:
@@ -261,6 +280,10 @@ class _FusedLayer2(torch.autograd.Function):
         if ctx.link is not None and ctx.needs_input_grad[0]:
             # layer 1's backward kernel computes (and layer 1's node returns) conv2's weight / bias gradient
             ctx.link["wgrad"] = (dy, p1, dysum)
+            # for the optimizer rider of layer 1's kernel: WHERE these gradients were written — addresses, not tensors (an extra
+            # reference would make autograd's AccumulateGrad clone the gradient instead of adopting the bucket view)
+            ctx.link["prev"] = ((fcw_p, dfcw.data_ptr() if dfcw is not None else 0), (fcb_p, dfcb.data_ptr() if dfcb is not None else 0),
+                                (g_p, dg.data_ptr()), (be_p, dbe.data_ptr()), ctx.link.pop("prev_fresh", False))
             return dp1, None, None, dg, dbe, None, None, None, None, None, dfcw, dfcb, None, None, None
         dw = _grad_dst(w_p, w)
         db = _grad_dst(b_p, b_p) if b_p is not None else None

@@ -63,6 +63,74 @@ class SGD(torch.optim.Optimizer):
                 ent[0].fill_(float(group["lr"]))
                 ent[1] = float(group["lr"])
 
+    # ---- single GPU: the update rides on the model's last backward kernel ---------------------------------
+    def ride_on_backward(self, model) -> bool:
+        """Let the reference ConvNet's last backward kernel apply this optimizer's update (csrc/cuda/fused_convnet.cu: SgdRider): the
+        thread that writes a folded gradient element updates the parameter with the value still in its register; the parameters whose
+        gradients are complete earlier are updated in the shadow of that kernel's first grid barrier.  ``step()`` then has only
+        bookkeeping left.  Used by ``engine.GraphedTrainStep`` when the gradient reduction does not already carry the update (one GPU).
+
+        Same contract as :meth:`fuse_with_ddp`: between ``backward()`` and ``step()`` the parameters are already updated.  Returns
+        False (and changes nothing) when the model / optimizer combination does not qualify."""
+        import os
+
+        from .. import distributed as dist
+        from ..ops import functional as OF
+
+        if os.environ.get("PDT_SGD_RIDER", "1") == "0":
+            return False
+        group_ = getattr(model, "process_group", None)
+        world = group_.size() if group_ is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        if world > 1:
+            return False   # the gradients still have to be averaged: the reduce kernels carry the update (fuse_with_ddp)
+        inner = getattr(model, "module", model)
+        try:
+            c1, b1, c2, b2, fc = inner.layer1[0], inner.layer1[1], inner.layer2[0], inner.layer2[1], inner.fc
+            params = [c1.weight, c1.bias, b1.weight, b1.bias, c2.weight, c2.bias, fc.weight, fc.bias, b2.weight, b2.bias]
+        except (AttributeError, IndexError, TypeError):
+            return False
+        if len(self.param_groups) != 1 or any(q is None for q in params):
+            return False
+        group = self.param_groups[0]
+        mine = group["params"]
+        if len(mine) != len(params) or {id(q) for q in mine} != {id(q) for q in params}:
+            return False
+        if not all(q.is_cuda and q.dtype == torch.float32 and q.is_contiguous() for q in params):
+            return False
+        self._rider_params = params
+        self._rode = False
+
+        def args(prev_grads):
+            if getattr(self, "_fused_active", False):   # the reduce kernels carry the update (N >= 2)
+                return None
+            g = self.param_groups[0]
+            bufs = []
+            first = False
+            if g["momentum"] != 0:
+                states = [self.state[q] for q in params]
+                have = [st.get("momentum_buffer") is not None for st in states]
+                if any(have) and not all(have):
+                    return None   # mixed first-step state: leave this iteration to step()
+                first = not any(have)
+                for q, st in zip(params, states):
+                    if st.get("momentum_buffer") is None:
+                        st["momentum_buffer"] = torch.zeros_like(q, memory_format=torch.contiguous_format)
+                    bufs.append(st["momentum_buffer"])
+            self._rode = True
+            return (params, list(prev_grads), bufs, float(g["lr"]), self._lr_tensor(0, g, params[0].device), float(g["momentum"]),
+                    float(g["dampening"]), float(g["weight_decay"]), bool(g["nesterov"]), bool(g["maximize"]), first)
+
+        OF._sgd_rider = {"params": params, "args": args, "owner": self}
+        return True
+
+    def stop_riding(self) -> None:
+        """Undo :meth:`ride_on_backward`."""
+        from ..ops import functional as OF
+
+        if OF._sgd_rider is not None and OF._sgd_rider.get("owner") is self:
+            OF._sgd_rider = None
+        self._rode = False
+
     # ---- DDP fusion: the update rides on the gradient reduction ----------------------------------------
     def fuse_with_ddp(self, ddp) -> "SGD":
         """Fuse this optimizer into DDP's gradient reduction.
@@ -172,6 +240,9 @@ class SGD(torch.optim.Optimizer):
                 loss = closure()
         from .. import ops
 
+        if getattr(self, "_rode", False):
+            self._rode = False   # the last backward kernel applied this step's update (ride_on_backward)
+            return loss
         if self._ddp is not None:
             if self._fused_step():
                 return loss

@@ -457,3 +457,40 @@ def test_cross_entropy_folded_into_the_forward_kernel(B, late):
     with OF.upcoming_targets(t):
         out = a(x)
     assert abs(crit(out, t2).item() - F.cross_entropy(out.detach().double(), t2).item()) < 1e-5
+
+
+@pytest.mark.parametrize("momentum,nesterov,wd", [(0.0, False, 0.0), (0.9, True, 1e-3)])
+def test_optimizer_rides_on_the_last_backward_kernel(momentum, nesterov, wd):
+    """optim.SGD.ride_on_backward: the layer-1 backward kernel applies the update of all ten parameters (fused_convnet.cu: SgdRider);
+    parameters and momentum buffers must follow the separate multi-tensor SGD kernel."""
+    torch.manual_seed(4)
+    a = pdt.models.ConvNet(fused=True).to(dev())
+    b = pdt.models.ConvNet(fused=True).to(dev())
+    b.load_state_dict(a.state_dict())
+    oa = pdt.optim.SGD(a.parameters(), 0.05, momentum=momentum, nesterov=nesterov, weight_decay=wd)
+    ob = pdt.optim.SGD(b.parameters(), 0.05, momentum=momentum, nesterov=nesterov, weight_decay=wd)
+    crit = pdt.nn.CrossEntropyLoss()
+    assert oa.ride_on_backward(a)
+    try:
+        for s in range(4):
+            x = torch.rand(100, 1, 28, 28, device=dev(), generator=torch.Generator(device=dev()).manual_seed(s))
+            t = torch.randint(0, 10, (100,), device=dev(), generator=torch.Generator(device=dev()).manual_seed(50 + s))
+            before = _C.kernel_launch_count()
+            oa.zero_grad()
+            crit(a(x), t).backward()
+            assert oa._rode, "the backward kernel should have applied the update"
+            oa.step()
+            riding = _C.kernel_launch_count() - before
+            before = _C.kernel_launch_count()
+            ob.zero_grad()
+            crit(b(x), t).backward()
+            ob.step()
+            separate = _C.kernel_launch_count() - before
+            assert riding < separate, (riding, separate)
+            for (n1, p1), (_, p2) in zip(a.named_parameters(), b.named_parameters()):
+                assert torch.allclose(p1, p2, atol=1e-6, rtol=1e-5), (s, n1, (p1 - p2).abs().max().item())
+        if momentum:
+            for p1, p2 in zip(a.parameters(), b.parameters()):
+                assert torch.allclose(oa.state[p1]["momentum_buffer"], ob.state[p2]["momentum_buffer"], atol=1e-6, rtol=1e-5)
+    finally:
+        oa.stop_riding()
