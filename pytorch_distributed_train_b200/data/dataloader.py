@@ -207,7 +207,8 @@ class DataLoader:
             dev = torch.cuda.current_device() if pin else -1
             self._native = _native_mod().BatchStager(src["data"], src["targets"], list(src["sample_shape"]), int(self.batch_size),
                                                      bool(self.drop_last), float(src["scale"]), max(8, self.prefetch + 4), pin, dev)
-        order = torch.as_tensor(list(iter(self.sampler)), dtype=torch.int64)   # the sampler decides the epoch's order, once
+        # the sampler decides the epoch's order, once (tensor fast path: no 60,000-element Python list per epoch)
+        order = self.sampler.indices_tensor() if hasattr(self.sampler, "indices_tensor") else torch.as_tensor(list(iter(self.sampler)), dtype=torch.int64)
         self._native.start(order)
         while True:
             item = self._native.next()

@@ -118,6 +118,32 @@ class DistributedSampler(Sampler):
         assert len(shard) == self.num_samples
         return iter(shard)
 
+    def indices_tensor(self) -> torch.Tensor:
+        """This rank's indices of the current epoch as an int64 tensor — the same sequence ``__iter__`` yields, built with tensor ops
+        only (60,000 Python ints cost ~2 ms per epoch start, 25 training steps of the reference ConvNet) and cached while
+        (seed, epoch) do not change: the reference never calls ``set_epoch``, so every epoch after the first restarts for free."""
+        n = len(self.dataset)
+        key = (self.seed, self.epoch, self.shuffle, n, self.num_replicas, self.rank, self.drop_last)
+        if getattr(self, "_order_key", None) == key:
+            return self._order_cache
+        if self.shuffle:
+            g = torch.Generator()
+            g.manual_seed(self.seed + self.epoch)
+            order = torch.randperm(n, generator=g)
+        else:
+            order = torch.arange(n, dtype=torch.int64)
+        if not self.drop_last:
+            pad = self.total_size - n
+            if pad > 0:
+                reps = math.ceil(pad / max(n, 1))
+                order = torch.cat([order, order.repeat(reps)[:pad]])
+        else:
+            order = order[: self.total_size]
+        shard = order[self.rank: self.total_size: self.num_replicas].contiguous()
+        assert shard.numel() == self.num_samples
+        self._order_key, self._order_cache = key, shard
+        return shard
+
     def __len__(self) -> int:
         return self.num_samples
 

@@ -66,3 +66,14 @@ def test_invalid_rank():
 def test_batch_sampler():
     assert list(BatchSampler(range(7), 3, False)) == [[0, 1, 2], [3, 4, 5], [6]]
     assert list(BatchSampler(range(7), 3, True)) == [[0, 1, 2], [3, 4, 5]]
+
+
+@pytest.mark.parametrize("n,world,shuffle,drop_last", [(103, 4, True, False), (103, 4, True, True), (10, 4, False, False), (3, 8, True, False)])
+def test_indices_tensor_is_the_iterated_sequence(n, world, shuffle, drop_last):
+    ds = list(range(n))
+    for rank in range(world):
+        s = DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=shuffle, drop_last=drop_last, seed=3)
+        for epoch in (0, 1):
+            s.set_epoch(epoch)
+            assert s.indices_tensor().tolist() == list(iter(s))
+            assert s.indices_tensor() is s.indices_tensor()   # cached until the epoch changes

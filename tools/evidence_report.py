@@ -32,8 +32,8 @@ WORK = {
                               "classifier bwd + pool/ReLU/BN2 bwd + conv2 dgrad (tcgen05)"),
     "convnet_l1_bwd_kernel": (p1f + y1 + x0 + dy2f + p1f, 2 * B * 784 * 16 * 25 + 2 * B * 196 * 32 * 400,
                               "pool/ReLU/BN1 bwd + conv1 wgrad (mma.sync) + conv2 wgrad (tcgen05, TMA)"),
-    "conv5x5_wgrad_win_kernel": (dy2f + p1f, 2 * B * 196 * 32 * 400, "conv2 wgrad (tcgen05, TMA) as its own kernel"),
-    "linear_bwd_kernel": (2 * p2 + 2 * 10 * 1568 * f, 4 * B * 10 * 1568, "fc dX, dW, db"),
+    "conv5x5_wgrad_win_kernel": (dy2f + p1f, 2 * B * 196 * 32 * 400, "(stand-alone variant, PDT_WGRAD_MERGED=0) conv2 wgrad, TMA-materialised tap pairs"),
+    "linear_bwd_kernel": (2 * p2 + 2 * 10 * 1568 * f, 4 * B * 10 * 1568, "(stand-alone variant, PDT_FC_MERGED=0) fc dX, dW, db"),
 }
 METRICS = [
     ("gpu__time_duration.sum", "duration under ncu"),
@@ -143,8 +143,9 @@ def ncu_md():
         "Every kernel is 10-40× above its roofline: the step is bound by *dependent phases*, not by bandwidth or FLOPs.  Each cooperative",
         "kernel is a chain of short phases (load, reduce, grid barrier ≈ 1.8 µs, fold, MMA, epilogue) in which one CTA per image keeps",
         "≤ 25 warps on an SM; the stall tables above show it (CTA-barrier and long-scoreboard waits dominate, achieved occupancy 10-40 %).",
-        "That is why the optimisation work of this round went into removing phases (launches 20 → 7, grid barriers merged, the conv2 weight",
-        "gradient hidden behind layer-1 backward) rather than into the inner loops; `fused_trace_*.log` has the per-phase timelines.", ""]
+        "That is why the optimisation work of this round went into removing phases (launches 20 → 3, grid barriers merged and their shadows",
+        "filled, the conv2 weight gradient hidden behind layer-1 backward, the classifier / loss / optimizer riding on the layer kernels)",
+        "rather than into the inner loops; `fused_trace.log` has the per-phase timelines (eager and inside the replayed graph).", ""]
     open(os.path.join(OUT, "ncu_fused.md"), "w").write("\n".join(out))
 
 
