@@ -49,7 +49,11 @@ BatchStager::BatchStager(at::Tensor data, at::Tensor targets, std::vector<int64_
   for (auto d : sample_shape_) want *= d;
   TORCH_CHECK(want == row_elems_, "BatchStager: sample_shape does not match the dataset rows");
   ring_.resize(static_cast<size_t>(depth_));
-  for (auto& s : ring_) alloc_slot(s);
+  int64_t slot_index = 0;
+  for (auto& s : ring_) {
+    alloc_slot(s);
+    s.seq = slot_index++;   // slot i takes batches i, i + depth, i + 2·depth, … (numbered across epochs)
+  }
 }
 
 BatchStager::~BatchStager() { stop_worker(); }
@@ -82,24 +86,17 @@ void BatchStager::start(at::Tensor indices) {
   indices_ = indices.contiguous();
   const int64_t n = indices_.numel();
   nbatches_ = drop_last_ ? n / batch_ : (n + batch_ - 1) / batch_;
-  produce_ = consume_ = reap_ = 0;
+  // Batches are numbered across epochs (consume_ never resets): the slots handed back in the previous epoch whose CUDA events are
+  // still pending stay in the ring's normal reaping order instead of being waited for here — with a 75-step epoch (8 ranks) that
+  // wait (the device is ~15 steps behind the host) stalled the training thread for 3 ms per epoch (profiles/r2/e2e_stalls.md).
+  base_ = consume_;
+  produce_ = 0;
   st_fill_us_ = st_wait_free_us_ = st_next_wait_us_ = st_ready_sum_ = st_alloc_us_ = 0;
   st_allocs_ = 0;
   st_next_calls_ = 0;
-  last_handed_ = prev_handed_ = -1;
   ++epoch_;
-  int64_t slot_index = 0;
   for (auto& s : ring_) {
-    s.seq = slot_index++;
-    if (s.state == 2) s.state = 0;   // a batch of the abandoned epoch may still be in user hands: the retention check covers it
-    if (s.state == 1) s.state = 0;
-    if (s.state == 3) {              // handed back in the previous epoch, its event still pending: wait for it here, once
-#if PDT_WITH_CUDA
-      if (s.event) static_cast<at::cuda::CUDAEvent*>(s.event.get())->synchronize();
-#endif
-      s.event.reset();
-      s.state = 0;
-    }
+    if (s.state == 1) s.state = 0;   // staged for the abandoned epoch: its number (seq) now belongs to a batch of this epoch
   }
   running_ = true;
   if (const char* e = std::getenv("PDT_LOADER_WORKERS")) nworkers_ = std::max(1, std::atoi(e));
@@ -115,7 +112,7 @@ void BatchStager::worker(int w) {
   const int64_t* idx = indices_.data_ptr<int64_t>();
   const int64_t N = data_.size(0);
   const size_t tsize = targets_.element_size();
-  for (int64_t b = w; b < nbatches_; b += nworkers_) {
+  for (int64_t b = base_ + w; b < base_ + nbatches_; b += nworkers_) {   // b: global batch number, b - base_: index in this epoch
     Slot& s = ring_[static_cast<size_t>(b % depth_)];
     const auto tw0 = std::chrono::steady_clock::now();
     {
@@ -132,7 +129,7 @@ void BatchStager::worker(int w) {
       fresh = true;
     }
     const auto tw1b = std::chrono::steady_clock::now();
-    const int64_t lo = b * batch_, hi = std::min(n, lo + batch_);
+    const int64_t lo = (b - base_) * batch_, hi = std::min(n, lo + batch_);
     float* out = s.images.data_ptr<float>();
     char* tout = static_cast<char*>(s.targets.data_ptr());
     const char* tin = static_cast<const char*>(targets_.data_ptr());
@@ -236,7 +233,7 @@ bool BatchStager::next(at::Tensor* images, at::Tensor* targets) {
   }
   prev_handed_ = last_handed_;
   last_handed_ = -1;
-  if (consume_ >= nbatches_) return false;
+  if (consume_ >= base_ + nbatches_) return false;
   Slot& s = ring_[static_cast<size_t>(consume_ % depth_)];
   {
     std::unique_lock<std::mutex> lk(mu_);

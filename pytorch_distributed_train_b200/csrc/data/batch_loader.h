@@ -65,7 +65,7 @@ class BatchStager {
   int nworkers_ = 1;
   std::mutex mu_;
   std::condition_variable cv_;
-  int64_t produce_ = 0, consume_ = 0, reap_ = 0, epoch_ = 0;
+  int64_t produce_ = 0, consume_ = 0, reap_ = 0, epoch_ = 0, base_ = 0;   // consume_/reap_/base_: global batch numbers
   double st_fill_us_ = 0, st_wait_free_us_ = 0, st_next_wait_us_ = 0, st_ready_sum_ = 0;
   int64_t st_next_calls_ = 0, st_allocs_ = 0;
   double st_alloc_us_ = 0;

@@ -128,3 +128,29 @@ def test_native_batch_stager_matches_python_loader_and_never_overwrites_a_retain
     assert all(torch.allclose(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(kept, ref))
     # a transform forces the Python path
     assert pdt.data.MNIST(str(tmp_path), train=True, transform=lambda t: t).native_source() is None
+
+
+def test_native_stager_across_epochs_and_abandoned_epochs():
+    """Batches are numbered across epochs inside the stager (slots waiting for CUDA events survive an epoch boundary): every epoch —
+    full, shorter than the ring, or abandoned half-way — must still deliver exactly the sampler's order."""
+    import torch
+
+    from pytorch_distributed_train_b200.data import DataLoader, DistributedSampler, SyntheticMNIST
+
+    for n, batch in ((1000, 100), (5000, 100), (730, 64)):
+        ds = SyntheticMNIST(n, seed=1)
+        sampler = DistributedSampler(ds, num_replicas=2, rank=1, shuffle=True, seed=5)
+        loader = DataLoader(ds, batch_size=batch, sampler=sampler, prefetch=4)
+        assert loader._native_src is not None
+        for epoch in range(5):
+            sampler.set_epoch(epoch)
+            want = sampler.indices_tensor()
+            got = []
+            for k, (xb, yb) in enumerate(loader):
+                idx = want[k * batch:(k + 1) * batch]
+                assert torch.equal(xb, ds.data.index_select(0, idx)) and torch.equal(yb, ds.targets.index_select(0, idx)), (n, epoch, k)
+                got.append(xb.shape[0])
+                if epoch == 2 and k == 2:
+                    break   # abandon this epoch: the batches staged ahead must not leak into the next one
+            if epoch != 2:
+                assert sum(got) == want.numel()

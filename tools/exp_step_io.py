@@ -115,5 +115,9 @@ run("ring of 12 fixed pinned batches", fixed_ring)
 run("one fixed pinned batch", fixed)
 run("loader (native stager, pinned)", batches)
 run("loader, no loss reads", batches, read_every=0)
+# 20-batch epochs: an epoch boundary every 20 steps (8 ranks on MNIST: every 75)
+ds_small = pdt.data.SyntheticMNIST(2000)
+loader = pdt.DataLoader(ds_small, batch_size=100, pin_memory=True, sampler=pdt.DistributedSampler(ds_small, 1, 0), prefetch=8)
+run("loader, 20-batch epochs", batches)
 os.environ["X"] = "1"
 pdt.destroy_process_group()
