@@ -10,7 +10,8 @@ StepPipeline::StepPipeline(int device, int num_sets, at::ScalarType loss_dtype)
     : device_(device),
       copy_(c10::cuda::getStreamFromPool(/*isHighPriority=*/false, device)),
       d2h_(c10::cuda::getStreamFromPool(/*isHighPriority=*/false, device)),
-      after_(cudaEventDisableTiming) {
+      after_(cudaEventDisableTiming),
+      src_ready_(cudaEventDisableTiming) {
   TORCH_CHECK(num_sets >= 1, "StepPipeline: at least one input set");
   c10::cuda::CUDAGuard g(device_);
   auto cur = c10::cuda::getCurrentCUDAStream(device_);
@@ -34,8 +35,8 @@ void StepPipeline::stage_inputs(int i, const std::vector<at::Tensor>& dst, const
       bool any_dev = false;
       for (const auto& t : src) any_dev = any_dev || t.is_cuda();
       if (any_dev) {   // device-resident sources may still be in flight on the caller's stream
-        after_.record(cur);
-        after_.block(copy_);
+        src_ready_.record(cur);
+        src_ready_.block(copy_);
       }
     }
     {

@@ -39,7 +39,7 @@ class StepPipeline {
   std::vector<std::unique_ptr<at::cuda::CUDAEvent>> ready_, done_;
   std::vector<at::cuda::CUDAEvent*> loss_read_;   // per set: slot event of the last loss copy (nullptr: none pending)
   std::vector<std::unique_ptr<at::cuda::CUDAEvent>> slot_ev_;
-  at::cuda::CUDAEvent after_;
+  at::cuda::CUDAEvent after_, src_ready_;   // after_: behind the replay (loss hand-off); src_ready_: device-resident sources
   at::Tensor host_;   // pinned [kRing]
   int64_t gen_ = 0;
 };
