@@ -70,7 +70,8 @@ class GraphedTrainStep:
         if self._seed is None or self._seed.shape != loss.shape or self._seed.dtype != loss.dtype:
             self._seed = torch.ones_like(loss)
             self._seed._pdt_unit_seed = True   # lets ops that pre-compute their unit-gradient backward skip the scaling kernel
-        loss.backward(self._seed)
+        with OF.sgd_rider_enabled():   # an optimizer armed with ride_on_backward may apply its update inside this backward pass
+            loss.backward(self._seed)
         self.optimizer.step()
         return loss
 

@@ -165,6 +165,23 @@ class upcoming_targets:
 # The optimizer whose update rides on the last backward kernel (optim.SGD.ride_on_backward, armed by engine.GraphedTrainStep when the
 # gradient reduction does not already carry it, i.e. on one GPU): {"params": [...10 parameters...], "args": callable -> hyper-parameters}
 _sgd_rider: Optional[dict] = None
+_sgd_rider_enabled = False
+
+
+class sgd_rider_enabled:
+    """The armed optimizer may ride on backward passes started inside this context only (engine.GraphedTrainStep wraps its step in it):
+    a backward pass anywhere else — gradient inspection, clipping experiments, an eager loop — never updates parameters behind the
+    caller's back."""
+
+    def __enter__(self):
+        global _sgd_rider_enabled
+        self.prev, _sgd_rider_enabled = _sgd_rider_enabled, True
+        return self
+
+    def __exit__(self, *exc):
+        global _sgd_rider_enabled
+        _sgd_rider_enabled = self.prev
+        return False
 
 
 def _wgrad_rides_on_layer1() -> bool:
@@ -219,7 +236,7 @@ class _FusedLayer1(torch.autograd.Function):
             db2 = _grad_dst(b2_p, b2_p) if b2_p is not None else None
             sgd = None
             prev = ctx.link.pop("prev", None)
-            rider = _sgd_rider
+            rider = _sgd_rider if _sgd_rider_enabled else None
             if rider is not None and prev is not None and prev[4] and fresh:
                 mine = [w_p, b_p, g_p, be_p, w2_p, b2_p] + [q for q, _ in prev[:4]]
                 if len(mine) == len(rider["params"]) and all(a is b for a, b in zip(mine, rider["params"])):

@@ -477,7 +477,15 @@ def test_optimizer_rides_on_the_last_backward_kernel(momentum, nesterov, wd):
             t = torch.randint(0, 10, (100,), device=dev(), generator=torch.Generator(device=dev()).manual_seed(50 + s))
             before = _C.kernel_launch_count()
             oa.zero_grad()
-            crit(a(x), t).backward()
+            la = crit(a(x), t)
+            if s == 0:   # outside the engine's context an armed optimizer must not touch the parameters
+                la.backward(retain_graph=False)
+                assert not oa._rode
+                oa.zero_grad()
+                la = crit(a(x), t)
+            from pytorch_distributed_train_b200.ops import functional as OF
+            with OF.sgd_rider_enabled():
+                la.backward()
             assert oa._rode, "the backward kernel should have applied the update"
             oa.step()
             riding = _C.kernel_launch_count() - before
