@@ -482,6 +482,7 @@ def test_optimizer_rides_on_the_last_backward_kernel(momentum, nesterov, wd):
                 la.backward(retain_graph=False)
                 assert not oa._rode
                 oa.zero_grad()
+                before = _C.kernel_launch_count()
                 la = crit(a(x), t)
             from pytorch_distributed_train_b200.ops import functional as OF
             with OF.sgd_rider_enabled():
