@@ -7,7 +7,7 @@ GPU → init_process_group over TCP → seed → model → optional SyncBN → D
 
 Extra flags cover what the reference hard-codes: ``--init-method`` (its LAN address
 ``tcp://10.9.1.2:34567`` only works on the author's network, ref: ddp_example.py:110; we default
-to loopback with a free port), ``--data synthetic|mnist``, ``--model``, ``--comm fused|nccl``,
+to loopback with a free port), ``--data synthetic|mnist``, ``--model``, ``--comm fused|nccl``, ``--algo``,
 ``--steps``, ``--graph`` (whole-step CUDA graph), ``--batch-size``, ``--lr``, ``--checkpoint`` / ``--resume``.
 """
 from __future__ import annotations
@@ -35,6 +35,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--init-method", default=None, type=str, help="rendezvous URL (default: tcp://127.0.0.1:<free port>)")
     p.add_argument("--comm", default="fused", choices=["fused", "nccl"],
                    help="GPU collectives: our fused NVLink kernels (default) or the libnccl baseline")
+    p.add_argument("--algo", default="auto", choices=["auto", "oneshot", "oneshot_mc", "twoshot", "nvls"],
+                   help="allreduce algorithm of the fused backend (auto: by message size and world size; sets PDT_AR_ALGO)")
     p.add_argument("--data", default="synthetic", choices=["synthetic", "mnist"], help="dataset (no network: synthetic default)")
     p.add_argument("--data-root", default="./data", type=str)
     p.add_argument("--model", default="convnet", choices=["convnet", "resnet18"])
@@ -62,6 +64,10 @@ def dist_train(gpu: int, args) -> None:
     use_cuda = args.backend not in ("gloo", "cpu")
     if use_cuda:
         torch.cuda.set_device(gpu)
+    if getattr(args, "algo", "auto") != "auto":
+        import os
+
+        os.environ["PDT_AR_ALGO"] = args.algo   # read by the fused backend when the process group is created
     pdt.init_process_group(backend=args.backend, init_method=args.init_method, world_size=args.world_size,
                            rank=rank, comm=args.comm)
     torch.manual_seed(0)
