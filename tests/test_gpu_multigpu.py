@@ -240,7 +240,10 @@ def _resnet(rank, world, syncbn, port):
 
 @pytest.mark.parametrize("syncbn", [False, True])
 def test_ddp_resnet18_multibucket_matches_torch(syncbn):
-    res = run_ranks(_resnet, _world(), syncbn, free_port(), backend="nccl")
+    # Two ranks whatever the box has: the comparison is about multi-bucket / chunked reduction order and the generic SyncBN
+    # kernels, which do not depend on the world size, while its conditioning does (the 4-image batch per rank and the seeds were
+    # picked and validated for two ranks, see _resnet.data); collectives at the full world size are covered by the tests above.
+    res = run_ranks(_resnet, min(_world(), 2), syncbn, free_port(), backend="nccl")
     assert len({r["psum"] for r in res}) == 1, "parameters diverged between ranks"
     assert len(res[0]["buckets"]) >= 3 and sum(res[0]["buckets"]) == 4 * 11181642
     for r in res:
