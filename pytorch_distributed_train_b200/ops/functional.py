@@ -126,6 +126,8 @@ def fused_convnet_ok(x: torch.Tensor, model) -> bool:
     c1, b1, c2, b2, fc = model.layer1[0], model.layer1[1], model.layer2[0], model.layer2[1], model.fc
     if not (x.dim() == 4 and x.shape[1:] == (1, 28, 28) and x.is_contiguous() and _C.fused_convnet_supported(x.shape[0])):
         return False
+    if x.requires_grad and torch.is_grad_enabled():
+        return False   # the fused layer-1 backward produces parameter gradients only (the reference never asks for d/d(image))
     if not (c1.weight.shape == (16, 1, 5, 5) and c2.weight.shape == (32, 16, 5, 5) and fc.weight.shape[1] == 1568 and fc.weight.shape[0] <= 64):
         return False
     for bn in (b1, b2):
