@@ -354,6 +354,10 @@ def run_ours(args):
             "details": {"comm": info.get("comm_kind"), "cuda_graph": not args.no_graph, "buckets": info.get("bucket_sizes"),
                         "grad_copies_into_bucket": info.get("copies_into_bucket"),
                         "fused_allreduce_sgd": bool(getattr(optimizer, "_fused_active", False)),
+                        "optimizer_step": ("inside the gradient-reduce kernels (allreduce + SGD per chunk; tests/test_gpu_multigpu.py::test_fused_allreduce_sgd)"
+                                           if getattr(optimizer, "_fused_active", False) else
+                                           "inside the last backward kernel (SgdRider; tests/test_gpu_kernels.py::test_optimizer_rides_on_the_last_backward_kernel)"
+                                           if (not args.no_graph and launches_per_step == 3) else "separate multi-tensor SGD kernel"),
                         "reduce_chunks": info.get("reduce_chunks"), "backward_comm_exposed_us": (info.get("avg_backward_comm_exposed_time_us") if info.get("timed_iterations") else None),  # eager iterations past the reducer's 10-step warm-up only; a replayed graph carries no marks
                         "input_staging": ("double-buffered: the copy of batch k+1 into the step's input buffers (D2D from the resident pool / H2D "
                                           "from pinned memory in e2e) runs on a copy stream while step k replays; every step still copies its "
