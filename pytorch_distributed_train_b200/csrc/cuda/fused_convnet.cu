@@ -1,20 +1,28 @@
-// Cooperative fused layer kernels for the reference ConvNet (ref: ddp_example.py:22-41) — one CTA per image.
+// Cooperative fused kernels for the reference ConvNet (ref: ddp_example.py:22-41) — one CTA per image.
 //
 // A ConvNet step is ~10 µs of work spread over dependent kernel boundaries (profiles/roofline.md): every per-op kernel
-// pays launch + ramp + drain + a grid-wide reduction.  Here a whole layer is ONE kernel: everything that belongs to an
-// image stays inside its CTA (registers / shared memory / TMEM), and the only grid-wide dependency of a layer — the
-// BatchNorm batch statistics (forward) and the Σdz, Σdz·x̂ sums (backward) — is a device-side grid barrier in the middle
-// of the kernel instead of a kernel boundary:
+// pays launch + ramp + drain + a grid-wide reduction.  Here everything that belongs to an image stays inside its CTA
+// (registers / shared memory / TMEM), and the only grid-wide dependencies — the BatchNorm batch statistics (forward), the
+// Σdz, Σdz·x̂ sums (backward) and the folds of the weight gradients — are device-side grid barriers in the middle of a
+// kernel instead of kernel boundaries.  A training step is three launches:
 //
-//   l1_fwd : conv1 5x5 (1→16) + bias  ──grid barrier (Σy, Σy²)──  BN + ReLU + MaxPool2          (ref :25-28)
-//   l2_fwd : conv2 5x5 (16→32) on tcgen05 (window trick: ONE TMA load of the zero-haloed image, the 25 taps are
-//            row-shifted UMMA descriptors into it; accumulators in TMEM)  ──barrier──  BN + ReLU + MaxPool2 + fc  (ref :30-34,40)
-//   l2_bwd : MaxPool/ReLU/BN backward  ──barrier (Σdz, Σdz·x̂)──  dy → conv2 data gradient on tcgen05
-//   l1_bwd : MaxPool/ReLU/BN backward  ──barrier──  dy → conv1 weight gradient  ──barrier──  deterministic fold
+//   convnet_fwd_kernel         conv1 5x5 (1→16) ──barrier (Σy, Σy²)── BN + ReLU + MaxPool2 written straight into conv2's
+//                              swizzled smem patch ── conv2 5x5 (16→32) on tcgen05 (the 25 taps are row-shifted UMMA descriptors
+//                              into that patch; accumulators in TMEM) ──barrier── BN + ReLU + MaxPool2 + classifier
+//                              (+ cross-entropy term and d(loss)/d(logits) when the targets are known)           (ref :25-34,40)
+//   convnet_l2_bwd_kernel<FC>  classifier backward + MaxPool/ReLU/BN backward ──barrier (Σdz, Σdz·x̂)── dy → conv2 data
+//                              gradient on tcgen05
+//   convnet_l1_bwd_kernel<WG>  MaxPool/ReLU/BN backward ──barrier── conv1 weight gradient (mma.sync) ──barrier── folds,
+//                              while one extra warp computes conv2's weight gradient on tcgen05 (MN-major window) and — on one
+//                              GPU — the threads that write the folded gradients apply the SGD update (SgdRider)
+//
+// convnet_l1_fwd_kernel / convnet_l2_fwd_kernel (one kernel per layer) and the <false> instantiations are the variants without
+// the riders (PDT_FUSED_WHOLE_FWD / PDT_FC_MERGED / PDT_WGRAD_MERGED = 0); all of them are exercised by tests/test_gpu_kernels.py.
 //
 // All cross-CTA sums are "every CTA writes one partial row, barrier, every CTA folds the rows in the same fixed order",
 // so results are bit-reproducible and identical in every CTA.  The kernels are launched cooperatively (all CTAs
-// co-resident: one per image, at most one per SM).
+// co-resident: one per image, at most one per SM); grid barriers are split into arrive / wait so that independent work
+// (stores nobody in the kernel waits for, cp.async staging, gradient slices) runs in their shadow (grid_sync.cuh).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
