@@ -70,3 +70,39 @@ def test_padded_stats_view_logic():
     exact = torch.ones(2 * C + 1)
     assert _padded_stats(exact) is exact                     # no room behind it
     assert _padded_stats(torch.ones(8)).numel() == 8         # already a multiple of four
+
+
+def test_upcoming_targets_and_rider_contexts_nest_and_restore():
+    """Engine-level announcements (ops.functional): nested contexts restore the outer state; nothing leaks after exit."""
+    import torch
+
+    from pytorch_distributed_train_b200.ops import functional as OF
+
+    a, b = torch.zeros(3, dtype=torch.int64), torch.ones(3, dtype=torch.int64)
+    assert OF._upcoming_target is None and OF._loss_read_after_backward is False and OF._sgd_rider_enabled is False
+    with OF.upcoming_targets(a, loss_read_after_backward=True):
+        assert OF._upcoming_target is a and OF._loss_read_after_backward is True
+        with OF.upcoming_targets(b):
+            assert OF._upcoming_target is b and OF._loss_read_after_backward is False
+        assert OF._upcoming_target is a and OF._loss_read_after_backward is True
+        with OF.sgd_rider_enabled():
+            assert OF._sgd_rider_enabled is True
+        assert OF._sgd_rider_enabled is False
+    assert OF._upcoming_target is None and OF._loss_read_after_backward is False
+
+
+def test_sgd_rider_only_arms_for_the_fused_cuda_convnet():
+    """optim.SGD.ride_on_backward refuses everything but a CUDA fp32 reference ConvNet whose parameters are exactly the optimizer's."""
+    import torch
+
+    import pytorch_distributed_train_b200 as pdt
+    from pytorch_distributed_train_b200.ops import functional as OF
+
+    net = pdt.models.ConvNet()
+    opt = pdt.optim.SGD(net.parameters(), 0.1)
+    assert opt.ride_on_backward(net) is False            # CPU parameters
+    assert opt.ride_on_backward(torch.nn.Linear(4, 4)) is False   # not the ConvNet
+    part = pdt.optim.SGD(list(net.parameters())[:4], 0.1)
+    assert part.ride_on_backward(net) is False           # optimizer does not own every parameter
+    assert OF._sgd_rider is None
+    opt.step()                                           # the ordinary path still runs (no gradients: a no-op)
