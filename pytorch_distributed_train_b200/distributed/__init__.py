@@ -428,6 +428,97 @@ def all_to_all_single(output: torch.Tensor, input: torch.Tensor, group: Optional
     return _finish(g.comm.alltoall(_contig(output, "all_to_all output").view(-1), _contig(input, "all_to_all input").view(-1)), async_op)
 
 
+def all_to_all(output_tensor_list: List[torch.Tensor], input_tensor_list: List[torch.Tensor], group: Optional[ProcessGroup] = None,
+               async_op: bool = False):
+    """List form of the all-to-all (equal-sized chunks): ``input_tensor_list[j]`` goes to rank j, ``output_tensor_list[i]`` comes from
+    rank i (parity: distributed_c10d.py ``all_to_all``).  One flat exchange underneath."""
+    g = _group(group)
+    if len(output_tensor_list) != g.size() or len(input_tensor_list) != g.size():
+        raise ValueError("all_to_all: one input and one output tensor per rank expected")
+    shapes = {tuple(t.shape) for t in input_tensor_list} | {tuple(t.shape) for t in output_tensor_list}
+    if len(shapes) != 1:
+        raise ValueError("all_to_all: only equal-sized chunks are supported")
+    inp = torch.stack([_contig(t, "all_to_all input") for t in input_tensor_list]).view(-1)
+    out = torch.empty_like(inp)
+    work = all_to_all_single(out, inp, group=g, async_op=True)
+
+    def finish():
+        work.wait()
+        for i, t in enumerate(output_tensor_list):
+            t.copy_(out.view(g.size(), *t.shape)[i])
+
+    if async_op:
+        return _Deferred(finish)
+    finish()
+    return None
+
+
+def reduce_scatter(output: torch.Tensor, input_list: List[torch.Tensor], op=ReduceOp.SUM, group: Optional[ProcessGroup] = None,
+                   async_op: bool = False):
+    """List form of reduce-scatter: rank i receives the reduction of every rank's ``input_list[i]``."""
+    g = _group(group)
+    if len(input_list) != g.size():
+        raise ValueError("reduce_scatter: one input tensor per rank expected")
+    flat = torch.stack([_contig(t, "reduce_scatter input") for t in input_list]).view(-1)
+    return reduce_scatter_tensor(output, flat, op=op, group=g, async_op=async_op)
+
+
+class _Deferred:
+    """Work-like handle of an operation with a host-side epilogue (copy-out of a staged result)."""
+
+    def __init__(self, finish):
+        self._finish, self._done = finish, False
+
+    def wait(self, timeout=None):
+        if not self._done:
+            self._finish()
+            self._done = True
+        return True
+
+    def is_completed(self):
+        return self._done
+
+
+def get_process_group_ranks(group: Optional[ProcessGroup] = None) -> List[int]:
+    """Global ranks of the group, in group order (parity: distributed_c10d.py ``get_process_group_ranks``)."""
+    return list(_group(group).ranks)
+
+
+def get_global_rank(group: Optional[ProcessGroup], group_rank: int) -> int:
+    ranks = _group(group).ranks
+    if not 0 <= group_rank < len(ranks):
+        raise ValueError(f"get_global_rank: group rank {group_rank} out of range (group size {len(ranks)})")
+    return ranks[group_rank]
+
+
+def get_group_rank(group: Optional[ProcessGroup], global_rank: int) -> int:
+    return _group_rank(_group(group), global_rank, "get_group_rank")
+
+
+class P2POp:
+    """One point-to-point operation of a batch (parity: distributed_c10d.py ``P2POp``): ``op`` is ``isend`` or ``irecv``."""
+
+    def __init__(self, op, tensor: torch.Tensor, peer: int, group: Optional[ProcessGroup] = None, tag: int = 0):
+        if op not in (isend, irecv):
+            raise ValueError("P2POp: op must be distributed.isend or distributed.irecv")
+        self.op, self.tensor, self.peer, self.group, self.tag = op, tensor, peer, group, tag
+
+
+def batch_isend_irecv(p2p_op_list: List[P2POp]) -> list:
+    """Issue a list of sends / receives and return their work handles (in list order).  Both backends execute a rank's point-to-point
+    operations in issue order (one worker thread / one comm stream) with an eager protocol for messages up to the staging size: a send
+    completes without its receiver, a receive waits for its sender.  Sends are therefore issued first — a ring in which every rank
+    posted its receive first would wait on itself."""
+    if not p2p_op_list or not all(isinstance(o, P2POp) for o in p2p_op_list):
+        raise ValueError("batch_isend_irecv: a non-empty list of P2POp expected")
+    order = sorted(range(len(p2p_op_list)), key=lambda i: 0 if p2p_op_list[i].op is isend else 1)
+    works = [None] * len(p2p_op_list)
+    for i in order:
+        o = p2p_op_list[i]
+        works[i] = o.op(o.tensor, o.peer, o.group)
+    return works
+
+
 def send(tensor: torch.Tensor, dst: int, group: Optional[ProcessGroup] = None):
     g = _group(group)
     g.comm.send(_contig(tensor, "send"), _group_rank(g, dst, "send")).wait()

@@ -214,3 +214,46 @@ def test_object_collectives_and_store_hygiene():
         assert objs == [{"a": 1}, "x", 3.5] and got == f"for-{rank}" and b == {"k": [1, 2]}
         assert gathered == ([("r", 0), ("r", 1)] if rank == 0 else None)
         assert grown <= 2, "object exchanges must clean their keys out of the store"
+
+
+def _list_forms_and_p2p_batches(rank, world):
+    # all_to_all (list form): input j goes to rank j
+    outs = [torch.empty(3) for _ in range(world)]
+    dist.all_to_all(outs, [torch.full((3,), float(10 * rank + j)) for j in range(world)])
+    assert all(torch.equal(outs[i], torch.full((3,), float(10 * i + rank))) for i in range(world))
+    w = dist.all_to_all(outs, [torch.full((3,), float(100 * rank + j)) for j in range(world)], async_op=True)
+    assert w.wait() and w.is_completed()
+    assert all(torch.equal(outs[i], torch.full((3,), float(100 * i + rank))) for i in range(world))
+    # reduce_scatter (list form): rank i gets Σ_r input_list[i] of rank r
+    o = torch.empty(2)
+    dist.reduce_scatter(o, [torch.full((2,), float(rank + 1) * (j + 1)) for j in range(world)])
+    assert torch.equal(o, torch.full((2,), float(sum(range(1, world + 1)) * (rank + 1))))
+    # rank translation on a sub-group with non-trivial ranks
+    g = dist.new_group([1, 2])
+    assert dist.get_process_group_ranks() == list(range(world)) and dist.get_global_rank(None, 1) == 1
+    if g is not None:
+        assert dist.get_process_group_ranks(g) == [1, 2]
+        assert dist.get_group_rank(g, 2) == 1 and dist.get_global_rank(g, 0) == 1
+        try:
+            dist.get_group_rank(g, 0)
+            raise AssertionError("rank 0 is not in the group")
+        except ValueError:
+            pass
+    # a ring exchange as one batch of point-to-point operations: everybody sends right and receives from the left
+    right, left = (rank + 1) % world, (rank - 1) % world
+    got = torch.empty(4)
+    works = dist.batch_isend_irecv([dist.P2POp(dist.isend, torch.full((4,), float(rank)), right), dist.P2POp(dist.irecv, got, left)])
+    for wk in works:
+        wk.wait()
+    assert torch.equal(got, torch.full((4,), float(left)))
+    try:
+        dist.P2POp(dist.send, got, left)
+        raise AssertionError("only isend / irecv are valid batch members")
+    except ValueError:
+        pass
+    dist.barrier()
+    return True
+
+
+def test_list_collectives_rank_translation_and_p2p_batches():
+    assert all(run_ranks(_list_forms_and_p2p_batches, 3))
