@@ -91,6 +91,7 @@ void BatchStager::start(at::Tensor indices) {
   // wait (the device is ~15 steps behind the host) stalled the training thread for 3 ms per epoch (profiles/r2/e2e_stalls.md).
   base_ = consume_;
   produce_ = 0;
+  error_ = nullptr;
   st_fill_us_ = st_wait_free_us_ = st_next_wait_us_ = st_ready_sum_ = st_alloc_us_ = 0;
   st_allocs_ = 0;
   st_next_calls_ = 0;
@@ -105,6 +106,19 @@ void BatchStager::start(at::Tensor indices) {
 }
 
 void BatchStager::worker(int w) {
+  // an exception in a std::thread would terminate the process: park it and let the consumer's next() rethrow it
+  try {
+    worker_loop(w);
+  } catch (...) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      if (!error_) error_ = std::current_exception();
+    }
+    cv_.notify_all();
+  }
+}
+
+void BatchStager::worker_loop(int w) {
 #if PDT_WITH_CUDA
   if (pin_ && device_ >= 0) cudaSetDevice(device_);
 #endif
@@ -246,6 +260,11 @@ bool BatchStager::next(at::Tensor* images, at::Tensor* targets) {
       ~Acc() { dst += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); }
     } acc{st_next_wait_us_, tn0};
     while (s.state != 1) {
+      if (error_) {   // a worker failed (bad index, allocation failure): surface it on the training thread
+        std::exception_ptr e = error_;
+        lk.unlock();
+        std::rethrow_exception(e);
+      }
       // the batch is not staged yet: maybe every slot is waiting for the device — keep reaping while we wait
       const int64_t before = reap_;
       reap_events_locked();

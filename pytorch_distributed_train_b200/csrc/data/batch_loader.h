@@ -18,6 +18,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <exception>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -50,6 +51,7 @@ class BatchStager {
     std::shared_ptr<void> event;   // at::cuda::CUDAEvent recorded when the consumer moved on (opaque here)
   };
   void worker(int w);
+  void worker_loop(int w);
   void alloc_slot(Slot& s);
   void reap_events_locked();   // returned slots whose event has completed become free (consumer thread, mu_ held)
   void stop_worker();
@@ -71,6 +73,7 @@ class BatchStager {
   double st_alloc_us_ = 0;
   int64_t last_handed_ = -1, prev_handed_ = -1;
   bool stop_ = false, running_ = false;
+  std::exception_ptr error_;   // first exception of a worker thread, rethrown by next()
 };
 
 }  // namespace pdt

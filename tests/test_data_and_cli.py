@@ -157,3 +157,23 @@ def test_native_stager_across_epochs_and_abandoned_epochs():
                     break   # abandon this epoch: the batches staged ahead must not leak into the next one
             if epoch != 2:
                 assert sum(got) == want.numel()
+
+
+def test_native_stager_reports_a_worker_failure_on_the_training_thread():
+    """A bad index inside the C++ gather thread must surface as an exception from next(), not abort the process."""
+    import pytest
+    import torch
+
+    from pytorch_distributed_train_b200 import _C
+
+    data = torch.zeros(10, 4, dtype=torch.uint8)
+    st = _C.BatchStager(data, torch.zeros(10, dtype=torch.int64), [4], 2, False, 1.0, 4, False, -1)
+    st.start(torch.tensor([0, 1, 2, 99, 4, 5], dtype=torch.int64))
+    assert st.next() is not None                     # batch (0, 1) is fine
+    with pytest.raises(Exception, match="out of range"):
+        for _ in range(3):
+            st.next()
+    st.start(torch.tensor([3, 4, 5, 6], dtype=torch.int64))   # the stager is usable again after a restart
+    a = st.next()
+    b = st.next()
+    assert a is not None and b is not None and st.next() is None
